@@ -1,0 +1,159 @@
+"""ctypes binding of libfvvdp_b200.so (C ABI: include/fvvdp_b200.h).  No torch types cross this boundary:
+device buffers are passed as integer addresses (tensor.data_ptr()).  There is NO CPU fallback: if the
+library is missing and cannot be built, or no CUDA device exists, the caller gets a RuntimeError."""
+import ctypes as C
+import os
+
+from . import build as _build
+
+ABI_VERSION = 1
+MAX_LEVELS = 16
+MAX_FILTER_LEN = 32
+MAX_BLOCK_FRAMES = 64
+MAX_SLOTS = MAX_BLOCK_FRAMES + MAX_FILTER_LEN
+
+EOTF_CODES = {"none": 0, "sRGB": 1, "gamma": 2, "PQ": 3, "linear": 4, "absolute": 5}
+DTYPE_F32, DTYPE_U8, DTYPE_U16 = 0, 1, 2
+TAP_R, TAP_GAUSS, TAP_CONTRAST, TAP_LBKG, TAP_S, TAP_D, TAP_DMAP_BAND = range(7)
+
+EXPORTS = ["fvvdp_b200_create", "fvvdp_b200_score_block", "fvvdp_b200_heatmap", "fvvdp_b200_read_tap",
+           "fvvdp_b200_level_size", "fvvdp_b200_launch_count", "fvvdp_b200_traffic_model", "fvvdp_b200_destroy",
+           "fvvdp_b200_last_error", "fvvdp_b200_abi_version"]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("n_levels", C.c_int32),
+        ("band_freq", C.c_float * MAX_LEVELS),
+        ("temp_ch", C.c_int32),
+        ("filter_len", C.c_int32),
+        ("filt", (C.c_float * MAX_FILTER_LEN) * 2),
+        ("eotf", C.c_int32),
+        ("Y_peak", C.c_float), ("Y_black", C.c_float), ("gamma", C.c_float), ("L_min", C.c_float), ("L_max", C.c_float),
+        ("rgb2y", C.c_float * 3),
+        ("in_dtype", C.c_int32),
+        ("in_channels", C.c_int32),
+        ("csf_rho_log", C.c_void_p), ("csf_Y_log", C.c_void_p), ("csf_ecc_sqrt", C.c_void_p), ("csf_S_log", C.c_void_p),
+        ("csf_rho_range", C.c_float * 2), ("csf_Y_range", C.c_float * 2), ("csf_ecc_range", C.c_float * 2),
+        ("mask_p", C.c_float), ("mask_q", C.c_float * 2), ("mask_c_mul", C.c_float),
+        ("sens_mul", C.c_float),
+        ("beta", C.c_float),
+        ("w_transient", C.c_float),
+        ("foveated", C.c_int32),
+        ("display_size_m", C.c_float * 2), ("distance_m", C.c_float), ("ppd_centre", C.c_float),
+        ("want_dmap", C.c_int32),
+        ("want_taps", C.c_int32),
+        ("max_block_frames", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def library_path():
+    return _build.LIB
+
+
+def load_library():
+    """dlopen libfvvdp_b200.so (building it first if the sources are newer).  Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if _build.is_stale():
+        path = _build.build_native()
+    if not os.path.isfile(path):
+        raise RuntimeError(f"{path} is missing and could not be built; fovvideovdp_b200 has no CPU fallback")
+    lib = C.CDLL(path)
+    lib.fvvdp_b200_create.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(C.c_void_p)]
+    lib.fvvdp_b200_create.restype = C.c_int
+    lib.fvvdp_b200_score_block.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int,
+                                           C.POINTER(C.c_float), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.fvvdp_b200_score_block.restype = C.c_int
+    lib.fvvdp_b200_heatmap.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    lib.fvvdp_b200_heatmap.restype = C.c_int
+    lib.fvvdp_b200_read_tap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.fvvdp_b200_read_tap.restype = C.c_int64
+    lib.fvvdp_b200_level_size.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.fvvdp_b200_level_size.restype = C.c_int
+    lib.fvvdp_b200_launch_count.argtypes = [C.c_void_p]
+    lib.fvvdp_b200_launch_count.restype = C.c_int64
+    lib.fvvdp_b200_traffic_model.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.fvvdp_b200_traffic_model.restype = C.c_int
+    lib.fvvdp_b200_destroy.argtypes = [C.c_void_p]
+    lib.fvvdp_b200_destroy.restype = C.c_int
+    lib.fvvdp_b200_last_error.argtypes = [C.c_void_p]
+    lib.fvvdp_b200_last_error.restype = C.c_char_p
+    lib.fvvdp_b200_abi_version.argtypes = []
+    lib.fvvdp_b200_abi_version.restype = C.c_int
+    if lib.fvvdp_b200_abi_version() != ABI_VERSION:
+        raise RuntimeError("libfvvdp_b200.so ABI version mismatch; rebuild with python -m fovvideovdp_b200.build")
+    _lib = lib
+    return lib
+
+
+def last_error(handle=None):
+    return load_library().fvvdp_b200_last_error(handle).decode("utf-8", "replace")
+
+
+class Context:
+    """RAII wrapper of fvvdp_b200_ctx."""
+
+    def __init__(self, cfg: Config, device_index: int, keepalive=()):
+        self._lib = load_library()
+        self._keep = keepalive
+        h = C.c_void_p()
+        rc = self._lib.fvvdp_b200_create(C.byref(cfg), int(device_index), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"fvvdp_b200_create failed ({rc}): {last_error(None)}")
+        self.handle = h
+        self.cfg = cfg
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.fvvdp_b200_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise RuntimeError(f"{what} failed ({rc}): {last_error(self.handle)}")
+        return rc
+
+    def score_block(self, test_ptrs, ref_ptrs, strides, n_frames, fixation_xy, q_ptr, q_stride, q_col0, flags_ptr, stream):
+        n = len(test_ptrs)
+        assert n == len(ref_ptrs)
+        tp = (C.c_void_p * n)(*test_ptrs)
+        rp = (C.c_void_p * n)(*ref_ptrs)
+        st = (C.c_int64 * 3)(*[int(s) for s in strides])
+        fx = None
+        if fixation_xy is not None:
+            flat = [float(v) for xy in fixation_xy for v in xy]
+            fx = (C.c_float * len(flat))(*flat)
+        rc = self._lib.fvvdp_b200_score_block(self.handle, tp, rp, st, int(n_frames), fx, C.c_void_p(q_ptr), int(q_stride),
+                                              int(q_col0), C.c_void_p(flags_ptr) if flags_ptr else None, C.c_void_p(stream))
+        self._check(rc, "fvvdp_b200_score_block")
+
+    def heatmap(self, frame, beta_jod, jod_a_abs, out_ptr, stream):
+        self._check(self._lib.fvvdp_b200_heatmap(self.handle, int(frame), float(beta_jod), float(jod_a_abs), C.c_void_p(out_ptr),
+                                                 C.c_void_p(stream)), "fvvdp_b200_heatmap")
+
+    def read_tap(self, tap, level, frame, dst_ptr, capacity, stream):
+        return self._check(self._lib.fvvdp_b200_read_tap(self.handle, int(tap), int(level), int(frame), C.c_void_p(dst_ptr),
+                                                         int(capacity), C.c_void_p(stream)), "fvvdp_b200_read_tap")
+
+    def level_size(self, level):
+        h, w = C.c_int32(), C.c_int32()
+        self._check(self._lib.fvvdp_b200_level_size(self.handle, int(level), C.byref(h), C.byref(w)), "fvvdp_b200_level_size")
+        return h.value, w.value
+
+    def launch_count(self):
+        return int(self._lib.fvvdp_b200_launch_count(self.handle))
+
+    def traffic_model(self):
+        out = (C.c_double * 2)()
+        self._check(self._lib.fvvdp_b200_traffic_model(self.handle, out), "fvvdp_b200_traffic_model")
+        return float(out[0]), float(out[1])

@@ -1,0 +1,444 @@
+// Host side of libfvvdp_b200.so: the C ABI declared in include/fvvdp_b200.h.
+// Everything is enqueued on the caller's stream; no host synchronisation in score_block.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "fvvdp_kernels.cuh"
+
+using namespace fvvdp;
+
+struct fvvdp_b200_ctx {
+  fvvdp_b200_config cfg;
+  int dev = 0;
+  int nch = 4, n_bands = 0, T = 1;
+  int lh[FVVDP_B200_MAX_LEVELS], lw[FVVDP_B200_MAX_LEVELS];
+  int tiles_x[FVVDP_B200_MAX_LEVELS], tiles_y[FVVDP_B200_MAX_LEVELS];
+  float* G[FVVDP_B200_MAX_LEVELS] = {};        // G[0] = R; [T][nch][h_l][w_l]
+  float* partial[FVVDP_B200_MAX_LEVELS] = {};  // [T][2][ntiles_l]
+  float* tapC[FVVDP_B200_MAX_LEVELS] = {};
+  float* tapL[FVVDP_B200_MAX_LEVELS] = {};
+  float* tapS[FVVDP_B200_MAX_LEVELS] = {};
+  float* tapD[FVVDP_B200_MAX_LEVELS] = {};
+  float* dmap[FVVDP_B200_MAX_LEVELS] = {};
+  float* recon[2] = {};                        // ping-pong buffers for the heat-map reconstruction
+  float* axes = nullptr;                       // x[3][32], inv[3][32]
+  float* csf1d = nullptr;                      // [n_bands][2][32]
+  float* lut3d = nullptr;                      // [2][32][32][32]
+  float* vx[FVVDP_B200_MAX_LEVELS] = {};
+  float* vy[FVVDP_B200_MAX_LEVELS] = {};
+  CsfAxes ax;
+  float log2_sens_mul = 0.f;
+  int last_n_frames = 0;
+  int64_t launches = 0;
+  double bytes_alg = 0, bytes_plan = 0;
+  char err[512] = {0};
+};
+
+static char g_create_err[512] = "";
+
+static int fail(fvvdp_b200_ctx* c, int code, const char* fmt, ...) {
+  char* dst = c ? c->err : g_create_err;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+static void locate_host(float q, const float* x, int& j0, int& j1, float& f) {
+  // get_interpolants_v1, interp.py:11-20
+  int j = 0;
+  while (j < 32 && !(x[j] >= q)) ++j;  // bucketize(right=False)
+  if (j > 31) j = 31;
+  j1 = j;
+  j0 = j - 1 < 0 ? 0 : j - 1;
+  f = (q - x[j0]) / (x[j1] - x[j0] + 0.000001f);
+  if (j1 == j0) f = 0.f;
+  if (f < 0.f) f = 0.f;
+}
+
+static void free_ctx(fvvdp_b200_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->dev);
+  for (int l = 0; l < FVVDP_B200_MAX_LEVELS; ++l) {
+    cudaFree(c->G[l]); cudaFree(c->partial[l]); cudaFree(c->tapC[l]); cudaFree(c->tapL[l]);
+    cudaFree(c->tapS[l]); cudaFree(c->tapD[l]); cudaFree(c->dmap[l]); cudaFree(c->vx[l]); cudaFree(c->vy[l]);
+  }
+  cudaFree(c->recon[0]); cudaFree(c->recon[1]);
+  cudaFree(c->axes); cudaFree(c->csf1d); cudaFree(c->lut3d);
+  delete c;
+}
+
+extern "C" int fvvdp_b200_abi_version(void) { return FVVDP_B200_ABI_VERSION; }
+
+extern "C" const char* fvvdp_b200_last_error(const fvvdp_b200_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+
+extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, fvvdp_b200_ctx** out) {
+  fvvdp_b200_ctx* ctx = nullptr;  // errors before allocation go to g_create_err
+  if (!cfg || !out) return fail(ctx, FVVDP_B200_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != FVVDP_B200_ABI_VERSION) return fail(ctx, FVVDP_B200_ERR_INVALID, "ABI version mismatch (%d vs %d)", cfg->abi_version, FVVDP_B200_ABI_VERSION);
+  if (cfg->width < 4 || cfg->height < 4) return fail(ctx, FVVDP_B200_ERR_INVALID, "frame too small (%dx%d)", cfg->width, cfg->height);
+  if (cfg->n_levels < 2 || cfg->n_levels > FVVDP_B200_MAX_LEVELS) return fail(ctx, FVVDP_B200_ERR_INVALID, "n_levels out of range: %d", cfg->n_levels);
+  if (cfg->temp_ch != 1 && cfg->temp_ch != 2) return fail(ctx, FVVDP_B200_ERR_INVALID, "temp_ch must be 1 or 2");
+  if (cfg->filter_len < 1 || cfg->filter_len > FVVDP_B200_MAX_FILTER_LEN) return fail(ctx, FVVDP_B200_ERR_INVALID, "filter_len %d not in 1..%d", cfg->filter_len, FVVDP_B200_MAX_FILTER_LEN);
+  if (cfg->in_channels != 1 && cfg->in_channels != 3) return fail(ctx, FVVDP_B200_ERR_INVALID, "The content must have either 1 or 3 colour channels.");
+  if (cfg->in_dtype < 0 || cfg->in_dtype > 2) return fail(ctx, FVVDP_B200_ERR_INVALID, "Only uint8, uint16 and float32 is currently supported");
+  if (cfg->eotf < 0 || cfg->eotf > 5) return fail(ctx, FVVDP_B200_ERR_INVALID, "Unknown EOTF %d", cfg->eotf);
+  if (cfg->max_block_frames < 1 || cfg->max_block_frames > FVVDP_B200_MAX_BLOCK_FRAMES) return fail(ctx, FVVDP_B200_ERR_INVALID, "max_block_frames %d not in 1..%d", cfg->max_block_frames, FVVDP_B200_MAX_BLOCK_FRAMES);
+  if (!cfg->csf_rho_log || !cfg->csf_Y_log || !cfg->csf_ecc_sqrt || !cfg->csf_S_log) return fail(ctx, FVVDP_B200_ERR_INVALID, "CSF look-up tables missing");
+  {
+    int hh = cfg->height, ww = cfg->width;
+    for (int l = 0; l + 1 < cfg->n_levels; ++l) {  // every scored band needs >= 2 rows and columns
+      if (hh < 2 || ww < 2) return fail(ctx, FVVDP_B200_ERR_INVALID, "too many pyramid levels (%d) for %dx%d", cfg->n_levels, cfg->width, cfg->height);
+      hh = (hh + 1) / 2; ww = (ww + 1) / 2;
+    }
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(ctx, FVVDP_B200_ERR_CUDA, "no CUDA device available (the B200 core has no CPU fallback)");
+  if (cuda_device < 0 || cuda_device >= ndev) return fail(ctx, FVVDP_B200_ERR_INVALID, "cuda_device %d out of range", cuda_device);
+
+  fvvdp_b200_ctx* c = new (std::nothrow) fvvdp_b200_ctx();
+  if (!c) return fail(ctx, FVVDP_B200_ERR_NOMEM, "out of host memory");
+  ctx = c;
+  c->cfg = *cfg;
+  c->cfg.csf_rho_log = c->cfg.csf_Y_log = c->cfg.csf_ecc_sqrt = c->cfg.csf_S_log = nullptr;  // host tables are not retained
+  c->dev = cuda_device;
+  c->nch = 2 * cfg->temp_ch;
+  c->n_bands = cfg->n_levels - 1;
+  c->T = cfg->max_block_frames;
+#define CUC(call)                                                                                     \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) {                                                                          \
+      fail(nullptr, FVVDP_B200_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));                    \
+      free_ctx(c);                                                                                    \
+      return e_ == cudaErrorMemoryAllocation ? FVVDP_B200_ERR_NOMEM : FVVDP_B200_ERR_CUDA;            \
+    }                                                                                                 \
+  } while (0)
+  CUC(cudaSetDevice(cuda_device));
+  const int T = c->T, nch = c->nch;
+  int hh = cfg->height, ww = cfg->width;
+  for (int l = 0; l < cfg->n_levels; ++l) {
+    c->lh[l] = hh; c->lw[l] = ww;
+    c->tiles_x[l] = (ww + TW - 1) / TW; c->tiles_y[l] = (hh + TH - 1) / TH;
+    hh = (hh + 1) / 2; ww = (ww + 1) / 2;
+  }
+  for (int l = 0; l < cfg->n_levels; ++l) {
+    const size_t px = (size_t)c->lh[l] * c->lw[l];
+    // the last Gaussian level (base band) only lives in shared memory of the last band's kernel
+    if (l < c->n_bands) CUC(cudaMalloc(&c->G[l], sizeof(float) * px * nch * T));
+    if (l < c->n_bands) {
+      CUC(cudaMalloc(&c->partial[l], sizeof(float) * (size_t)T * 2 * c->tiles_x[l] * c->tiles_y[l]));
+      if (cfg->want_taps) {
+        CUC(cudaMalloc(&c->tapC[l], sizeof(float) * px * nch * T));
+        CUC(cudaMalloc(&c->tapL[l], sizeof(float) * px * T));
+        CUC(cudaMalloc(&c->tapS[l], sizeof(float) * px * cfg->temp_ch * T));
+        CUC(cudaMalloc(&c->tapD[l], sizeof(float) * px * cfg->temp_ch * T));
+      }
+      if (cfg->want_dmap) CUC(cudaMalloc(&c->dmap[l], sizeof(float) * px * T));
+    }
+  }
+  if (cfg->want_taps) {  // keep the base level readable too
+    const int l = c->n_bands;
+    CUC(cudaMalloc(&c->G[l], sizeof(float) * (size_t)c->lh[l] * c->lw[l] * nch * T));
+  }
+  if (cfg->want_dmap) {
+    CUC(cudaMalloc(&c->recon[0], sizeof(float) * (size_t)cfg->height * cfg->width));
+    CUC(cudaMalloc(&c->recon[1], sizeof(float) * (size_t)cfg->height * cfg->width));
+  }
+
+  // ---- CSF tables ----
+  float hax[6][32];
+  const float* src_ax[3] = {cfg->csf_rho_log, cfg->csf_Y_log, cfg->csf_ecc_sqrt};
+  for (int a = 0; a < 3; ++a) {
+    for (int j = 0; j < 32; ++j) {
+      hax[a][j] = src_ax[a][j];
+      hax[3 + a][j] = (j == 0) ? 0.f : 1.0f / (src_ax[a][j] - src_ax[a][j - 1] + 0.000001f);
+    }
+  }
+  CUC(cudaMalloc(&c->axes, sizeof(hax)));
+  CUC(cudaMemcpy(c->axes, hax, sizeof(hax), cudaMemcpyHostToDevice));
+  for (int a = 0; a < 3; ++a) {
+    c->ax.x[a] = c->axes + a * 32;
+    c->ax.inv[a] = c->axes + (3 + a) * 32;
+    c->ax.x0[a] = src_ax[a][0];
+    c->ax.inv_dx[a] = 31.0f / (src_ax[a][31] - src_ax[a][0]);
+  }
+  c->ax.lo[0] = cfg->csf_rho_range[0]; c->ax.hi[0] = cfg->csf_rho_range[1];
+  c->ax.lo[1] = cfg->csf_Y_range[0];   c->ax.hi[1] = cfg->csf_Y_range[1];
+  c->ax.lo[2] = cfg->csf_ecc_range[0]; c->ax.hi[2] = cfg->csf_ecc_range[1];
+  c->log2_sens_mul = log2f(cfg->sens_mul);
+  CUC(cudaMalloc(&c->lut3d, sizeof(float) * 2 * 32768));
+  CUC(cudaMemcpy(c->lut3d, cfg->csf_S_log, sizeof(float) * 2 * 32768, cudaMemcpyHostToDevice));
+  {
+    // non-foveated: rho and ecc (=0) are constant per band -> 32-entry table over log2 Y per (band, cc)
+    // (cached_sensitivity fvvdp.py:520-537 with rho = rho_band[bb], ecc = 0, fvvdp.py:438-442)
+    std::vector<float> tab((size_t)c->n_bands * 2 * 32);
+    for (int bb = 0; bb < c->n_bands; ++bb) {
+      float rho = fminf(fmaxf(cfg->band_freq[bb], cfg->csf_rho_range[0]), cfg->csf_rho_range[1]);
+      int i0, i1; float fi;
+      locate_host(log2f(rho), cfg->csf_rho_log, i0, i1, fi);
+      for (int cc = 0; cc < 2; ++cc)
+        for (int j = 0; j < 32; ++j) {
+          const float* v = cfg->csf_S_log + (size_t)cc * 32768 + (size_t)j * 1024;
+          tab[((size_t)bb * 2 + cc) * 32 + j] = (v[i0 * 32] * (1.0f - fi) + v[i1 * 32] * fi) + c->log2_sens_mul;
+        }
+    }
+    CUC(cudaMalloc(&c->csf1d, sizeof(float) * tab.size()));
+    CUC(cudaMemcpy(c->csf1d, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice));
+  }
+  if (cfg->foveated) {
+    // pix2view_direction of each band's pixel centres, the band spanning the whole display
+    // (fvvdp.py:422-428, fvvdp_display_model.py:498-510)
+    for (int l = 0; l < c->n_bands; ++l) {
+      std::vector<float> vx(c->lw[l]), vy(c->lh[l]);
+      for (int x = 0; x < c->lw[l]; ++x) {
+        float xr = ((float)x + 0.5f) - (float)(c->lw[l] / 2.0);
+        float xm = xr * cfg->display_size_m[0] / (float)c->lw[l];
+        vx[x] = (float)(atan((double)(xm / cfg->distance_m)) * 180.0 / M_PI);
+      }
+      for (int y = 0; y < c->lh[l]; ++y) {
+        float yr = ((float)y + 0.5f) - (float)(c->lh[l] / 2.0);
+        float ym = -yr * cfg->display_size_m[1] / (float)c->lh[l];
+        vy[y] = (float)(atan((double)(ym / cfg->distance_m)) * 180.0 / M_PI);
+      }
+      CUC(cudaMalloc(&c->vx[l], sizeof(float) * vx.size()));
+      CUC(cudaMalloc(&c->vy[l], sizeof(float) * vy.size()));
+      CUC(cudaMemcpy(c->vx[l], vx.data(), sizeof(float) * vx.size(), cudaMemcpyHostToDevice));
+      CUC(cudaMemcpy(c->vy[l], vy.data(), sizeof(float) * vy.size(), cudaMemcpyHostToDevice));
+    }
+  }
+  CUC(cudaFuncSetAttribute(level_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)level_smem_bytes(4)));
+  CUC(cudaFuncSetAttribute(level_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)level_smem_bytes(4)));
+  CUC(cudaFuncSetAttribute(level_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)level_smem_bytes(2)));
+  CUC(cudaFuncSetAttribute(level_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)level_smem_bytes(2)));
+#undef CUC
+  *out = c;
+  return FVVDP_B200_OK;
+}
+
+extern "C" int fvvdp_b200_destroy(fvvdp_b200_ctx* ctx) {
+  free_ctx(ctx);
+  return FVVDP_B200_OK;
+}
+
+extern "C" int fvvdp_b200_level_size(const fvvdp_b200_ctx* ctx, int level, int32_t* h, int32_t* w) {
+  if (!ctx || level < 0 || level >= ctx->cfg.n_levels) return FVVDP_B200_ERR_INVALID;
+  if (h) *h = ctx->lh[level];
+  if (w) *w = ctx->lw[level];
+  return FVVDP_B200_OK;
+}
+
+extern "C" int64_t fvvdp_b200_launch_count(const fvvdp_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int fvvdp_b200_traffic_model(const fvvdp_b200_ctx* ctx, double out_bytes[2]) {
+  if (!ctx || !out_bytes) return FVVDP_B200_ERR_INVALID;
+  out_bytes[0] = ctx->bytes_alg;
+  out_bytes[1] = ctx->bytes_plan;
+  return FVVDP_B200_OK;
+}
+
+template <int FL, int PX, bool CONTIG>
+static cudaError_t launch_front(const FrontParams& fp, cudaStream_t st) {
+  const long long npx = (long long)fp.H * fp.W;
+  const long long nthreads = (npx + PX - 1) / PX;
+  const unsigned blocks = (unsigned)((nthreads + 255) / 256);
+  front_kernel<FL, PX, CONTIG><<<blocks, 256, 0, st>>>(fp);
+  return cudaGetLastError();
+}
+
+extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* test_slots, const void* const* ref_slots,
+                                      const int64_t strides[3], int n_frames, const float* fixation_xy, float* q_out,
+                                      int64_t q_stride, int64_t q_col0, uint32_t* flags_out, void* cuda_stream) {
+  if (!ctx) return FVVDP_B200_ERR_INVALID;
+  const fvvdp_b200_config& cfg = ctx->cfg;
+  if (!test_slots || !ref_slots || !strides || !q_out) return fail(ctx, FVVDP_B200_ERR_INVALID, "null argument");
+  if (n_frames < 1 || n_frames > ctx->T) return fail(ctx, FVVDP_B200_ERR_INVALID, "n_frames %d not in 1..%d", n_frames, ctx->T);
+  if (q_col0 < 0 || q_col0 + n_frames > q_stride) return fail(ctx, FVVDP_B200_ERR_INVALID, "q_out columns out of range");
+  if (cfg.foveated && !fixation_xy) return fail(ctx, FVVDP_B200_ERR_INVALID, "foveated scoring needs fixation points");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  CU(cudaSetDevice(ctx->dev));
+  const int fl = cfg.filter_len, n_slots = n_frames + fl - 1;
+  const int H = cfg.height, W = cfg.width;
+
+  // ---- K_front ----
+  FrontParams fp;
+  memset(&fp, 0, sizeof(fp));
+  bool aligned = true;
+  for (int s = 0; s < n_slots; ++s) {
+    if (!test_slots[s] || !ref_slots[s]) return fail(ctx, FVVDP_B200_ERR_INVALID, "null frame pointer in slot %d", s);
+    fp.slot[0][s] = test_slots[s];
+    fp.slot[1][s] = ref_slots[s];
+    aligned = aligned && (((uintptr_t)test_slots[s] | (uintptr_t)ref_slots[s]) % 16 == 0);
+  }
+  const int FLT = fl <= 8 ? 8 : (fl <= 16 ? 16 : 32);
+  for (int cc = 0; cc < cfg.temp_ch; ++cc)
+    for (int k = 0; k < FLT; ++k) {
+      const int kk = k - (FLT - fl);  // window position within the real filter, 0 = oldest
+      fp.wgt[cc][k] = kk >= 0 ? cfg.filt[cc][fl - 1 - kk] : 0.0f;  // corr_filter = F.flip(0), fvvdp.py:298
+    }
+  fp.R = ctx->G[0];
+  fp.flags = flags_out;
+  fp.sC = strides[0]; fp.sH = strides[1]; fp.sW = strides[2];
+  fp.H = H; fp.W = W; fp.n_frames = n_frames; fp.fl = fl; fp.nch = ctx->nch; fp.C = cfg.in_channels;
+  fp.dtype = cfg.in_dtype; fp.eotf = cfg.eotf;
+  fp.Yscale = cfg.Y_peak - cfg.Y_black; fp.Y_black = cfg.Y_black; fp.Y_peak = cfg.Y_peak; fp.gamma = cfg.gamma;
+  fp.L_min = cfg.L_min; fp.L_max = cfg.L_max;
+  for (int i = 0; i < 3; ++i) fp.rgb2y[i] = cfg.rgb2y[i];
+  const bool contig = cfg.in_dtype == FVVDP_B200_F32 && cfg.in_channels == 1 && strides[2] == 1 && aligned;
+  cudaError_t le;
+  if (FLT == 8) {
+    if (contig && W % 4 == 0 && strides[1] % 4 == 0) le = launch_front<8, 4, true>(fp, st);
+    else le = launch_front<8, 1, false>(fp, st);
+  } else if (FLT == 16) {
+    if (contig && W % 2 == 0 && strides[1] % 2 == 0) le = launch_front<16, 2, true>(fp, st);
+    else le = launch_front<16, 1, false>(fp, st);
+  } else {
+    if (contig) le = launch_front<32, 1, true>(fp, st);
+    else le = launch_front<32, 1, false>(fp, st);
+  }
+  if (le != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "front_kernel launch: %s", cudaGetErrorString(le));
+  ctx->launches++;
+
+  // ---- K_level per band ----
+  LevelParams lp;  // POD incl. the per-frame gaze table; filled per launch, passed by value
+  for (int l = 0; l < ctx->n_bands; ++l) {
+    memset(&lp, 0, sizeof(lp));
+    lp.G = ctx->G[l];
+    lp.Gn = ctx->G[l + 1];  // nullptr for the base level unless taps are kept
+    lp.partial = ctx->partial[l];
+    lp.h = ctx->lh[l]; lp.w = ctx->lw[l]; lp.h2 = ctx->lh[l + 1]; lp.w2 = ctx->lw[l + 1];
+    // gausspyr_reduce keys the last-column term on the ROW count (fvvdp_lpyr_dec.py:202)
+    const bool h_odd = lp.h & 1, w_odd = lp.w & 1;
+    lp.quirk = (h_odd && !w_odd) ? 1 : ((!h_odd && w_odd) ? 2 : 0);
+    lp.ntiles = ctx->tiles_x[l] * ctx->tiles_y[l];
+    lp.band_mul = (l == 0) ? 1.0f : 2.0f;  // get_band, fvvdp_lpyr_dec.py:57-63 (the base band is never scored)
+    lp.rho_band = cfg.band_freq[l];
+    lp.ax = ctx->ax;
+    lp.csf1d = ctx->csf1d + (size_t)l * 64;
+    lp.lut3d = ctx->lut3d;
+    lp.log2_sens_mul = ctx->log2_sens_mul;
+    lp.mask_p = cfg.mask_p; lp.mask_q[0] = cfg.mask_q[0]; lp.mask_q[1] = cfg.mask_q[1];
+    lp.mask_c_mul = cfg.mask_c_mul; lp.beta = cfg.beta; lp.w_transient = cfg.w_transient;
+    if (cfg.foveated) {
+      lp.vx = ctx->vx[l]; lp.vy = ctx->vy[l];
+      // ppd(a)/ppd_c = (tan(a+d) - tan a)/tan d = cos d / (cos a cos(a+d)), d = half a central pixel
+      const double delta = (1.0 / cfg.ppd_centre) / 2.0 * M_PI / 180.0;
+      lp.res_k0 = (float)cos(delta);
+      lp.res_delta_rad = (float)delta;
+      for (int i = 0; i < n_frames; ++i) {
+        // gaze view direction at frame resolution, fixation + 0.5 (fvvdp.py:429-431)
+        const float gx = fixation_xy[2 * i] + 0.5f, gy = fixation_xy[2 * i + 1] + 0.5f;
+        const float xm = (gx - (float)(W / 2.0)) * cfg.display_size_m[0] / (float)W;
+        const float ym = -(gy - (float)(H / 2.0)) * cfg.display_size_m[1] / (float)H;
+        lp.gaze[i][0] = (float)(atan((double)(xm / cfg.distance_m)) * 180.0 / M_PI);
+        lp.gaze[i][1] = (float)(atan((double)(ym / cfg.distance_m)) * 180.0 / M_PI);
+      }
+    }
+    lp.tapC = ctx->tapC[l]; lp.tapL = ctx->tapL[l]; lp.tapS = ctx->tapS[l]; lp.tapD = ctx->tapD[l];
+    lp.dmap = ctx->dmap[l];
+    dim3 grid(ctx->tiles_x[l], ctx->tiles_y[l], n_frames);
+    const size_t smem = level_smem_bytes(ctx->nch);
+    if (ctx->nch == 4) {
+      if (cfg.foveated) level_kernel<4, true><<<grid, LEVEL_THREADS, smem, st>>>(lp);
+      else level_kernel<4, false><<<grid, LEVEL_THREADS, smem, st>>>(lp);
+    } else {
+      if (cfg.foveated) level_kernel<2, true><<<grid, LEVEL_THREADS, smem, st>>>(lp);
+      else level_kernel<2, false><<<grid, LEVEL_THREADS, smem, st>>>(lp);
+    }
+    le = cudaGetLastError();
+    if (le != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "level_kernel[%d] launch: %s", l, cudaGetErrorString(le));
+    ctx->launches++;
+  }
+
+  // ---- K_final ----
+  FinalParams fin;
+  memset(&fin, 0, sizeof(fin));
+  for (int l = 0; l < ctx->n_bands; ++l) {
+    fin.partial[l] = ctx->partial[l];
+    fin.ntiles[l] = ctx->tiles_x[l] * ctx->tiles_y[l];
+    fin.npix[l] = (double)ctx->lh[l] * ctx->lw[l];
+  }
+  fin.q_out = q_out; fin.q_stride = q_stride; fin.q_col0 = q_col0;
+  fin.n_bands = ctx->n_bands; fin.n_frames = n_frames; fin.temp_ch = cfg.temp_ch;
+  fin.inv_beta = 1.0 / (double)cfg.beta;
+  final_kernel<<<n_frames * ctx->n_bands * 2, 128, 0, st>>>(fin);
+  le = cudaGetLastError();
+  if (le != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "final_kernel launch: %s", cudaGetErrorString(le));
+  ctx->launches++;
+  ctx->last_n_frames = n_frames;
+
+  // traffic model: compulsory input bytes; bytes this kernel plan moves through global memory
+  const double esz = cfg.in_dtype == FVVDP_B200_F32 ? 4.0 : (cfg.in_dtype == FVVDP_B200_U8 ? 1.0 : 2.0);
+  const double P0 = (double)H * W;
+  ctx->bytes_alg = 2.0 * P0 * cfg.in_channels * esz * n_frames;
+  double plan = 2.0 * P0 * cfg.in_channels * esz * n_slots + 4.0 * P0 * ctx->nch * n_frames;
+  for (int l = 0; l < ctx->n_bands; ++l) {
+    plan += 4.0 * ctx->nch * n_frames * (double)ctx->lh[l] * ctx->lw[l];
+    if (l + 1 < ctx->n_bands) plan += 4.0 * ctx->nch * n_frames * (double)ctx->lh[l + 1] * ctx->lw[l + 1];
+  }
+  ctx->bytes_plan = plan;
+  return FVVDP_B200_OK;
+}
+
+extern "C" int64_t fvvdp_b200_read_tap(fvvdp_b200_ctx* ctx, int tap, int level, int frame, float* dst, int64_t cap, void* cuda_stream) {
+  if (!ctx) return FVVDP_B200_ERR_INVALID;
+  if (!dst) return fail(ctx, FVVDP_B200_ERR_INVALID, "null destination");
+  if (frame < 0 || frame >= ctx->last_n_frames) return fail(ctx, FVVDP_B200_ERR_INVALID, "frame %d not in the last block", frame);
+  if (tap == FVVDP_B200_TAP_R) level = 0;
+  if (level < 0 || level >= ctx->cfg.n_levels) return fail(ctx, FVVDP_B200_ERR_INVALID, "level out of range");
+  const size_t px = (size_t)ctx->lh[level] * ctx->lw[level];
+  const float* src = nullptr;
+  size_t n = 0;
+  switch (tap) {
+    case FVVDP_B200_TAP_R:
+    case FVVDP_B200_TAP_GAUSS: src = ctx->G[level]; n = px * ctx->nch; break;
+    case FVVDP_B200_TAP_CONTRAST: src = level < ctx->n_bands ? ctx->tapC[level] : nullptr; n = px * ctx->nch; break;
+    case FVVDP_B200_TAP_LBKG: src = level < ctx->n_bands ? ctx->tapL[level] : nullptr; n = px; break;
+    case FVVDP_B200_TAP_S: src = level < ctx->n_bands ? ctx->tapS[level] : nullptr; n = px * ctx->cfg.temp_ch; break;
+    case FVVDP_B200_TAP_D: src = level < ctx->n_bands ? ctx->tapD[level] : nullptr; n = px * ctx->cfg.temp_ch; break;
+    case FVVDP_B200_TAP_DMAP_BAND: src = level < ctx->n_bands ? ctx->dmap[level] : nullptr; n = px; break;
+    default: return fail(ctx, FVVDP_B200_ERR_INVALID, "unknown tap %d", tap);
+  }
+  if (!src) return fail(ctx, FVVDP_B200_ERR_INVALID, "tap %d level %d not kept (create the ctx with want_taps / want_dmap)", tap, level);
+  if ((int64_t)n > cap) return fail(ctx, FVVDP_B200_ERR_INVALID, "destination too small (%lld < %lld floats)", (long long)cap, (long long)n);
+  CU(cudaSetDevice(ctx->dev));
+  CU(cudaMemcpyAsync(dst, src + (size_t)frame * n, n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream));
+  return (int64_t)n;
+}
+
+extern "C" int fvvdp_b200_heatmap(fvvdp_b200_ctx* ctx, int frame, float beta_jod, float jod_a_abs, void* dmap_out_f16, void* cuda_stream) {
+  if (!ctx) return FVVDP_B200_ERR_INVALID;
+  if (!ctx->cfg.want_dmap) return fail(ctx, FVVDP_B200_ERR_INVALID, "ctx was created without want_dmap");
+  if (!dmap_out_f16) return fail(ctx, FVVDP_B200_ERR_INVALID, "null destination");
+  if (frame < 0 || frame >= ctx->last_n_frames) return fail(ctx, FVVDP_B200_ERR_INVALID, "frame %d not in the last block", frame);
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  CU(cudaSetDevice(ctx->dev));
+  // reconstruct (fvvdp_lpyr_dec.py:94-101) with a zero base band: coarse -> fine, expand + add
+  const float* coarse = nullptr;
+  int ch = 0, cw = 0;
+  for (int l = ctx->n_bands - 1; l >= 0; --l) {
+    const int h = ctx->lh[l], w = ctx->lw[l];
+    const float* band = ctx->dmap[l] + (size_t)frame * h * w;
+    float* out = ctx->recon[l & 1];
+    dim3 grid((w + 31) / 32, (h + 7) / 8);
+    recon_kernel<<<grid, 256, 0, st>>>(coarse, ch, cw, band, out, l == 0 ? (__half*)dmap_out_f16 : nullptr, h, w, beta_jod, jod_a_abs);
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "recon_kernel launch: %s", cudaGetErrorString(le));
+    ctx->launches++;
+    coarse = out; ch = h; cw = w;
+  }
+  return FVVDP_B200_OK;
+}

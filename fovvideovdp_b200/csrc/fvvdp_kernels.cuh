@@ -1,0 +1,494 @@
+// Device kernels of the B200-native FovVideoVDP core (sm_100a).  See DESIGN.md for the data layout and
+// the roofline of each kernel.  Reference semantics are cited per function (pyfvvdp file:line).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "../../include/fvvdp_b200.h"
+
+namespace fvvdp {
+
+// ------------------------------------------------------------------------------------------------
+// small math helpers (MUFU based: lg2.approx / ex2.approx / rcp.approx)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_log2(float x) { return __log2f(x); }
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_pow(float x, float p) { return fast_exp2(p * fast_log2(x)); }
+__device__ __forceinline__ float fast_rcp(float x) { return __frcp_rn(x); }
+
+// ------------------------------------------------------------------------------------------------
+// K_front: display EOTF -> luminance, sliding temporal window, sustained + transient FIR
+//   reference: video_source.py:180-208 (_get_frame), fvvdp_display_model.py:147-165 (EOTF),
+//              fvvdp.py:258-300 (window + FIR), channel order [T_sust, R_sust, T_trans, R_trans]
+// ------------------------------------------------------------------------------------------------
+struct FrontParams {
+  const void* slot[2][FVVDP_B200_MAX_SLOTS];  // [test|ref][window slot] frame base pointers (device)
+  float wgt[2][FVVDP_B200_MAX_FILTER_LEN];    // [channel][window position], position 0 = OLDEST frame
+  float* R;                                   // [n_frames][nch][H][W]
+  uint32_t* flags;
+  long long sC, sH, sW;                       // element strides of the input frames
+  int H, W, n_frames, fl, nch, C, dtype, eotf;
+  float Yscale, Y_black, Y_peak, gamma, L_min, L_max;
+  float rgb2y[3];
+};
+
+__device__ __forceinline__ float eotf_apply(float v, const FrontParams& p, bool& oor) {
+  switch (p.eotf) {
+    case FVVDP_B200_EOTF_NONE:
+      return v;
+    case FVVDP_B200_EOTF_ABSOLUTE:  // fvvdp_display_model.py:206
+      return fminf(fmaxf(v, p.L_min), p.L_max);
+    case FVVDP_B200_EOTF_LINEAR:    // :163
+      return fminf(fmaxf(v, 0.005f), p.Y_peak) + p.Y_black;
+    default:
+      break;
+  }
+  oor |= (v > 1.0f) | (v < 0.0f);   // :149-151 (warn + clamp)
+  v = fminf(fmaxf(v, 0.0f), 1.0f);
+  if (p.eotf == FVVDP_B200_EOTF_SRGB) {  // :17-19
+    float lin = (v > 0.04045f) ? fast_pow((v + 0.055f) / 1.055f, 2.4f) : v / 12.92f;
+    return p.Yscale * lin + p.Y_black;
+  } else if (p.eotf == FVVDP_B200_EOTF_GAMMA) {
+    return p.Yscale * fast_pow(v, p.gamma) + p.Y_black;
+  } else {  // PQ :100-112,161
+    const float n_inv = 1.0f / 0.15930175781250000f, m_inv = 1.0f / 78.843750000000000f;
+    const float c1 = 0.83593750000000000f, c2 = 18.851562500000000f, c3 = 18.687500000000000f;
+    float t = fast_pow(v, m_inv);
+    float L = 10000.0f * fast_pow(fmaxf(t - c1, 0.0f) / (c2 - c3 * t), n_inv);
+    return fminf(fmaxf(L, 0.005f), p.Y_peak) + p.Y_black;
+  }
+}
+
+__device__ __forceinline__ float load_sample(const void* base, long long off, int dtype) {
+  if (dtype == FVVDP_B200_F32) return __ldg(reinterpret_cast<const float*>(base) + off);
+  if (dtype == FVVDP_B200_U8) return static_cast<float>(__ldg(reinterpret_cast<const uint8_t*>(base) + off)) / 255.0f;
+  int v = static_cast<int>(__ldg(reinterpret_cast<const int16_t*>(base) + off)) & 0xFFFF;  // video_source.py:186-196
+  return static_cast<float>(v) / 65535.0f;
+}
+
+// luminance of PX consecutive pixels of one frame
+template <int PX, bool CONTIG>
+__device__ __forceinline__ void load_lum(const FrontParams& p, const void* base, int y, int x, float (&out)[PX], bool& oor) {
+  if (CONTIG) {  // float32, 1 channel, unit column stride, 16-byte aligned rows
+    const float* src = reinterpret_cast<const float*>(base) + (long long)y * p.sH + x;
+    if (PX == 4) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(src));
+      out[0] = v.x; out[1 % PX] = v.y; out[2 % PX] = v.z; out[3 % PX] = v.w;
+    } else if (PX == 2) {
+      float2 v = __ldg(reinterpret_cast<const float2*>(src));
+      out[0] = v.x; out[1 % PX] = v.y;
+    } else {
+      out[0] = __ldg(src);
+    }
+#pragma unroll
+    for (int i = 0; i < PX; ++i) out[i] = eotf_apply(out[i], p, oor);
+  } else {
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+      long long off = (long long)y * p.sH + (long long)(x + i) * p.sW;
+      if (p.C == 3) {
+        float r = eotf_apply(load_sample(base, off, p.dtype), p, oor);
+        float g = eotf_apply(load_sample(base, off + p.sC, p.dtype), p, oor);
+        float b = eotf_apply(load_sample(base, off + 2 * p.sC, p.dtype), p, oor);
+        out[i] = r * p.rgb2y[0] + g * p.rgb2y[1] + b * p.rgb2y[2];  // video_source.py:206
+      } else {
+        out[i] = eotf_apply(load_sample(base, off, p.dtype), p, oor);
+      }
+    }
+  }
+}
+
+template <int PX>
+__device__ __forceinline__ void store_px(float* dst, const float (&v)[PX]) {
+  if (PX == 4) {
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1 % PX], v[2 % PX], v[3 % PX]);
+  } else if (PX == 2) {
+    *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1 % PX]);
+  } else {
+    dst[0] = v[0];
+  }
+}
+
+// One thread owns PX consecutive pixels and walks the frames of the block keeping the last FL luminance
+// samples of both streams in a register ring (position of slot s is (s + FL - fl) % FL, all indices static
+// after unrolling).  Every input sample is read from HBM once per block and EOTF'd once.
+template <int FL, int PX, bool CONTIG>
+__global__ void __launch_bounds__(256) front_kernel(const __grid_constant__ FrontParams p) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long npx = (long long)p.H * p.W;
+  const long long pix = gid * PX;
+  if (pix >= npx) return;
+  const int y = (int)(pix / p.W), x = (int)(pix % p.W);
+  const int o = FL - p.fl;  // leading window positions that do not exist (weights are zero there)
+  float win[2][FL][PX];
+  bool oor = false;
+#pragma unroll
+  for (int k = 0; k < FL; ++k)
+#pragma unroll
+    for (int i = 0; i < PX; ++i) win[0][k][i] = win[1][k][i] = 0.0f;
+  // pre-load window positions 0..FL-2 of output frame 0
+#pragma unroll
+  for (int k = 0; k < FL - 1; ++k) {
+    const int s = k - o;
+    if (s >= 0) {
+      load_lum<PX, CONTIG>(p, p.slot[0][s], y, x, win[0][k], oor);
+      load_lum<PX, CONTIG>(p, p.slot[1][s], y, x, win[1][k], oor);
+    }
+  }
+  const long long plane = npx;
+  for (int i0 = 0; i0 < p.n_frames; i0 += FL) {
+#pragma unroll
+    for (int j = 0; j < FL; ++j) {
+      const int i = i0 + j;
+      if (i < p.n_frames) {
+        // newest frame of output i: window position FL-1 -> ring position (j + FL - 1) % FL, slot i + fl - 1
+        const int rp = (j + FL - 1) % FL;
+        load_lum<PX, CONTIG>(p, p.slot[0][i + p.fl - 1], y, x, win[0][rp], oor);
+        load_lum<PX, CONTIG>(p, p.slot[1][i + p.fl - 1], y, x, win[1][rp], oor);
+        float* dst = p.R + ((long long)i * p.nch) * plane + pix;
+        const int ncc = p.nch >> 1;
+        for (int cc = 0; cc < ncc; ++cc) {
+          float at[PX], ar[PX];
+#pragma unroll
+          for (int e = 0; e < PX; ++e) at[e] = ar[e] = 0.0f;
+#pragma unroll
+          for (int k = 0; k < FL; ++k) {
+            const float w = p.wgt[cc][k];
+#pragma unroll
+            for (int e = 0; e < PX; ++e) {
+              at[e] = fmaf(win[0][(j + k) % FL][e], w, at[e]);
+              ar[e] = fmaf(win[1][(j + k) % FL][e], w, ar[e]);
+            }
+          }
+          store_px<PX>(dst + (cc * 2 + 0) * plane, at);
+          store_px<PX>(dst + (cc * 2 + 1) * plane, ar);
+        }
+      }
+    }
+  }
+  if (oor && p.flags) atomicOr(p.flags, 1u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_level: one pyramid level, fully fused
+//   gausspyr_reduce (fvvdp_lpyr_dec.py:183-207) -> G_{l+1} tile (+1 halo) in shared memory (+ written out)
+//   gausspyr_expand (:219-235,126-142), band = G_l - E, L_bkg = max(E[ref_sust],0.1), contrast (:259-269)
+//   CSF look-up (fvvdp.py:520-537, interp.py:11-59), masking (:574-596), sum of D^beta (:467,598-607)
+// ------------------------------------------------------------------------------------------------
+constexpr int TH = 32, TW = 64, HALO = 4;
+constexpr int SGH = TH + 2 * HALO, SGW = TW + 2 * HALO;  // G_l tile with halo: 40 x 72
+constexpr int NH = TH / 2 + 2, NW = TW / 2 + 2;          // G_{l+1} tile with 1-px halo: 18 x 34
+constexpr int LEVEL_THREADS = 256;
+
+struct CsfAxes {           // device pointers, 32 entries each
+  const float* x[3];       // 0: rho_log, 1: Y_log, 2: ecc_sqrt
+  const float* inv[3];     // 1 / (x[j] - x[j-1] + 1e-6), inv[0] unused
+  float x0[3], inv_dx[3];  // uniform-grid first guess
+  float lo[3], hi[3];      // clamp range in linear units
+};
+
+struct LevelParams {
+  const float* G;     // [F][NCH][h][w]
+  float* Gn;          // [F][NCH][h2][w2] or nullptr for the last band
+  float* partial;     // [F][2][ntiles]
+  int h, w, h2, w2, quirk, ntiles;
+  float band_mul;
+  float rho_band;
+  // CSF
+  CsfAxes ax;
+  const float* csf1d;  // [2][32] pre-blended log2(S * sens_mul) over log2 Y for this band (non-foveated)
+  const float* lut3d;  // [2][32(Y)][32(rho)][32(ecc)] log2 S
+  float log2_sens_mul;
+  // masking
+  float mask_p, mask_q[2], mask_c_mul, beta, w_transient;
+  // foveation
+  const float* vx;     // [w] horizontal view direction of the band's pixel columns (deg)
+  const float* vy;     // [h]
+  float res_k0, res_delta_rad;  // res_mag = res_k0 / (cos(a) cos(a+delta))
+  float gaze[FVVDP_B200_MAX_BLOCK_FRAMES][2];
+  // optional outputs
+  float* tapC;  // [F][NCH][h][w]
+  float* tapL;  // [F][h][w]
+  float* tapS;  // [F][TC][h][w]
+  float* tapD;  // [F][TC][h][w]
+  float* dmap;  // [F][h][w]
+};
+
+__device__ __forceinline__ int mirror_idx(int i, int n) {
+  if (i < 0) i = -1 - i;
+  if (i >= n) i = 2 * n - 1 - i;
+  return min(max(i, 0), n - 1);
+}
+
+// bucketize + fraction exactly as get_interpolants_v1 (interp.py:11-20): j1 = first index with x[j1] >= q
+__device__ __forceinline__ void locate(float q, const float* __restrict__ x, const float* __restrict__ inv, float x0, float inv_dx,
+                                       int& j0, int& j1, float& f) {
+  int j = (int)ceilf((q - x0) * inv_dx);
+  j = min(max(j, 0), 31);
+  if (j > 0 && x[j - 1] >= q) --j;
+  else if (j < 31 && x[j] < q) ++j;
+  j1 = j;
+  j0 = max(j - 1, 0);
+  f = (j1 == j0) ? 0.0f : fmaxf((q - x[j0]) * inv[j1], 0.0f);
+}
+
+template <int NCH, bool FOV>
+__global__ void __launch_bounds__(LEVEL_THREADS) level_kernel(const __grid_constant__ LevelParams p) {
+  constexpr int TC = NCH / 2;
+  extern __shared__ float smem[];
+  float* sG = smem;                        // [NCH][SGH][SGW]
+  float* sV = sG + NCH * SGH * SGW;        // [NCH][NH][SGW]
+  float* sN = sV + NCH * NH * SGW;         // [NCH][NH][NW]
+  float* sAx = sN + NCH * NH * NW;         // Y_log[32], invY[32], tab[2][32]
+  __shared__ float sRed[2][LEVEL_THREADS / 32];
+
+  const int tid = threadIdx.x;
+  const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+  const int f = blockIdx.z;
+  const int h = p.h, w = p.w, h2 = p.h2, w2 = p.w2;
+  const int jx0 = tx0 >> 1, jy0 = ty0 >> 1;
+  const long long plane = (long long)h * w;
+  const float* Gf = p.G + (long long)f * NCH * plane;
+
+  if (tid < 32) {
+    sAx[tid] = p.ax.x[1][tid];
+    sAx[32 + tid] = p.ax.inv[1][tid];
+    if (!FOV) {
+      sAx[64 + tid] = p.csf1d[tid];
+      sAx[96 + tid] = p.csf1d[32 + tid];
+    }
+  }
+
+  // ---- stage the G_l tile (mirror-extended at the image border) ----
+  const bool interior = (ty0 - HALO >= 0) && (ty0 + TH + HALO <= h) && (tx0 - HALO >= 0) && (tx0 + TW + HALO <= w) && ((w & 3) == 0);
+  if (interior) {
+    constexpr int V4 = SGW / 4;
+    for (int idx = tid; idx < NCH * SGH * V4; idx += LEVEL_THREADS) {
+      const int c4 = idx % V4, r = (idx / V4) % SGH, ch = idx / (V4 * SGH);
+      const float4 v = __ldg(reinterpret_cast<const float4*>(Gf + ch * plane + (long long)(ty0 - HALO + r) * w + (tx0 - HALO)) + c4);
+      *reinterpret_cast<float4*>(sG + (ch * SGH + r) * SGW + c4 * 4) = v;
+    }
+  } else {
+    for (int idx = tid; idx < NCH * SGH * SGW; idx += LEVEL_THREADS) {
+      const int c = idx % SGW, r = (idx / SGW) % SGH, ch = idx / (SGW * SGH);
+      const int gy = mirror_idx(ty0 - HALO + r, h), gx = mirror_idx(tx0 - HALO + c, w);
+      sG[idx] = __ldg(Gf + ch * plane + (long long)gy * w + gx);
+    }
+  }
+  __syncthreads();
+
+  const float K0 = 0.05f, K1 = 0.25f, K2 = 0.4f, K3 = 0.25f, K4 = 0.05f;
+  // ---- reduce, rows: sV[ch][a][c] = sum_k K[k] G[2j-2+k][c], j = clamp(jy0-1+a) ----
+  for (int idx = tid; idx < NCH * NH * SGW; idx += LEVEL_THREADS) {
+    const int c = idx % SGW, a = (idx / SGW) % NH, ch = idx / (SGW * NH);
+    const int jc = min(max(jy0 - 1 + a, 0), h2 - 1);
+    const float* g = sG + (ch * SGH + 2 * (jc - jy0) + 2) * SGW + c;
+    sV[idx] = K0 * g[0] + K1 * g[SGW] + K2 * g[2 * SGW] + K3 * g[3 * SGW] + K4 * g[4 * SGW];
+  }
+  __syncthreads();
+  // ---- reduce, columns (with the reference's row-parity quirk on the last column, fvvdp_lpyr_dec.py:202) ----
+  for (int idx = tid; idx < NCH * NH * NW; idx += LEVEL_THREADS) {
+    const int b = idx % NW, a = (idx / NW) % NH, ch = idx / (NW * NH);
+    const int ic = min(max(jx0 - 1 + b, 0), w2 - 1);
+    const float* v = sV + (ch * NH + a) * SGW + 2 * (ic - jx0) + 2;
+    float o;
+    if (p.quirk != 0 && ic == w2 - 1) {
+      if (p.quirk == 1) o = (K0 * v[0] + K1 * v[1] + K2 * v[2] + K3 * v[3]) + (v[3] * K3 + v[2] * K4);  // W even, H odd
+      else              o = (K0 * v[0] + K1 * v[1] + K2 * v[2]) + v[2] * K4;                            // W odd, H even
+    } else {
+      o = K0 * v[0] + K1 * v[1] + K2 * v[2] + K3 * v[3] + K4 * v[4];
+    }
+    sN[idx] = o;
+    if (p.Gn != nullptr && a >= 1 && a <= TH / 2 && b >= 1 && b <= TW / 2) {
+      const int j = jy0 - 1 + a, i = jx0 - 1 + b;
+      if (j < h2 && i < w2) p.Gn[((long long)(f * NCH + ch) * h2 + j) * w2 + i] = o;
+    }
+  }
+  __syncthreads();
+
+  // ---- expand + contrast + CSF + masking + pooling; one thread per 2x2 output quad ----
+  float acc[2] = {0.0f, 0.0f};
+  const float* sY = sAx;
+  const float* sYinv = sAx + 32;
+  const float log2_dmax = 13.287712379549449f;  // log2(1e4), clamp of fvvdp.py:595
+  for (int q = tid; q < (TH / 2) * (TW / 2); q += LEVEL_THREADS) {
+    const int qa = q / (TW / 2), qb = q % (TW / 2);
+    const int y0 = ty0 + 2 * qa, x0 = tx0 + 2 * qb;
+    if (y0 >= h || x0 >= w) continue;
+    float E[NCH][2][2];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const float* n = sN + (ch * NH + qa) * NW + qb;
+      float ve[3], vo[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float n0 = n[c], n1 = n[NW + c], n2 = n[2 * NW + c];
+        ve[c] = 0.1f * n0 + 0.8f * n1 + 0.1f * n2;  // even row: taps 2K[0],2K[2],2K[4]
+        vo[c] = 0.5f * n1 + 0.5f * n2;              // odd row:  taps 2K[1],2K[3]
+      }
+      E[ch][0][0] = 0.1f * ve[0] + 0.8f * ve[1] + 0.1f * ve[2];
+      E[ch][0][1] = 0.5f * ve[1] + 0.5f * ve[2];
+      E[ch][1][0] = 0.1f * vo[0] + 0.8f * vo[1] + 0.1f * vo[2];
+      E[ch][1][1] = 0.5f * vo[1] + 0.5f * vo[2];
+    }
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int y = y0 + dy, x = x0 + dx;
+        if (y >= h || x >= w) continue;
+        const float Lb = fmaxf(E[1][dy][dx], 0.1f);
+        const float invL = fast_rcp(Lb);
+        float C[NCH];
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          const float g = sG[(ch * SGH + 2 * qa + dy + HALO) * SGW + 2 * qb + dx + HALO];
+          C[ch] = fminf((g - E[ch][dy][dx]) * invL, 1000.0f) * p.band_mul;
+        }
+        const long long pofs = (long long)y * w + x;
+        // CSF query along Y (shared by both temporal channels)
+        const float yq = fast_log2(fminf(fmaxf(Lb, p.ax.lo[1]), p.ax.hi[1]));
+        int j0, j1;
+        float fj;
+        locate(yq, sY, sYinv, p.ax.x0[1], p.ax.inv_dx[1], j0, j1, fj);
+        int i0 = 0, i1 = 0, k0 = 0, k1 = 0;
+        float fi = 0.0f, fk = 0.0f;
+        if (FOV) {
+          const float vx = __ldg(p.vx + x), vy = __ldg(p.vy + y);
+          const float ex = vx - p.gaze[f][0], ey = vy - p.gaze[f][1];
+          const float ecc = sqrtf(ex * ex + ey * ey);
+          const float va = fminf(sqrtf(vx * vx + vy * vy), 89.9f) * 0.017453292519943295f;
+          const float res_mag = p.res_k0 / (__cosf(va) * __cosf(va + p.res_delta_rad));
+          const float rq = fast_log2(fminf(fmaxf(p.rho_band * res_mag, p.ax.lo[0]), p.ax.hi[0]));
+          const float eq = sqrtf(fminf(fmaxf(ecc, p.ax.lo[2]), p.ax.hi[2]));
+          locate(rq, p.ax.x[0], p.ax.inv[0], p.ax.x0[0], p.ax.inv_dx[0], i0, i1, fi);
+          locate(eq, p.ax.x[2], p.ax.inv[2], p.ax.x0[2], p.ax.inv_dx[2], k0, k1, fk);
+        }
+        float Dsum = 0.0f;
+#pragma unroll
+        for (int cc = 0; cc < TC; ++cc) {
+          float ls;
+          if (FOV) {
+            const float* v = p.lut3d + cc * 32768;
+            const float a00 = __ldg(v + (j0 * 32 + i0) * 32 + k0), a01 = __ldg(v + (j0 * 32 + i1) * 32 + k0);
+            const float a10 = __ldg(v + (j1 * 32 + i0) * 32 + k0), a11 = __ldg(v + (j1 * 32 + i1) * 32 + k0);
+            const float b00 = __ldg(v + (j0 * 32 + i0) * 32 + k1), b01 = __ldg(v + (j0 * 32 + i1) * 32 + k1);
+            const float b10 = __ldg(v + (j1 * 32 + i0) * 32 + k1), b11 = __ldg(v + (j1 * 32 + i1) * 32 + k1);
+            const float lo = (a00 * (1.0f - fi) + a01 * fi) * (1.0f - fj) + (a10 * (1.0f - fi) + a11 * fi) * fj;
+            const float hi = (b00 * (1.0f - fi) + b01 * fi) * (1.0f - fj) + (b10 * (1.0f - fi) + b11 * fi) * fj;
+            ls = lo * (1.0f - fk) + hi * fk + p.log2_sens_mul;
+          } else {
+            const float* tab = sAx + 64 + cc * 32;
+            ls = tab[j0] * (1.0f - fj) + tab[j1] * fj;
+          }
+          const float S = fast_exp2(ls);
+          const float Tn = C[cc * 2 + 0] * S, Rn = C[cc * 2 + 1] * S;
+          const float d = fabsf(Tn - Rn);
+          const float M = fminf(fabsf(Tn), fabsf(Rn)) * p.mask_c_mul;
+          const float Mq = fast_exp2(p.mask_q[cc] * fast_log2(M));
+          float lD = p.mask_p * fast_log2(d) - fast_log2(1.0f + Mq);
+          lD = fminf(lD, log2_dmax);
+          acc[cc] += fast_exp2(p.beta * lD);
+          if (p.tapS) p.tapS[((long long)(f * TC + cc)) * plane + pofs] = S;
+          if (p.tapD || p.dmap) {
+            const float D = fast_exp2(lD);
+            if (p.tapD) p.tapD[((long long)(f * TC + cc)) * plane + pofs] = D;
+            Dsum += (cc == 0 ? 1.0f : p.w_transient) * D;
+          }
+        }
+        if (p.dmap) p.dmap[(long long)f * plane + pofs] = Dsum / p.band_mul;
+        if (p.tapL) p.tapL[(long long)f * plane + pofs] = Lb;
+        if (p.tapC) {
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) p.tapC[((long long)(f * NCH + ch)) * plane + pofs] = C[ch];
+        }
+      }
+    }
+  }
+  // ---- block reduction of sum D^beta (warp shuffles, then one partial per tile: deterministic) ----
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    float v = acc[cc];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) sRed[cc][tid >> 5] = v;
+  }
+  __syncthreads();
+  if (tid < 2) {
+    float v = 0.0f;
+#pragma unroll
+    for (int i = 0; i < LEVEL_THREADS / 32; ++i) v += sRed[tid][i];
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    p.partial[((long long)f * 2 + tid) * p.ntiles + tile] = v;
+  }
+}
+
+constexpr size_t level_smem_bytes(int nch) { return sizeof(float) * (size_t)(nch * SGH * SGW + nch * NH * SGW + nch * NH * NW + 128); }
+
+// ------------------------------------------------------------------------------------------------
+// K_final: Q[bb,cc,f] = (sum_tiles partial / Npix)^(1/beta)      (lp_norm, fvvdp.py:598-607)
+// ------------------------------------------------------------------------------------------------
+struct FinalParams {
+  const float* partial[FVVDP_B200_MAX_LEVELS];
+  int ntiles[FVVDP_B200_MAX_LEVELS];
+  double npix[FVVDP_B200_MAX_LEVELS];
+  float* q_out;
+  long long q_stride, q_col0;
+  int n_bands, n_frames, temp_ch;
+  double inv_beta;
+};
+
+__global__ void __launch_bounds__(128) final_kernel(const __grid_constant__ FinalParams p) {
+  const int cc = blockIdx.x & 1, bb = (blockIdx.x >> 1) % p.n_bands, f = (blockIdx.x >> 1) / p.n_bands;
+  __shared__ double sd[4];
+  double s = 0.0;
+  if (cc < p.temp_ch) {
+    const float* src = p.partial[bb] + ((long long)f * 2 + cc) * p.ntiles[bb];
+    for (int i = threadIdx.x; i < p.ntiles[bb]; i += 128) s += (double)src[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sd[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double t = sd[0] + sd[1] + sd[2] + sd[3];
+    const double q = (cc < p.temp_ch) ? pow(t / p.npix[bb], p.inv_beta) : 0.0;
+    p.q_out[((long long)bb * 2 + cc) * p.q_stride + p.q_col0 + f] = (float)q;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_recon: heat-map pyramid reconstruction  img_l = expand(img_{l+1}) + band_l   (fvvdp_lpyr_dec.py:94-101)
+// and final |jod_a| * img^beta_jod -> fp16 (fvvdp.py:470-473)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) recon_kernel(const float* __restrict__ coarse, int h2, int w2, const float* __restrict__ band,
+                                                    float* __restrict__ out, __half* __restrict__ out16, int h, int w, float beta_jod,
+                                                    float jod_a_abs) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= w || y >= h) return;
+  float e = 0.0f;
+  if (coarse != nullptr) {
+    // expand: rows first, then columns; z[m] = x[clamp(m/2-1)] on even m (see oracle/_expand_axis)
+    float col[3];
+    const int cx = x >> 1, cy = y >> 1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int xi = min(max(cx - 1 + c, 0), w2 - 1);
+      const float n0 = coarse[(long long)min(max(cy - 1, 0), h2 - 1) * w2 + xi];
+      const float n1 = coarse[(long long)min(cy, h2 - 1) * w2 + xi];
+      const float n2 = coarse[(long long)min(cy + 1, h2 - 1) * w2 + xi];
+      col[c] = (y & 1) ? (0.5f * n1 + 0.5f * n2) : (0.1f * n0 + 0.8f * n1 + 0.1f * n2);
+    }
+    e = (x & 1) ? (0.5f * col[1] + 0.5f * col[2]) : (0.1f * col[0] + 0.8f * col[1] + 0.1f * col[2]);
+  }
+  const float v = e + band[(long long)y * w + x];
+  if (out16 != nullptr) out16[(long long)y * w + x] = __float2half(powf(v, beta_jod) * jod_a_abs);
+  else out[(long long)y * w + x] = v;
+}
+
+}  // namespace fvvdp
