@@ -18,7 +18,9 @@ TAP_R, TAP_GAUSS, TAP_CONTRAST, TAP_LBKG, TAP_S, TAP_D, TAP_DMAP_BAND = range(7)
 
 EXPORTS = ["fvvdp_b200_create", "fvvdp_b200_score_block", "fvvdp_b200_heatmap", "fvvdp_b200_read_tap",
            "fvvdp_b200_level_size", "fvvdp_b200_launch_count", "fvvdp_b200_traffic_model", "fvvdp_b200_destroy",
-           "fvvdp_b200_last_error", "fvvdp_b200_abi_version"]
+           "fvvdp_b200_last_error", "fvvdp_b200_abi_version", "fvvdp_b200_pool_jod",
+           "fvvdp_b200_profile", "fvvdp_b200_profile_read"]
+PROFILE_CLASSES = MAX_LEVELS + 2
 
 
 class Config(C.Structure):
@@ -47,6 +49,11 @@ class Config(C.Structure):
         ("want_taps", C.c_int32),
         ("max_block_frames", C.c_int32),
     ]
+
+
+class PoolParams(C.Structure):
+    _fields_ = [("beta_sch", C.c_float), ("beta_tch", C.c_float), ("beta_t", C.c_float), ("w_transient", C.c_float),
+                ("jod_a", C.c_float), ("log_jod_exp", C.c_float)]
 
 
 _lib = None
@@ -88,6 +95,12 @@ def load_library():
     lib.fvvdp_b200_last_error.restype = C.c_char_p
     lib.fvvdp_b200_abi_version.argtypes = []
     lib.fvvdp_b200_abi_version.restype = C.c_int
+    lib.fvvdp_b200_profile.argtypes = [C.c_void_p, C.c_int]
+    lib.fvvdp_b200_profile.restype = C.c_int
+    lib.fvvdp_b200_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+    lib.fvvdp_b200_profile_read.restype = C.c_int
+    lib.fvvdp_b200_pool_jod.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.POINTER(PoolParams), C.c_int, C.c_void_p, C.c_void_p]
+    lib.fvvdp_b200_pool_jod.restype = C.c_int
     if lib.fvvdp_b200_abi_version() != ABI_VERSION:
         raise RuntimeError("libfvvdp_b200.so ABI version mismatch; rebuild with python -m fovvideovdp_b200.build")
     _lib = lib
@@ -150,6 +163,17 @@ class Context:
         self._check(self._lib.fvvdp_b200_level_size(self.handle, int(level), C.byref(h), C.byref(w)), "fvvdp_b200_level_size")
         return h.value, w.value
 
+    def profile(self, enable):
+        self._check(self._lib.fvvdp_b200_profile(self.handle, 1 if enable else 0), "fvvdp_b200_profile")
+
+    def profile_read(self):
+        """{class name: (milliseconds, launches)} since the last read; classes 'front', 'level0'.., 'final'."""
+        ms = (C.c_float * PROFILE_CLASSES)()
+        cnt = (C.c_int32 * PROFILE_CLASSES)()
+        self._check(self._lib.fvvdp_b200_profile_read(self.handle, ms, cnt), "fvvdp_b200_profile_read")
+        names = ["front"] + [f"level{l}" for l in range(MAX_LEVELS)] + ["final"]
+        return {names[i]: (float(ms[i]), int(cnt[i])) for i in range(PROFILE_CLASSES) if cnt[i] > 0}
+
     def launch_count(self):
         return int(self._lib.fvvdp_b200_launch_count(self.handle))
 
@@ -157,3 +181,12 @@ class Context:
         out = (C.c_double * 2)()
         self._check(self._lib.fvvdp_b200_traffic_model(self.handle, out), "fvvdp_b200_traffic_model")
         return float(out[0]), float(out[1])
+
+
+def pool_jod(q_ptr, n_bands, n_frames, q_stride, params: PoolParams, device_index, out_ptr, stream):
+    """do_pooling_and_jods on the device: out[0] = JOD, out[1] = pooled Q."""
+    lib = load_library()
+    rc = lib.fvvdp_b200_pool_jod(C.c_void_p(q_ptr), int(n_bands), int(n_frames), int(q_stride), C.byref(params), int(device_index),
+                                 C.c_void_p(out_ptr), C.c_void_p(stream))
+    if rc != 0:
+        raise RuntimeError(f"fvvdp_b200_pool_jod failed ({rc}): {last_error(None)}")

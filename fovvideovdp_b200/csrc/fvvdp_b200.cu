@@ -35,6 +35,10 @@ struct fvvdp_b200_ctx {
   float log2_sens_mul = 0.f;
   int last_n_frames = 0;
   int64_t launches = 0;
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev;  // pairs (start, stop)
+  std::vector<int> ev_class;
+  size_t ev_used = 0;
   double bytes_alg = 0, bytes_plan = 0;
   char err[512] = {0};
 };
@@ -77,6 +81,7 @@ static void free_ctx(fvvdp_b200_ctx* c) {
   }
   cudaFree(c->recon[0]); cudaFree(c->recon[1]);
   cudaFree(c->axes); cudaFree(c->csf1d); cudaFree(c->lut3d);
+  for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   delete c;
 }
 
@@ -250,6 +255,48 @@ extern "C" int fvvdp_b200_traffic_model(const fvvdp_b200_ctx* ctx, double out_by
   return FVVDP_B200_OK;
 }
 
+// RAII bracket: records a start event now and a stop event when it goes out of scope (profiling only)
+struct ProfScope {
+  fvvdp_b200_ctx* c;
+  cudaStream_t st;
+  cudaEvent_t stop = nullptr;
+  ProfScope(fvvdp_b200_ctx* c_, int cls, cudaStream_t st_) : c(c_), st(st_) {
+    if (!c->profiling) return;
+    if (c->ev_used * 2 >= c->ev.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+      c->ev.push_back(a); c->ev.push_back(b); c->ev_class.push_back(cls);
+    }
+    c->ev_class[c->ev_used] = cls;
+    cudaEventRecord(c->ev[2 * c->ev_used], st);
+    stop = c->ev[2 * c->ev_used + 1];
+    c->ev_used++;
+  }
+  ~ProfScope() { if (stop) cudaEventRecord(stop, st); }
+};
+
+extern "C" int fvvdp_b200_profile(fvvdp_b200_ctx* ctx, int enable) {
+  if (!ctx) return FVVDP_B200_ERR_INVALID;
+  ctx->profiling = enable != 0;
+  ctx->ev_used = 0;
+  return FVVDP_B200_OK;
+}
+
+extern "C" int fvvdp_b200_profile_read(fvvdp_b200_ctx* ctx, float* ms, int32_t* count) {
+  if (!ctx || !ms || !count) return FVVDP_B200_ERR_INVALID;
+  for (int i = 0; i < FVVDP_B200_PROFILE_CLASSES; ++i) { ms[i] = 0.f; count[i] = 0; }
+  CU(cudaSetDevice(ctx->dev));
+  if (ctx->ev_used > 0) CU(cudaEventSynchronize(ctx->ev[2 * ctx->ev_used - 1]));
+  for (size_t i = 0; i < ctx->ev_used; ++i) {
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, ctx->ev[2 * i], ctx->ev[2 * i + 1]));
+    ms[ctx->ev_class[i]] += t;
+    count[ctx->ev_class[i]]++;
+  }
+  ctx->ev_used = 0;
+  return FVVDP_B200_OK;
+}
+
 template <int FL, int PX, bool CONTIG>
 static cudaError_t launch_front(const FrontParams& fp, cudaStream_t st) {
   const long long npx = (long long)fp.H * fp.W;
@@ -299,6 +346,8 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
   for (int i = 0; i < 3; ++i) fp.rgb2y[i] = cfg.rgb2y[i];
   const bool contig = cfg.in_dtype == FVVDP_B200_F32 && cfg.in_channels == 1 && strides[2] == 1 && aligned;
   cudaError_t le;
+  {
+  ProfScope prof(ctx, 0, st);
   if (FLT == 8) {
     if (contig && W % 4 == 0 && strides[1] % 4 == 0) le = launch_front<8, 4, true>(fp, st);
     else le = launch_front<8, 1, false>(fp, st);
@@ -308,6 +357,7 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
   } else {
     if (contig) le = launch_front<32, 1, true>(fp, st);
     else le = launch_front<32, 1, false>(fp, st);
+  }
   }
   if (le != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "front_kernel launch: %s", cudaGetErrorString(le));
   ctx->launches++;
@@ -351,6 +401,7 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
     lp.dmap = ctx->dmap[l];
     dim3 grid(ctx->tiles_x[l], ctx->tiles_y[l], n_frames);
     const size_t smem = level_smem_bytes(ctx->nch);
+    ProfScope prof(ctx, 1 + l, st);
     if (ctx->nch == 4) {
       if (cfg.foveated) level_kernel<4, true><<<grid, LEVEL_THREADS, smem, st>>>(lp);
       else level_kernel<4, false><<<grid, LEVEL_THREADS, smem, st>>>(lp);
@@ -374,7 +425,10 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
   fin.q_out = q_out; fin.q_stride = q_stride; fin.q_col0 = q_col0;
   fin.n_bands = ctx->n_bands; fin.n_frames = n_frames; fin.temp_ch = cfg.temp_ch;
   fin.inv_beta = 1.0 / (double)cfg.beta;
-  final_kernel<<<n_frames * ctx->n_bands * 2, 128, 0, st>>>(fin);
+  {
+    ProfScope prof(ctx, FVVDP_B200_MAX_LEVELS + 1, st);
+    final_kernel<<<n_frames * ctx->n_bands * 2, 128, 0, st>>>(fin);
+  }
   le = cudaGetLastError();
   if (le != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "final_kernel launch: %s", cudaGetErrorString(le));
   ctx->launches++;
@@ -440,5 +494,17 @@ extern "C" int fvvdp_b200_heatmap(fvvdp_b200_ctx* ctx, int frame, float beta_jod
     ctx->launches++;
     coarse = out; ch = h; cw = w;
   }
+  return FVVDP_B200_OK;
+}
+
+extern "C" int fvvdp_b200_pool_jod(const float* q, int n_bands, int64_t n_frames, int64_t q_stride, const fvvdp_b200_pool_params* params,
+                                   int cuda_device, float* jod_out, void* cuda_stream) {
+  fvvdp_b200_ctx* ctx = nullptr;  // ctx-free: errors are reported through fvvdp_b200_last_error(NULL)
+  if (!q || !params || !jod_out) return fail(ctx, FVVDP_B200_ERR_INVALID, "null argument");
+  if (n_bands < 1 || n_bands >= FVVDP_B200_MAX_LEVELS || n_frames < 1 || q_stride < n_frames) return fail(ctx, FVVDP_B200_ERR_INVALID, "bad q_per_ch shape");
+  CU(cudaSetDevice(cuda_device));
+  pool_kernel<<<1, 256, 0, (cudaStream_t)cuda_stream>>>(q, n_bands, (long long)n_frames, (long long)q_stride, *params, jod_out);
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "pool_kernel launch: %s", cudaGetErrorString(le));
   return FVVDP_B200_OK;
 }

@@ -463,6 +463,47 @@ __global__ void __launch_bounds__(128) final_kernel(const __grid_constant__ Fina
 }
 
 // ------------------------------------------------------------------------------------------------
+// K_pool: do_pooling_and_jods (fvvdp.py:337-357).  One block; fp64 accumulation (a few thousand terms).
+//   Q_sc[cc,f] = (sum_bb |w_cc Q[bb,cc,f]|^b_sch)^(1/b_sch);  Q_tc[f] = (sum_cc Q_sc^b_tch)^(1/b_tch)
+//   Q = (sum_f Q_tc^b_t / N)^(1/b_t);  JOD = 10 + sign(a) (|a|^(1/b) Q)^b,  b = 10^log_jod_exp
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ q, int n_bands, long long n_frames, long long q_stride,
+                                                   const fvvdp_b200_pool_params p, float* __restrict__ out) {
+  __shared__ double sd[8];
+  double acc = 0.0;
+  for (long long f = threadIdx.x; f < n_frames; f += 256) {
+    double tc = 0.0;
+    for (int cc = 0; cc < 2; ++cc) {
+      const double w = cc == 0 ? 1.0 : (double)p.w_transient;
+      double sc = 0.0;
+      for (int bb = 0; bb < n_bands; ++bb) {
+        const double v = fabs((double)(q[((long long)bb * 2 + cc) * q_stride + f] * (float)w));
+        sc += (p.beta_sch == 1.0f) ? v : pow(v, (double)p.beta_sch);
+      }
+      if (p.beta_sch != 1.0f) sc = pow(sc, 1.0 / (double)p.beta_sch);
+      tc += sc > 0.0 ? pow(sc, (double)p.beta_tch) : 0.0;
+    }
+    tc = tc > 0.0 ? pow(tc, 1.0 / (double)p.beta_tch) : 0.0;
+    acc += (p.beta_t == 1.0f) ? tc : pow(tc, (double)p.beta_t);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sd[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += sd[i];
+    double Q = t / (double)n_frames;
+    if (p.beta_t != 1.0f) Q = pow(Q, 1.0 / (double)p.beta_t);
+    const double b = pow(10.0, (double)p.log_jod_exp);
+    const double a = (double)p.jod_a;
+    const double sgn = a < 0.0 ? -1.0 : 1.0;
+    out[0] = (float)(sgn * pow(pow(fabs(a), 1.0 / b) * Q, b) + 10.0);
+    out[1] = (float)Q;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K_recon: heat-map pyramid reconstruction  img_l = expand(img_{l+1}) + band_l   (fvvdp_lpyr_dec.py:94-101)
 // and final |jod_a| * img^beta_jod -> fp16 (fvvdp.py:470-473)
 // ------------------------------------------------------------------------------------------------

@@ -1,0 +1,448 @@
+"""The FovVideoVDP metric object, B200-native.
+
+Public surface = the reference's `pyfvvdp.fvvdp` class (pyfvvdp/fvvdp.py:58-665): constructor arguments,
+predict(), predict_video_source(), set_display_model(), update_device(), load_config(), get_info_string(),
+short_name(), quality_unit(), write_features_to_json(), and the `stats` dictionary.  What differs is what
+happens inside predict_video_source(): instead of ~7k tensor ops per frame (fvvdp.py:246-311,359-478) the
+frames are scored in blocks by the hand-written sm_100a kernels of libfvvdp_b200.so (C ABI in
+include/fvvdp_b200.h), called through ctypes with raw device pointers.
+
+There is no CPU fallback: constructing the metric without a CUDA device, or with device='cpu', raises.
+The metric is inference-only (`use_checkpoints` is accepted for signature compatibility and ignored).
+"""
+import ctypes
+import json
+import logging
+import math
+
+import numpy as np
+import torch
+
+from . import _native, config
+from .display_model import (fvvdp_display_geometry, fvvdp_display_photometry, geometry_is_stock, photometry_kernel_spec)
+from .video_source import fvvdp_video_source_array, is_array_source
+
+_DTYPES = {torch.float32: _native.DTYPE_F32, torch.uint8: _native.DTYPE_U8, torch.int16: _native.DTYPE_U16}
+_WORKSPACE_BUDGET_BYTES = 16e9  # device memory a scoring context may take for its per-block pyramids
+
+
+def pyramid_layout(width, height, ppd):
+    """Number of Gaussian levels and the band centre frequencies [cpd] for a W x H frame seen at `ppd`
+    pixels per degree (fvvdp_lpyr_dec.__init__, fvvdp_lpyr_dec.py:15-49).  Returns (n_levels, freqs) with
+    len(freqs) == n_levels; the last entry belongs to the base band, which is never scored."""
+    most = int(math.floor(math.log2(min(height, width)))) - 1
+    # band k>=1 peaks at 0.3228 * 2^-(k-1) of the Nyquist frequency ppd/2; band 0 sits at Nyquist
+    peak = [1.0] + [0.3228 * 2.0 ** (-k) for k in range(14)]
+    n_bands = most
+    for k, rel in enumerate(peak):
+        if rel * ppd / 2.0 <= 0.5:  # bands at or below 0.5 cpd are folded into the base band
+            n_bands = k
+            break
+    n_bands = max(0, min(n_bands + 1, most))
+    freqs = np.array(peak[:n_bands + 1], dtype=np.float64) * ppd / 2.0
+    return n_bands + 1, freqs
+
+
+def temporal_filters(frames_per_second, filter_len, sigma, beta):
+    """Sustained / transient temporal impulse responses sampled at the frame times, float32 (2, filter_len)
+    (get_temporal_filters, fvvdp.py:609-630).  Tap 0 weighs the newest frame."""
+    f32 = np.float32
+    t = np.linspace(0.0, filter_len / frames_per_second, filter_len).astype(f32)
+    lg = np.log(t + f32(1e-4)) - np.log(f32(beta))
+    sust = np.exp(-(lg * lg) / f32(2.0 * sigma * sigma)).astype(f32)
+    sust = sust / sust.sum(dtype=f32)
+    trans = np.zeros(filter_len, f32)
+    if filter_len > 1:
+        trans[:-1] = f32(0.062170507756932) * (np.diff(sust) / (t[1] - t[0]))
+    return np.stack([sust, trans]).astype(f32)
+
+
+def initial_window(n_frames, filter_len, temp_padding):
+    """Frame indices that fill the temporal window when frame 0 is scored, oldest first (fvvdp.py:258-285)."""
+    fl = filter_len
+    if temp_padding == "replicate":
+        return [0] * fl
+    if temp_padding == "circular":
+        return [(n_frames - 1 - fl + k) % n_frames for k in range(fl)]
+    if temp_padding == "pingpong":
+        there_and_back = list(range(n_frames)) + list(range(n_frames - 2, 0, -1))
+        seq = []
+        while len(seq) < fl - 1:
+            seq = seq + there_and_back
+        return (seq[-(fl - 1):] if fl > 1 else []) + [0]
+    raise RuntimeError('Unknown padding method "{}"'.format(temp_padding))
+
+
+def frame_block(n_frames, rank, world_size):
+    """Contiguous block of frames [begin, end) scored by `rank` when a clip is sharded over `world_size`
+    processes."""
+    return (rank * n_frames) // world_size, ((rank + 1) * n_frames) // world_size
+
+
+class _FrameSet:
+    """Resolves frame index -> (test pointer, reference pointer) on the device for one clip.
+
+    Three kinds of source:
+      * array source already on the metric's device: pointers into the user's tensors, nothing is copied;
+      * array source in host memory: frames are uploaded (raw dtype, original memory layout) into a small pool
+        of device buffers as blocks need them;
+      * any other fvvdp_video_source: get_test_frame()/get_reference_frame() supply float32 luminance frames.
+    """
+
+    def __init__(self, vid_source, device, raw):
+        self.vs = vid_source
+        self.device = device
+        self.raw = raw
+        self.held = {}      # frame index -> (test tensor, ref tensor) on the device
+        self.free = []      # recycled upload buffers
+        self.h2d_bytes = 0
+        if raw:
+            tv, rv = vid_source.test_video, vid_source.reference_video
+            if tv.shape[0] != 1:
+                raise RuntimeError("Batches of more than one clip are not supported (the reference is limited to B=1 as well)")
+            if tv.dtype != rv.dtype or tv.dtype not in _DTYPES:
+                raise RuntimeError("Only uint8, uint16 and float32 is currently supported")
+            self.dtype = tv.dtype
+            self.resident = tv.device == device and rv.device == device
+            self.same_layout = tv.stride() == rv.stride()
+            v = tv[0, :, 0]
+            if self.resident and self.same_layout:
+                self.strides = tuple(v.stride())
+            else:
+                self._order = sorted(range(3), key=lambda d: -v.stride(d))
+                vp = v.permute(self._order)
+                if not (vp.is_contiguous() and self.same_layout):
+                    self._order = [0, 1, 2]
+                    vp = v
+                self._buf_shape = tuple(vp.shape)
+                inv = [self._order.index(d) for d in range(3)]
+                self._inv = inv
+                self.strides = tuple(torch.empty(self._buf_shape, dtype=self.dtype, device="meta").permute(inv).stride())
+                self.resident = False
+        else:
+            self.dtype = torch.float32
+            self.strides = None
+
+    def _upload(self, src):
+        buf = self.free.pop() if self.free else torch.empty(self._buf_shape, dtype=self.dtype, device=self.device)
+        buf.copy_(src.permute(self._order), non_blocking=True)
+        self.h2d_bytes += buf.numel() * buf.element_size()
+        return buf
+
+    def fetch(self, idx):
+        if idx in self.held:
+            return
+        if self.raw:
+            tv, rv = self.vs.test_video, self.vs.reference_video
+            k = self.vs.local_index(idx) if hasattr(self.vs, "local_index") else idx
+            if self.resident:
+                self.held[idx] = (tv[0, :, k], rv[0, :, k])
+            else:
+                self.held[idx] = (self._upload(tv[0, :, k]), self._upload(rv[0, :, k]))
+        else:
+            t = self.vs.get_test_frame(idx, device=self.device)
+            r = self.vs.get_reference_frame(idx, device=self.device)
+            t = t.to(device=self.device, dtype=torch.float32).reshape(t.shape[-2], t.shape[-1]).contiguous()
+            r = r.to(device=self.device, dtype=torch.float32).reshape(r.shape[-2], r.shape[-1]).contiguous()
+            self.held[idx] = (t, r)
+            if self.strides is None:
+                self.strides = (0, t.stride(0), t.stride(1))
+
+    def pointers(self, idx):
+        t, r = self.held[idx]
+        return t.data_ptr(), r.data_ptr()
+
+    def retain_only(self, keep):
+        for idx in [k for k in self.held if k not in keep]:
+            t, r = self.held.pop(idx)
+            if self.raw and not self.resident:
+                self.free.extend((t, r))
+
+
+class fvvdp:
+    def __init__(self, display_name="standard_4k", display_photometry=None, display_geometry=None, color_space="sRGB", foveated=False,
+                 heatmap=None, quiet=False, device=None, temp_padding="replicate", use_checkpoints=False, block_frames=None,
+                 shard_frames=False):
+        assert heatmap in [None, "none", "raw", "threshold", "supra-threshold"], "Unsupported heatmap type"
+        assert temp_padding in ["replicate", "circular", "pingpong"], "Unsupported temporal padding method"
+        self.quiet = quiet
+        self.foveated = foveated
+        self.heatmap = heatmap
+        self.color_space = color_space
+        self.temp_padding = temp_padding
+        self.use_checkpoints = use_checkpoints
+        self.do_heatmap = heatmap is not None and heatmap != "none"
+        self.block_frames = block_frames
+        self.shard_frames = shard_frames
+        self.debug_taps = False           # tests: keep intermediate tensors of the last block readable
+        self._ctx = None
+        self._ctx_key = None
+        self.last_run = {}                # launch / traffic counters of the last predict call (bench.py)
+
+        if device is None:
+            if not (torch.cuda.is_available() and torch.cuda.device_count() > 0):
+                raise RuntimeError("fovvideovdp_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+            device = torch.device("cuda:0")
+        self.update_device(device, _reload=False)
+        _native.load_library()  # fail now, loudly, if the CUDA library is missing
+        self.set_display_model(display_name, display_photometry=display_photometry, display_geometry=display_geometry)
+        self.load_config()
+        self.lut = config.csf_lut()
+
+    # ------------------------------------------------------------------ configuration
+    def update_device(self, device, _reload=True):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError(f"fovvideovdp_b200 runs on CUDA devices only (got '{device}'); there is no CPU fallback")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = device
+        self._drop_ctx()
+
+    def load_config(self):
+        p = config.parameters()
+        self.parameters_file = config.config_files.find("fvvdp_parameters.json") or "<packaged>"
+        for k in ("mask_p", "mask_c", "pu_dilate", "w_transient", "beta", "beta_t", "beta_tch", "beta_sch", "sustained_sigma",
+                  "sustained_beta", "csf_sigma", "sensitivity_correction", "masking_model", "local_adapt", "contrast", "jod_a",
+                  "log_jod_exp", "mask_q_sust", "mask_q_trans", "k_cm", "filter_len", "version"):
+            setattr(self, k, p[k])
+        # the kernels implement the shipped calibration's model structure
+        if self.local_adapt != "gpyr" or self.contrast != "weber" or self.masking_model != "min_mutual_masking_perc_norm2" or self.pu_dilate != 0:
+            raise RuntimeError("Unsupported metric configuration: the B200 core implements local_adapt='gpyr', contrast='weber', "
+                               "masking_model='min_mutual_masking_perc_norm2', pu_dilate=0")
+        self._drop_ctx()
+
+    def set_display_model(self, display_name="standard_4k", display_photometry=None, display_geometry=None):
+        if display_photometry is None:
+            self.display_photometry = fvvdp_display_photometry.load(display_name)
+            self.display_name = display_name
+        else:
+            self.display_photometry = display_photometry
+            self.display_name = "unspecified"
+        self.display_geometry = fvvdp_display_geometry.load(display_name) if display_geometry is None else display_geometry
+        self.pix_per_deg = self.display_geometry.get_ppd()
+        self._drop_ctx()
+
+    def _drop_ctx(self):
+        if getattr(self, "_ctx", None) is not None:
+            self._ctx.close()
+        self._ctx = None
+        self._ctx_key = None
+
+    # ------------------------------------------------------------------ prediction
+    def predict(self, test_cont, reference_cont, dim_order="BCFHW", frames_per_second=0, fixation_point=None):
+        vs = fvvdp_video_source_array(test_cont, reference_cont, frames_per_second, dim_order=dim_order,
+                                      display_photometry=self.display_photometry, color_space_name=self.color_space)
+        return self.predict_video_source(vs, fixation_point=fixation_point)
+
+    def _context(self, key, build_cfg):
+        if self._ctx is None or self._ctx_key != key:
+            self._drop_ctx()
+            cfg, keep = build_cfg()
+            self._ctx = _native.Context(cfg, self.device.index, keepalive=keep)
+            self._ctx_key = key
+        return self._ctx
+
+    def _make_config(self, W, H, n_levels, freqs, temp_ch, fl, F, spec, dtype, C, T):
+        cfg = _native.Config()
+        cfg.abi_version = _native.ABI_VERSION
+        cfg.width, cfg.height, cfg.n_levels = W, H, n_levels
+        for i, f in enumerate(freqs):
+            cfg.band_freq[i] = float(f)
+        cfg.temp_ch, cfg.filter_len = temp_ch, fl
+        for cc in range(F.shape[0]):
+            for k in range(fl):
+                cfg.filt[cc][k] = float(F[cc, k])
+        cfg.eotf = _native.EOTF_CODES[spec["kind"]]
+        cfg.Y_peak = spec.get("Y_peak", 0.0)
+        cfg.Y_black = spec.get("Y_black", 0.0)
+        cfg.gamma = spec.get("gamma", 2.2)
+        cfg.L_min = spec.get("L_min", 0.0)
+        cfg.L_max = spec.get("L_max", 0.0)
+        w = config.rgb2y(self.color_space) if C == 3 else [1.0, 0.0, 0.0]
+        for i in range(3):
+            cfg.rgb2y[i] = w[i]
+        cfg.in_dtype, cfg.in_channels = _DTYPES[dtype], C
+        lut = self.lut
+        keep = [np.ascontiguousarray(lut[k], np.float32) for k in ("rho_log", "Y_log", "ecc_sqrt", "S_log")]
+        cfg.csf_rho_log, cfg.csf_Y_log, cfg.csf_ecc_sqrt, cfg.csf_S_log = [a.ctypes.data_as(ctypes.c_void_p) for a in keep]
+        for name, dst in (("rho", cfg.csf_rho_range), ("Y", cfg.csf_Y_range), ("ecc", cfg.csf_ecc_range)):
+            dst[0], dst[1] = float(lut[name][0]), float(lut[name][-1])
+        cfg.mask_p = self.mask_p
+        cfg.mask_q[0], cfg.mask_q[1] = self.mask_q_sust, self.mask_q_trans
+        cfg.mask_c_mul = 10.0 ** self.mask_c
+        cfg.sens_mul = 10.0 ** (self.sensitivity_correction / 20.0)
+        cfg.beta = self.beta
+        cfg.w_transient = self.w_transient
+        cfg.foveated = 1 if self.foveated else 0
+        geo = self.display_geometry
+        if self.foveated:
+            cfg.display_size_m[0], cfg.display_size_m[1] = float(geo.display_size_m[0]), float(geo.display_size_m[1])
+            cfg.distance_m = float(geo.distance_m)
+        cfg.ppd_centre = float(self.pix_per_deg)
+        cfg.want_dmap = 1 if self.do_heatmap else 0
+        cfg.want_taps = 1 if self.debug_taps else 0
+        cfg.max_block_frames = T
+        return cfg, keep
+
+    def predict_video_source(self, vid_source, fixation_point=None):
+        height, width, N_frames = vid_source.get_video_size()
+        height, width, N_frames = int(height), int(width), int(N_frames)
+        dev = self.device
+        is_image = N_frames == 1
+        fps = vid_source.get_frames_per_second()
+
+        if fixation_point is None:
+            fixation_point = np.array([width // 2, height // 2], dtype=np.float32)
+        elif torch.is_tensor(fixation_point):
+            fixation_point = fixation_point.detach().cpu().numpy()
+        fixation_point = np.asarray(fixation_point, dtype=np.float32)
+
+        n_levels, freqs = pyramid_layout(width, height, self.pix_per_deg)
+        n_bands = n_levels - 1
+        if n_bands < 1:
+            raise RuntimeError(f"Frames of {width}x{height} are too small to build a contrast pyramid")
+        if is_image:
+            temp_ch, fl = 1, 1
+            F = np.ones((1, 1), np.float32)
+        else:
+            temp_ch = 2
+            fl = int(math.ceil(250.0 / (1000.0 / fps)))
+            self.filter_len = fl
+            if fl > _native.MAX_FILTER_LEN:
+                raise RuntimeError(f"frame rate {fps} needs {fl} filter taps; at most {_native.MAX_FILTER_LEN} are supported")
+            F = temporal_filters(fps, fl, self.sustained_sigma, self.sustained_beta)
+            self.F = torch.from_numpy(F)
+
+        if self.foveated and not geometry_is_stock(self.display_geometry):
+            raise NotImplementedError("foveated scoring with a custom fvvdp_display_geometry subclass is not implemented yet")
+        if self.do_heatmap and self.heatmap != "raw":
+            raise NotImplementedError(f"heatmap='{self.heatmap}' is not implemented yet (use 'raw')")
+
+        # how the frames reach the kernels
+        spec = None
+        if is_array_source(vid_source):
+            spec = photometry_kernel_spec(vid_source.dm_photometry)
+        raw = spec is not None
+        frames = _FrameSet(vid_source, dev, raw)
+        if raw:
+            C = 3 if vid_source.is_color else 1
+            dtype = frames.dtype
+        else:
+            spec, C, dtype = dict(kind="none"), 1, torch.float32
+
+        # frames this process scores
+        f_begin, f_end = 0, N_frames
+        world = 1
+        if self.shard_frames and torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size()
+            if world > 1 and N_frames >= world:
+                f_begin, f_end = frame_block(N_frames, torch.distributed.get_rank(), world)
+            else:
+                world = 1  # replicas only: every rank scores the whole (short) clip
+
+        per_frame_bytes = 4.0 * (2 * temp_ch) * height * width * 4.0 / 3.0 * (3.0 if self.debug_taps else 1.0)
+        T = self.block_frames or int(max(1, min(_native.MAX_BLOCK_FRAMES, _WORKSPACE_BUDGET_BYTES // per_frame_bytes)))
+        T = max(1, min(T, _native.MAX_BLOCK_FRAMES, f_end - f_begin))
+
+        geo = self.display_geometry
+        key = (width, height, n_levels, tuple(float(f) for f in freqs), temp_ch, fl, F.tobytes(), tuple(sorted(spec.items())), dtype, C, T,
+               self.foveated, self.do_heatmap, self.debug_taps, self.color_space,
+               (tuple(geo.display_size_m), geo.distance_m) if self.foveated else None)
+        ctx = self._context(key, lambda: self._make_config(width, height, n_levels, freqs, temp_ch, fl, F, spec, dtype, C, T))
+
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        Q_per_ch = torch.zeros((n_bands, 2, N_frames), dtype=torch.float32, device=dev)
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        heatmap = None
+        if self.do_heatmap:
+            heatmap = torch.zeros([1, 1, N_frames, height, width], dtype=torch.float16, device="cpu")
+            hm_dev = torch.empty((height, width), dtype=torch.float16, device=dev)
+        first = initial_window(N_frames, fl, self.temp_padding) if not is_image else [0]
+
+        def frame_at(t):  # frame shown at time t (t <= 0 falls into the temporal padding)
+            return t if t >= 1 else first[fl - 1 + t]
+
+        launches0 = ctx.launch_count()
+        with torch.cuda.device(dev):
+            for f0 in range(f_begin, f_end, T):
+                n = min(T, f_end - f0)
+                slots = [frame_at(f0 - (fl - 1) + s) for s in range(n + fl - 1)]
+                for idx in slots:
+                    frames.fetch(idx)
+                ptrs = [frames.pointers(idx) for idx in slots]
+                fix = None
+                if self.foveated:
+                    fix = [fixation_point[f0 + i] if fixation_point.ndim == 2 else fixation_point for i in range(n)]
+                ctx.score_block([p[0] for p in ptrs], [p[1] for p in ptrs], frames.strides, n, fix, Q_per_ch.data_ptr(), N_frames, f0,
+                                flags.data_ptr(), stream)
+                if self.do_heatmap:
+                    beta_jod = 10.0 ** self.log_jod_exp
+                    for i in range(n):
+                        ctx.heatmap(i, beta_jod, abs(self.jod_a), hm_dev.data_ptr(), stream)
+                        heatmap[0, 0, f0 + i].copy_(hm_dev)
+                nxt = f0 + n
+                keep = set(frame_at(nxt - (fl - 1) + s) for s in range(fl - 1)) if nxt < f_end else set()
+                frames.retain_only(keep)
+            if world > 1:
+                torch.distributed.all_reduce(Q_per_ch)  # every column has exactly one non-zero contributor
+            out = torch.empty(2, dtype=torch.float32, device=dev)
+            pp = _native.PoolParams(self.beta_sch, self.beta_tch, self.beta_t, self.w_transient, self.jod_a, self.log_jod_exp)
+            _native.pool_jod(Q_per_ch.data_ptr(), n_bands, N_frames, N_frames, pp, dev.index, out.data_ptr(), stream)
+
+        alg, plan = ctx.traffic_model()
+        self.last_run = dict(gpu_launches=ctx.launch_count() - launches0 + 1, block_frames=T, h2d_bytes=frames.h2d_bytes,
+                             bytes_algorithmic_last_block=alg, bytes_plan_last_block=plan, frames_scored=f_end - f_begin)
+
+        stats = {}
+        host = torch.cat([Q_per_ch.reshape(-1), flags.to(torch.float32)]).cpu().numpy()  # one device->host read
+        stats["Q_per_ch"] = host[:-1].reshape(n_bands, 2, N_frames)
+        if host[-1] != 0:
+            logging.warning("Pixel outside the valid range 0-1")
+        stats["rho_band"] = freqs
+        stats["frames_per_second"] = fps
+        stats["width"] = width
+        stats["height"] = height
+        stats["N_frames"] = N_frames
+        if self.do_heatmap:
+            stats["heatmap"] = heatmap
+        return out[0], stats
+
+    # ------------------------------------------------------------------ debugging taps (tests)
+    def read_tap(self, tap, level, frame_in_block):
+        """Intermediate tensor of the last scored block (needs debug_taps=True before predict)."""
+        ctx = self._ctx
+        h, w = ctx.level_size(0 if tap == _native.TAP_R else level)
+        nch = 2 * ctx.cfg.temp_ch
+        planes = {_native.TAP_R: nch, _native.TAP_GAUSS: nch, _native.TAP_CONTRAST: nch, _native.TAP_LBKG: 1,
+                  _native.TAP_S: ctx.cfg.temp_ch, _native.TAP_D: ctx.cfg.temp_ch, _native.TAP_DMAP_BAND: 1}[tap]
+        dst = torch.empty((planes, h, w), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            ctx.read_tap(tap, level, frame_in_block, dst.data_ptr(), dst.numel(), torch.cuda.current_stream(self.device).cuda_stream)
+        return dst
+
+    # ------------------------------------------------------------------ reporting
+    def short_name(self):
+        return "FovVideoVDP"
+
+    def quality_unit(self):
+        return "JOD"
+
+    def get_info_string(self):
+        std = ", (" + self.display_name + ")" if self.display_name.startswith("standard_") else ""
+        mode = "foveated" if self.foveated else "non-foveated"
+        return '"FovVideoVDP v{}, {:.4g} [pix/deg], Lpeak={:.5g}, Lblack={:.4g} [cd/m^2], {}{}"'.format(
+            self.version, self.pix_per_deg, self.display_photometry.get_peak_luminance(), self.display_photometry.get_black_level(), mode, std)
+
+    def write_features_to_json(self, stats, dest_fname):
+        Q = stats["Q_per_ch"]
+        fmap = {}
+        for k, v in stats.items():
+            if k in ("Q_per_ch", "heatmap"):
+                continue
+            fmap[k] = v.tolist() if isinstance(v, np.ndarray) else v
+        for cc in range(Q.shape[1]):
+            for bb in range(Q.shape[0]):
+                fmap[f"t{cc}_b{bb}"] = Q[bb, cc, :].tolist()
+        with open(dest_fname, "w", encoding="utf-8") as f:
+            json.dump(fmap, f, ensure_ascii=False, indent=4)

@@ -12,6 +12,7 @@
  *                               sliding window + temporal FIR (:258-300), process_block_of_frames (:359-478):
  *                               fvvdp_contrast_pyr.decompose (fvvdp_lpyr_dec.py:248-273), cached_sensitivity
  *                               (:520-537, interp.py:11-59), apply_masking_model (:574-596), lp_norm (:598-607)
+ *   fvvdp_b200_pool_jod      <- do_pooling_and_jods (:337-357), run after the optional all-reduce of q_per_ch
  *   fvvdp_b200_read_tap      <- the debug tap points of fvvdp.py:364,410-411,456 (verify_against_matlab)
  *   fvvdp_b200_destroy       <- object lifetime (Python GC in the reference)
  *
@@ -19,8 +20,8 @@
  * negative fvvdp_b200_status and never throws; all device work is enqueued on the caller's stream and is
  * asynchronous (no host synchronisation inside score_block); the caller keeps every buffer it passes alive
  * until the stream has consumed it; a ctx owns its workspace and must be used from one thread/stream at a
- * time.  The final pooling over bands/channels/frames into JOD (do_pooling_and_jods, fvvdp.py:337-357)
- * stays on the host side because in the multi-GPU path it follows the all-reduce of q_per_ch.
+ * time.  The final pooling over bands/channels/frames into JOD (do_pooling_and_jods, fvvdp.py:337-357) is a
+ * separate, ctx-free entry point because in the multi-GPU path it follows the all-reduce of q_per_ch.
  */
 #ifndef FVVDP_B200_H_
 #define FVVDP_B200_H_
@@ -132,6 +133,19 @@ int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* test_slots, c
 int fvvdp_b200_heatmap(fvvdp_b200_ctx* ctx, int frame_in_block, float beta_jod, float jod_a_abs, void* dmap_out_f16,
                        void* cuda_stream);
 
+typedef struct fvvdp_b200_pool_params {
+  float beta_sch, beta_tch, beta_t; /* Lp exponents over spatial bands, temporal channels, frames */
+  float w_transient;                /* weight of the transient channel */
+  float jod_a, log_jod_exp;         /* JOD regression */
+} fvvdp_b200_pool_params;
+
+/*
+ * do_pooling_and_jods (fvvdp.py:337-357): q (DEVICE, (n_bands, 2, q_stride), columns [0, n_frames) used) ->
+ * jod_out[0] = JOD, jod_out[1] = pooled Q before the JOD regression (DEVICE, 2 floats).  Stream-ordered.
+ */
+int fvvdp_b200_pool_jod(const float* q, int n_bands, int64_t n_frames, int64_t q_stride, const fvvdp_b200_pool_params* params,
+                        int cuda_device, float* jod_out, void* cuda_stream);
+
 /* Copy an intermediate tensor of frame `frame_in_block` of the last score_block call to `dst` (DEVICE floats).
  * Requires want_taps (want_dmap for TAP_DMAP_BAND).  Returns the number of floats written, or <0. */
 int64_t fvvdp_b200_read_tap(fvvdp_b200_ctx* ctx, int tap, int level, int frame_in_block, float* dst, int64_t dst_capacity,
@@ -142,6 +156,17 @@ int fvvdp_b200_level_size(const fvvdp_b200_ctx* ctx, int level, int32_t* h, int3
 
 /* Kernel launches enqueued by this ctx so far (for bench.py's gpu_launches). */
 int64_t fvvdp_b200_launch_count(const fvvdp_b200_ctx* ctx);
+
+/*
+ * Per-kernel device timing (bench.py's roofline): when enabled, every kernel launch of score_block is bracketed by
+ * CUDA events on the caller's stream.  profile_read synchronises with the last recorded event, adds up the elapsed
+ * milliseconds and launch counts per kernel class since the previous read, and recycles the events.
+ * Classes: 0 = front (EOTF + temporal FIR), 1 + l = pyramid level l, FVVDP_B200_MAX_LEVELS + 1 = final.
+ * `ms` and `count` hold FVVDP_B200_PROFILE_CLASSES entries.
+ */
+#define FVVDP_B200_PROFILE_CLASSES (FVVDP_B200_MAX_LEVELS + 2)
+int fvvdp_b200_profile(fvvdp_b200_ctx* ctx, int enable);
+int fvvdp_b200_profile_read(fvvdp_b200_ctx* ctx, float* ms, int32_t* count);
 
 /* Algorithmic / structural byte counts of the last score_block call: [0] compulsory input bytes,
  * [1] bytes the kernels of this plan read+write to global memory. */

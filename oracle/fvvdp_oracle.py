@@ -442,12 +442,15 @@ def score_frame(R4, height, freqs, p, is_image, foveated=False, geo=None, frame_
 
 def predict(test, ref, dim_order="BCFHW", frames_per_second=0, display_name="standard_4k", photometry=None,
             geometry_=None, color_space="sRGB", foveated=False, fixation_point=None, temp_padding="replicate",
-            heatmap=None, frames=None, tap_frame=None):
+            heatmap=None, frames=None, tap_frame=None, lum_cache=None, frame_times=None):
     """fvvdp.predict / predict_video_source, fvvdp.py:181-334.
 
     frames: optional iterable of frame indices to score (the others are skipped; used by the bounded
     CPU-baseline sample and the sharding tests).  Returns (jod, stats); stats['taps'] holds the
-    intermediate tensors of frame `tap_frame` when requested."""
+    intermediate tensors of frame `tap_frame` when requested.  lum_cache: optional dict {(stream, frame): luminance}
+    of already converted frames (bench.py pre-fills the temporal window so that the timed region holds the
+    steady-state per-frame work only); frame_times: optional list that receives the seconds spent per scored frame."""
+    import time
     md = metric_data()
     p = md["parameters"]
     photo = photometry if photometry is not None else photometry_from_preset(display_name)
@@ -466,7 +469,7 @@ def predict(test, ref, dim_order="BCFHW", frames_per_second=0, display_name="sta
     want_hm = heatmap not in (None, "none")
     hm = np.zeros((1, 1, N, H, W), np.float16) if want_hm else None
     taps = None
-    lum_cache = {}
+    lum_cache = {} if lum_cache is None else lum_cache
 
     def lum(which, idx):
         key = (which, idx)
@@ -479,6 +482,7 @@ def predict(test, ref, dim_order="BCFHW", frames_per_second=0, display_name="sta
         fl = filter_len(frames_per_second)
         F = temporal_filters(frames_per_second, fl, p["sustained_sigma"], p["sustained_beta"])
     for ff in score:
+        t_start = time.perf_counter()
         if is_image:
             R4 = np.stack([lum(0, 0), lum(1, 0)], 0)
         else:
@@ -503,6 +507,8 @@ def predict(test, ref, dim_order="BCFHW", frames_per_second=0, display_name="sta
         Q_per_ch[:, :, ff] = Q
         if want_hm:
             hm[0, 0, ff] = dmap
+        if frame_times is not None:
+            frame_times.append(time.perf_counter() - t_start)
     sel = Q_per_ch if frames is None else Q_per_ch[:, :, score]
     jod = pool_to_jod(sel, p)
     stats = dict(Q_per_ch=Q_per_ch, rho_band=freqs, frames_per_second=frames_per_second, width=W, height=H, N_frames=N)

@@ -1,0 +1,312 @@
+"""Parity of the CUDA path (through the C ABI, via fovvideovdp_b200.fvvdp) against
+  (a) the golden vectors produced by the unmodified reference (tests/golden/*.npz, tools/gen_golden.py),
+  (b) the CPU oracle (oracle/fvvdp_oracle.py) on the same seeded inputs,
+  (c) size-independent properties at the benchmark's full frame sizes.
+
+Tolerances (BASELINE.json north_star): <= 1e-4 relative on the final JOD, <= 1e-3 max-abs on intermediate band
+contrasts (fp32).
+"""
+import numpy as np
+import pytest
+import torch
+
+from fovvideovdp_b200.synthetic import synth_pair_numpy, synth_pair_torch
+
+pytestmark = pytest.mark.gpu
+
+JOD_RTOL = 1e-4
+BAND_ATOL = 1e-3
+SY, SX = 5, 7
+
+
+@pytest.fixture(scope="module")
+def fv_mod():
+    import fovvideovdp_b200 as m
+    assert torch.cuda.is_available(), "the gpu-marked tests need a CUDA device"
+    return m
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import fvvdp_oracle
+    return fvvdp_oracle
+
+
+def sub(a):
+    return a if a.size <= 40000 else a[..., ::SY, ::SX]
+
+
+def check_jod(jod, want, rtol=JOD_RTOL):
+    jod = float(jod)
+    assert abs(jod - float(want)) / abs(float(want)) < rtol, (jod, float(want))
+
+
+def check_q(Q, gQ, tol=2e-4):
+    scale = np.maximum(np.abs(gQ).max(axis=(0, 2), keepdims=True), 1e-6)
+    err = (np.abs(Q - gQ) / scale).max()
+    assert err < tol, err
+
+
+def check_taps(fv, g, n_bands, temp_ch, frame_in_block, N=None):
+    from fovvideovdp_b200 import _native as nt
+    R = fv.read_tap(nt.TAP_R, 0, frame_in_block).cpu().numpy()
+    np.testing.assert_allclose(sub(R), g["R"], rtol=2e-5, atol=2e-4)
+    for bb in range(n_bands):
+        Cb = fv.read_tap(nt.TAP_CONTRAST, bb, frame_in_block).cpu().numpy()
+        Sb = fv.read_tap(nt.TAP_S, bb, frame_in_block).cpu().numpy()
+        Db = fv.read_tap(nt.TAP_D, bb, frame_in_block).cpu().numpy()
+        Lb = fv.read_tap(nt.TAP_LBKG, bb, frame_in_block).cpu().numpy()[0]
+        np.testing.assert_allclose(sub(Lb), g[f"L_bkg_{bb}"], rtol=2e-5)
+        for cc in range(temp_ch):
+            np.testing.assert_allclose(sub(Cb[2 * cc + 0]), g[f"T_f_{bb}_{cc}"], rtol=0, atol=BAND_ATOL)
+            np.testing.assert_allclose(sub(Cb[2 * cc + 1]), g[f"R_f_{bb}_{cc}"], rtol=0, atol=BAND_ATOL)
+            np.testing.assert_allclose(sub(Sb[cc]), g[f"S_{bb}_{cc}"], rtol=2e-4)
+            gD = g[f"D_{bb}_{cc}"]
+            np.testing.assert_allclose(sub(Db[cc]), gD, rtol=5e-3, atol=1e-5 + 2e-4 * float(gD.max()))
+
+
+# ---------------------------------------------------------------------------------------------- golden vectors
+def test_video_fhd_replicate_with_taps(fv_mod, golden):
+    g = golden("video_fhd_replicate")
+    t, r = synth_pair_numpy(12, 270, 480)
+    fv = fv_mod.fvvdp(display_name="standard_fhd")
+    fv.debug_taps = True
+    jod, st = fv.predict(t, r, frames_per_second=30)
+    check_jod(jod, g["jod"])
+    check_q(st["Q_per_ch"], g["Q_per_ch"])
+    np.testing.assert_allclose(st["rho_band"], g["rho_band"], rtol=1e-12)
+    assert st["N_frames"] == 12 and st["width"] == 480 and st["height"] == 270 and st["frames_per_second"] == 30
+    check_taps(fv, g, 6, 2, int(g["tap_frame"]))
+
+
+@pytest.mark.parametrize("pad", ["pingpong", "circular"])
+def test_video_padding_modes(fv_mod, golden, pad):
+    g = golden(f"video_fhd_{pad}")
+    t, r = synth_pair_numpy(12, 270, 480)
+    jod, st = fv_mod.fvvdp(display_name="standard_fhd", temp_padding=pad).predict(t, r, frames_per_second=30)
+    check_jod(jod, g["jod"])
+    check_q(st["Q_per_ch"], g["Q_per_ch"])
+
+
+@pytest.mark.parametrize("fps", [25, 60])
+@pytest.mark.parametrize("pad", ["replicate", "pingpong", "circular"])
+def test_short_clip_padding(fv_mod, golden, fps, pad):
+    """5-frame clips: the temporal window (7 / 15 taps) is longer than the clip."""
+    g = golden(f"video_short_{fps}fps_{pad}")
+    t, r = synth_pair_numpy(5, 270, 480)
+    jod, st = fv_mod.fvvdp(display_name="standard_fhd", temp_padding=pad).predict(t, r, frames_per_second=fps)
+    check_jod(jod, g["jod"])
+    check_q(st["Q_per_ch"], g["Q_per_ch"])
+
+
+def test_image_with_taps(fv_mod, golden):
+    g = golden("image_fhd")
+    t, r = synth_pair_numpy(1, 270, 480)
+    fv = fv_mod.fvvdp(display_name="standard_fhd")
+    fv.debug_taps = True
+    jod, st = fv.predict(t[0, :, 0:1], r[0, :, 0:1], dim_order="CFHW")
+    check_jod(jod, g["jod"])
+    assert st["Q_per_ch"].shape == (6, 2, 1) and np.all(st["Q_per_ch"][:, 1] == 0)
+    check_taps(fv, g, 6, 1, 0)
+
+
+def test_foveated_hdr_pq(fv_mod, golden):
+    g = golden("video_hdrpq_foveated")
+    t, r = synth_pair_numpy(12, 270, 480)
+    fv = fv_mod.fvvdp(display_name="standard_hdr_pq", foveated=True)
+    jod, st = fv.predict(0.1 + 0.65 * t, 0.1 + 0.65 * r, frames_per_second=30, fixation_point=g["gaze"])
+    check_jod(jod, g["jod"])
+    check_q(st["Q_per_ch"], g["Q_per_ch"], tol=1e-3)  # the reference's own res_mag carries ~1e-3 fp32 cancellation noise
+
+
+def test_foveated_hmd_fixed_gaze(fv_mod, golden):
+    g = golden("video_hmd_foveated_fixed")
+    t, r = synth_pair_numpy(4, 270, 480)
+    fv = fv_mod.fvvdp(display_name="standard_hmd", foveated=True)
+    jod, st = fv.predict(t, r, frames_per_second=30, fixation_point=torch.tensor([100.0, 50.0]))
+    check_jod(jod, g["jod"])
+    check_q(st["Q_per_ch"], g["Q_per_ch"], tol=1e-3)
+
+
+def test_heatmap_raw(fv_mod, golden):
+    g = golden("video_fhd_heatmap_raw")
+    t, r = synth_pair_numpy(4, 270, 480)
+    jod, st = fv_mod.fvvdp(display_name="standard_fhd", heatmap="raw").predict(t, r, frames_per_second=30)
+    check_jod(jod, g["jod"])
+    hm = st["heatmap"]
+    assert hm.dtype == torch.float16 and tuple(hm.shape) == (1, 1, 4, 270, 480) and hm.device.type == "cpu"
+    hm = hm.float().numpy()
+    np.testing.assert_allclose(hm[0, 0, :, ::SY, ::SX], g["heatmap_sub"], rtol=3e-3, atol=3e-3)
+    assert abs(hm.mean() - float(g["hm_mean"])) < 2e-4
+
+
+@pytest.mark.parametrize("hw", [(135, 240), (136, 241), (67, 97), (64, 64)])
+def test_odd_sizes_with_taps(fv_mod, golden, hw):
+    """Odd rows / columns at several pyramid levels, incl. the row-parity quirk of gausspyr_reduce
+    (fvvdp_lpyr_dec.py:202) at (135,240) and (136,241)."""
+    H, W = hw
+    g = golden(f"video_4k_{H}x{W}")
+    t, r = synth_pair_numpy(3, H, W)
+    fv = fv_mod.fvvdp(display_name="standard_4k")
+    fv.debug_taps = True
+    jod, st = fv.predict(t, r, frames_per_second=24)
+    check_jod(jod, g["jod"])
+    check_q(st["Q_per_ch"], g["Q_per_ch"])
+    check_taps(fv, g, st["Q_per_ch"].shape[0], 2, int(g["tap_frame"]))
+
+
+def test_u8_rgb_fhwc(fv_mod, golden):
+    g = golden("video_u8_rgb_fhwc")
+    jod, st = fv_mod.fvvdp(display_name="standard_fhd").predict(g["test"], g["ref"], dim_order="FHWC", frames_per_second=30)
+    check_jod(jod, g["jod"])
+    check_q(st["Q_per_ch"], g["Q_per_ch"])
+    # the same clip already resident on the GPU (strided channel-last view, no upload)
+    tt, rr = torch.from_numpy(g["test"]).cuda(), torch.from_numpy(g["ref"]).cuda()
+    jod2, st2 = fv_mod.fvvdp(display_name="standard_fhd").predict(tt, rr, dim_order="FHWC", frames_per_second=30)
+    assert float(jod2) == float(jod)
+
+
+def test_u16_rgb_gamma_bt2020(fv_mod, golden):
+    g = golden("image_u16_rgb_gamma_bt2020")
+    pm = fv_mod.fvvdp_display_photo_eotf(400, contrast=2000, EOTF="gamma", gamma=2.4, E_ambient=100)
+    fv = fv_mod.fvvdp(display_name="standard_4k", display_photometry=pm, color_space="BT.2020")
+    jod, st = fv.predict(g["test"], g["ref"], dim_order="HWC")
+    check_jod(jod, g["jod"])
+    check_q(st["Q_per_ch"], g["Q_per_ch"])
+
+
+def test_absolute_and_linear(fv_mod, golden):
+    t2, r2 = synth_pair_numpy(3, 64, 64)
+    ta, ra = (t2 * 300 + 0.001).astype(np.float32), (r2 * 300 + 0.001).astype(np.float32)
+    g = golden("video_absolute")
+    fv = fv_mod.fvvdp(display_name="standard_4k", display_photometry=fv_mod.fvvdp_display_photo_absolute(L_max=4000, L_min=0.01))
+    jod, st = fv.predict(ta, ra, frames_per_second=30)
+    check_jod(jod, g["jod"])
+    check_q(st["Q_per_ch"], g["Q_per_ch"])
+    g = golden("video_hdr_linear")
+    jod, st = fv_mod.fvvdp(display_name="standard_hdr_linear").predict(ta, ra, frames_per_second=30)
+    check_jod(jod, g["jod"])
+    check_q(st["Q_per_ch"], g["Q_per_ch"])
+
+
+# ---------------------------------------------------------------------------------------------- oracle, same inputs
+def test_against_oracle_random_content(fv_mod, oracle):
+    """Seeded noise + structure (not the analytic pattern), uint8 RGB, 60 fps (15 taps)."""
+    rng = np.random.default_rng(1234)
+    ref = rng.integers(0, 256, size=(6, 90, 121, 3), dtype=np.uint8)
+    ref[:, 20:60, 30:90] = (ref[:, 20:60, 30:90] // 4 + 150).astype(np.uint8)
+    test = np.clip(ref.astype(np.int32) + rng.integers(-12, 13, size=ref.shape), 0, 255).astype(np.uint8)
+    want, wst = oracle.predict(test, ref, dim_order="FHWC", frames_per_second=60, display_name="standard_fhd")
+    jod, st = fv_mod.fvvdp(display_name="standard_fhd").predict(test, ref, dim_order="FHWC", frames_per_second=60)
+    check_jod(jod, want)
+    check_q(st["Q_per_ch"], wst["Q_per_ch"])
+
+
+def test_against_oracle_1080p_video(fv_mod, oracle):
+    """BASELINE config 2 at full frame size, 3 frames (the oracle needs a few seconds per frame)."""
+    t, r = synth_pair_numpy(3, 1080, 1920)
+    want, wst = oracle.predict(t, r, frames_per_second=30, display_name="standard_fhd")
+    jod, st = fv_mod.fvvdp(display_name="standard_fhd").predict(t, r, frames_per_second=30)
+    check_jod(jod, want)
+    check_q(st["Q_per_ch"], wst["Q_per_ch"])
+
+
+def test_against_oracle_4k_image(fv_mod, oracle):
+    """One full 3840x2160 frame pair (BASELINE config 3 frame size), scored as an image."""
+    t, r = synth_pair_numpy(1, 2160, 3840)
+    want, wst = oracle.predict(t[0, 0, 0], r[0, 0, 0], dim_order="HW", display_name="standard_4k")
+    jod, st = fv_mod.fvvdp(display_name="standard_4k").predict(t[0, 0, 0], r[0, 0, 0], dim_order="HW")
+    check_jod(jod, want)
+    check_q(st["Q_per_ch"], wst["Q_per_ch"])
+
+
+# ---------------------------------------------------------------------------------------------- plumbing variants
+def test_block_size_and_residency_do_not_change_results(fv_mod):
+    t, r = synth_pair_numpy(13, 135, 240)
+    base, bst = fv_mod.fvvdp(display_name="standard_4k").predict(t, r, frames_per_second=30)
+    for bf in (1, 5):
+        jod, st = fv_mod.fvvdp(display_name="standard_4k", block_frames=bf).predict(t, r, frames_per_second=30)
+        np.testing.assert_allclose(st["Q_per_ch"], bst["Q_per_ch"], rtol=1e-6, atol=1e-9)
+        assert abs(float(jod) - float(base)) < 1e-6
+    tt, rr = torch.from_numpy(t).cuda(), torch.from_numpy(r).cuda()
+    jod, st = fv_mod.fvvdp(display_name="standard_4k", block_frames=5).predict(tt, rr, frames_per_second=30)
+    np.testing.assert_allclose(st["Q_per_ch"], bst["Q_per_ch"], rtol=1e-6, atol=1e-9)
+    assert isinstance(jod, torch.Tensor) and jod.dim() == 0 and jod.device.type == "cuda"
+
+
+def test_generic_video_source_matches_array_source(fv_mod):
+    """A user-defined fvvdp_video_source (luminance frames from get_*_frame) and a custom photometry subclass go
+    through the plug-in path (EOTF by the plug-in, then the kernels) and must agree with the fused path."""
+    t, r = synth_pair_numpy(6, 96, 160)
+    fv = fv_mod.fvvdp(display_name="standard_fhd", temp_padding="pingpong")
+    base, bst = fv.predict(t, r, frames_per_second=30)
+
+    class my_photometry(fv_mod.fvvdp_display_photo_eotf):  # subclass => not restated in-kernel
+        def forward(self, V):
+            return super().forward(V)
+
+    pm = my_photometry(200, contrast=1000, EOTF="sRGB", E_ambient=250)
+    inner = fv_mod.fvvdp_video_source_array(t, r, 30, display_photometry=pm)
+
+    class my_source(fv_mod.fvvdp_video_source):
+        def get_video_size(self):
+            return inner.get_video_size()
+
+        def get_frames_per_second(self):
+            return 30
+
+        def get_test_frame(self, frame, device):
+            return inner.get_test_frame(frame, device)
+
+        def get_reference_frame(self, frame, device):
+            return inner.get_reference_frame(frame, device)
+
+    jod, st = fv.predict_video_source(my_source())
+    check_jod(jod, base, rtol=2e-6)
+    check_q(st["Q_per_ch"], bst["Q_per_ch"], tol=2e-5)
+    fv2 = fv_mod.fvvdp(display_name="standard_fhd", display_photometry=pm, temp_padding="pingpong")
+    jod, st = fv2.predict(t, r, frames_per_second=30)
+    check_jod(jod, base, rtol=2e-6)
+
+
+def test_errors_and_warnings(fv_mod, caplog):
+    fv = fv_mod.fvvdp(display_name="standard_fhd")
+    t, r = synth_pair_numpy(2, 64, 64)
+    with pytest.raises(RuntimeError):
+        fv.predict(t, r)  # video without frames_per_second
+    with pytest.raises(RuntimeError):
+        fv.predict(t, r[:, :, :1], frames_per_second=30)
+    with pytest.raises(RuntimeError):
+        fv.predict(t.astype(np.float64), r.astype(np.float64), frames_per_second=30)
+    with pytest.raises(RuntimeError):
+        fv_mod.fvvdp(display_name="standard_fhd", device="cpu")
+    with pytest.raises(RuntimeError):
+        fv_mod.fvvdp(display_name="no_such_display")
+    with pytest.raises(AssertionError):
+        fv_mod.fvvdp(temp_padding="mirror")
+    import logging
+    with caplog.at_level(logging.WARNING):
+        fv.predict(t * 1.5, r, frames_per_second=30)
+    assert any("outside the valid range" in rec.message for rec in caplog.records)
+    assert fv.get_info_string() == '"FovVideoVDP v1.2.3, 37.84 [pix/deg], Lpeak=200, Lblack=0.5979 [cd/m^2], non-foveated, (standard_fhd)"'
+
+
+# ---------------------------------------------------------------------------------------------- full-size properties
+def test_full_size_properties_4k(fv_mod):
+    """BASELINE config 3 frame size (3840x2160, standard_4k), 12 frames resident on the GPU:
+    identical clips score exactly 10 JOD; a frame block scored on its own reproduces the same per-frame
+    pooled energies as the whole clip (what frame sharding relies on); a static clip has constant Q."""
+    dev = torch.device("cuda:0")
+    t, r = synth_pair_torch(12, 2160, 3840, dev)
+    fv = fv_mod.fvvdp(display_name="standard_4k", block_frames=4)
+    jod, st = fv.predict(r, r, frames_per_second=30)
+    assert float(jod) == 10.0 and np.all(st["Q_per_ch"] == 0)
+    jod, st = fv.predict(t, r, frames_per_second=30)
+    assert 5.0 < float(jod) < 10.0 and np.all(np.isfinite(st["Q_per_ch"]))
+    fv12 = fv_mod.fvvdp(display_name="standard_4k", block_frames=12)
+    jod12, st12 = fv12.predict(t, r, frames_per_second=30)
+    np.testing.assert_allclose(st12["Q_per_ch"], st["Q_per_ch"], rtol=1e-6)
+    stat_t, stat_r = t[:, :, 3:4].expand(1, 1, 9, 2160, 3840), r[:, :, 3:4].expand(1, 1, 9, 2160, 3840)
+    jod_s, st_s = fv.predict(stat_t, stat_r, frames_per_second=30)
+    q = st_s["Q_per_ch"]
+    np.testing.assert_allclose(q, np.repeat(q[:, :, :1], 9, axis=2), rtol=1e-6)
