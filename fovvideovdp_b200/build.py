@@ -1,13 +1,23 @@
-"""Ahead-of-time build of libfvvdp_b200.so (nvcc, sm_100a only, in-tree so that it travels with gpurun)."""
+"""Ahead-of-time build of libfvvdp_b200.so (nvcc, sm_100a only, in-tree so that it travels with gpurun).
+The translation units are compiled in parallel and linked into one shared library."""
 import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(PKG, "csrc", "fvvdp_b200.cu")
-DEPS = [SRC, os.path.join(PKG, "csrc", "fvvdp_kernels.cuh"), os.path.join(os.path.dirname(PKG), "include", "fvvdp_b200.h")]
+CSRC = os.path.join(PKG, "csrc")
+HEADERS = [os.path.join(CSRC, h) for h in ("fvvdp_common.cuh", "fvvdp_kernels.cuh", "fvvdp_fused.cuh", "fvvdp_fused_launch.h")] + \
+    [os.path.join(os.path.dirname(PKG), "include", "fvvdp_b200.h")]
+# (object name, source, extra defines)
+UNITS = [("fvvdp_b200", "fvvdp_b200.cu", []), ("fused_dispatch", "fvvdp_fused_dispatch.cu", [])] + \
+    [(f"fused_{k}_{v}", "fvvdp_fused_inst.cu", [f"-DFUSED_KIND={k}", f"-DFUSED_VIDEO={v}"]) for k in range(3) for v in range(2)]
+DEPS = HEADERS + [os.path.join(CSRC, u[1]) for u in UNITS]
+OBJ_DIR = os.path.join(PKG, "_lib", "obj")
 LIB = os.path.join(PKG, "_lib", "libfvvdp_b200.so")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def nvcc_path():
@@ -24,21 +34,39 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build_native(force=False, verbose=False):
-    """Compile csrc/fvvdp_b200.cu -> _lib/libfvvdp_b200.so for sm_100a.  Returns the library path."""
-    if not force and not is_stale():
-        return LIB
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3", "-o", LIB + ".tmp", SRC]
+def _compile(unit, verbose):
+    name, src, defs = unit
+    obj = os.path.join(OBJ_DIR, name + ".o")
+    srcp = os.path.join(CSRC, src)
+    if os.path.isfile(obj) and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in HEADERS + [srcp]):
+        return obj, ""
+    cmd = [nvcc_path()] + ARCH + FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", srcp, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return obj, r.stderr
+
+
+def build_native(force=False, verbose=False):
+    """Compile csrc/*.cu -> _lib/libfvvdp_b200.so for sm_100a.  Returns the library path."""
+    if not force and not is_stale():
+        return LIB
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    if force:
+        for f in os.listdir(OBJ_DIR):
+            os.remove(os.path.join(OBJ_DIR, f))
+    with ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 1)) as ex:
+        res = list(ex.map(lambda u: _compile(u, verbose), UNITS))
+    cmd = [nvcc_path()] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", LIB + ".tmp"] + [r[0] for r in res]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     os.replace(LIB + ".tmp", LIB)
     if verbose:
-        sys.stderr.write(r.stderr)
+        for u, (_, log) in zip(UNITS, res):
+            sys.stderr.write(f"==== {u[0]} ====\n{log}")
     return LIB
 
 
 if __name__ == "__main__":
-    print(build_native(force=True, verbose="-v" in sys.argv))
+    print(build_native(force="-f" in sys.argv, verbose="-v" in sys.argv))

@@ -8,6 +8,10 @@
 #include <new>
 #include <vector>
 
+#include <stdlib.h>
+
+#include "fvvdp_fused.cuh"
+#include "fvvdp_fused_launch.h"
 #include "fvvdp_kernels.cuh"
 
 using namespace fvvdp;
@@ -18,7 +22,11 @@ struct fvvdp_b200_ctx {
   int nch = 4, n_bands = 0, T = 1;
   int lh[FVVDP_B200_MAX_LEVELS], lw[FVVDP_B200_MAX_LEVELS];
   int tiles_x[FVVDP_B200_MAX_LEVELS], tiles_y[FVVDP_B200_MAX_LEVELS];
-  float* G[FVVDP_B200_MAX_LEVELS] = {};        // G[0] = R; [T][nch][h_l][w_l]
+  bool fused = false;                          // fused band kernels (filter_len <= 8) or the general v1 path
+  float* P[FVVDP_B200_MAX_LEVELS] = {};        // fused: luminance pyramid planes, level >= 1: [slots][2][h_l][pitch_l]
+  int pitch[FVVDP_B200_MAX_LEVELS] = {};
+  float* cell = nullptr;                       // fused: [n_bands][32][8] CSF cells over log2 Y
+  float* G[FVVDP_B200_MAX_LEVELS] = {};        // v1 (and taps): G[0] = R; [T][nch][h_l][w_l]
   float* partial[FVVDP_B200_MAX_LEVELS] = {};  // [T][2][ntiles_l]
   float* tapC[FVVDP_B200_MAX_LEVELS] = {};
   float* tapL[FVVDP_B200_MAX_LEVELS] = {};
@@ -78,7 +86,9 @@ static void free_ctx(fvvdp_b200_ctx* c) {
   for (int l = 0; l < FVVDP_B200_MAX_LEVELS; ++l) {
     cudaFree(c->G[l]); cudaFree(c->partial[l]); cudaFree(c->tapC[l]); cudaFree(c->tapL[l]);
     cudaFree(c->tapS[l]); cudaFree(c->tapD[l]); cudaFree(c->dmap[l]); cudaFree(c->vx[l]); cudaFree(c->vy[l]);
+    cudaFree(c->P[l]);
   }
+  cudaFree(c->cell);
   cudaFree(c->recon[0]); cudaFree(c->recon[1]);
   cudaFree(c->axes); cudaFree(c->csf1d); cudaFree(c->lut3d);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
@@ -135,15 +145,27 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
   CUC(cudaSetDevice(cuda_device));
   const int T = c->T, nch = c->nch;
   int hh = cfg->height, ww = cfg->width;
+  {
+    const char* force = getenv("FVVDP_B200_PATH");
+    c->fused = cfg->filter_len <= fused::RING && !(force && strcmp(force, "v1") == 0);
+  }
+  const int tile_w = c->fused ? fused::TW : TW, tile_h = c->fused ? fused::TH : TH;
   for (int l = 0; l < cfg->n_levels; ++l) {
     c->lh[l] = hh; c->lw[l] = ww;
-    c->tiles_x[l] = (ww + TW - 1) / TW; c->tiles_y[l] = (hh + TH - 1) / TH;
+    c->tiles_x[l] = (ww + tile_w - 1) / tile_w; c->tiles_y[l] = (hh + tile_h - 1) / tile_h;
+    c->pitch[l] = (ww + 3) & ~3;
     hh = (hh + 1) / 2; ww = (ww + 1) / 2;
   }
   for (int l = 0; l < cfg->n_levels; ++l) {
     const size_t px = (size_t)c->lh[l] * c->lw[l];
-    // the last Gaussian level (base band) only lives in shared memory of the last band's kernel
-    if (l < c->n_bands) CUC(cudaMalloc(&c->G[l], sizeof(float) * px * nch * T));
+    // v1: 4-channel Gaussian levels of the temporal channels; the last level (base band) only lives in shared memory
+    if (l < c->n_bands && (!c->fused || cfg->want_taps)) CUC(cudaMalloc(&c->G[l], sizeof(float) * px * nch * T));
+    // fused: 2-plane luminance pyramid per window slot; the row padding must stay zero (it is read as zero padding)
+    if (c->fused && l >= 1 && l < c->n_bands) {
+      const size_t n = (size_t)(T + cfg->filter_len - 1) * 2 * c->lh[l] * c->pitch[l];
+      CUC(cudaMalloc(&c->P[l], sizeof(float) * n));
+      CUC(cudaMemset(c->P[l], 0, sizeof(float) * n));
+    }
     if (l < c->n_bands) {
       CUC(cudaMalloc(&c->partial[l], sizeof(float) * (size_t)T * 2 * c->tiles_x[l] * c->tiles_y[l]));
       if (cfg->want_taps) {
@@ -203,6 +225,21 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
     }
     CUC(cudaMalloc(&c->csf1d, sizeof(float) * tab.size()));
     CUC(cudaMemcpy(c->csf1d, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice));
+    // fused kernels: per band 32 cells {Y_log[j], 1/(Y_log[j+1]-Y_log[j]+1e-6), t0[j], t0[j+1]-t0[j], t1[j], t1[j+1]-t1[j], 0, 0}
+    std::vector<float> cell((size_t)c->n_bands * 32 * 8, 0.f);
+    for (int bb = 0; bb < c->n_bands; ++bb)
+      for (int j = 0; j < 32; ++j) {
+        float* q = &cell[((size_t)bb * 32 + j) * 8];
+        const int j1 = j < 31 ? j + 1 : 31;
+        q[0] = cfg->csf_Y_log[j];
+        q[1] = j < 31 ? 1.0f / (cfg->csf_Y_log[j1] - cfg->csf_Y_log[j] + 0.000001f) : 0.f;
+        for (int cc = 0; cc < 2; ++cc) {
+          q[2 + 2 * cc] = tab[((size_t)bb * 2 + cc) * 32 + j];
+          q[3 + 2 * cc] = tab[((size_t)bb * 2 + cc) * 32 + j1] - tab[((size_t)bb * 2 + cc) * 32 + j];
+        }
+      }
+    CUC(cudaMalloc(&c->cell, sizeof(float) * cell.size()));
+    CUC(cudaMemcpy(c->cell, cell.data(), sizeof(float) * cell.size(), cudaMemcpyHostToDevice));
   }
   if (cfg->foveated) {
     // pix2view_direction of each band's pixel centres, the band spanning the whole display
@@ -225,6 +262,7 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
       CUC(cudaMemcpy(c->vy[l], vy.data(), sizeof(float) * vy.size(), cudaMemcpyHostToDevice));
     }
   }
+  CUC(fused::configure_band_kernels());
   CUC(cudaFuncSetAttribute(level_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)level_smem_bytes(4)));
   CUC(cudaFuncSetAttribute(level_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)level_smem_bytes(4)));
   CUC(cudaFuncSetAttribute(level_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)level_smem_bytes(2)));
@@ -320,6 +358,87 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
   const int fl = cfg.filter_len, n_slots = n_frames + fl - 1;
   const int H = cfg.height, W = cfg.width;
 
+  cudaError_t le = cudaSuccess;
+  if (ctx->fused) {
+    // ---- fused band kernels: one launch per pyramid level (fvvdp_fused.cuh) ----
+    static_assert(sizeof(fused::BandParams) <= 4096, "kernel parameter space");
+    fused::BandParams bp;
+    memset(&bp, 0, sizeof(bp));
+    bool aligned = true;
+    for (int s = 0; s < n_slots; ++s) {
+      if (!test_slots[s] || !ref_slots[s]) return fail(ctx, FVVDP_B200_ERR_INVALID, "null frame pointer in slot %d", s);
+      bp.slot[0][s] = test_slots[s];
+      bp.slot[1][s] = ref_slots[s];
+      aligned = aligned && (((uintptr_t)test_slots[s] | (uintptr_t)ref_slots[s]) % 16 == 0);
+    }
+    const bool contig = cfg.in_dtype == FVVDP_B200_F32 && cfg.in_channels == 1 && strides[2] == 1 && aligned && W % 4 == 0 &&
+                        strides[1] % 4 == 0 && strides[1] >= W && strides[1] * (int64_t)H < (1ll << 31);
+    const bool video = cfg.temp_ch == 2;
+    for (int cc = 0; cc < cfg.temp_ch; ++cc)
+      for (int k = 0; k < fused::RING; ++k) {
+        const int kk = k - (fused::RING - fl);  // window position within the real filter, 0 = oldest
+        bp.wgt[cc][k] = kk >= 0 ? cfg.filt[cc][fl - 1 - kk] : 0.0f;  // corr_filter = F.flip(0), fvvdp.py:298
+      }
+    bp.n_frames = n_frames; bp.fl = fl;
+    bp.sC = strides[0]; bp.sH = strides[1]; bp.sW = strides[2];
+    bp.C = cfg.in_channels; bp.dtype = cfg.in_dtype; bp.eotf = cfg.eotf;
+    bp.Yscale = cfg.Y_peak - cfg.Y_black; bp.Y_black = cfg.Y_black; bp.Y_peak = cfg.Y_peak; bp.gamma = cfg.gamma;
+    bp.L_min = cfg.L_min; bp.L_max = cfg.L_max;
+    for (int i = 0; i < 3; ++i) bp.rgb2y[i] = cfg.rgb2y[i];
+    bp.flags = flags_out;
+    bp.y0 = ctx->ax.x0[1]; bp.inv_dy = ctx->ax.inv_dx[1]; bp.lg_y_hi = log2f(cfg.csf_Y_range[1]);
+    bp.mask_p = cfg.mask_p; bp.mask_q[0] = cfg.mask_q[0]; bp.mask_q[1] = cfg.mask_q[1];
+    bp.log2_mask_c = log2f(cfg.mask_c_mul); bp.beta = cfg.beta; bp.w_transient = cfg.w_transient;
+    bp.ax = ctx->ax; bp.lut3d = ctx->lut3d; bp.log2_sens_mul = ctx->log2_sens_mul;
+    if (cfg.foveated) {
+      const double delta = (1.0 / cfg.ppd_centre) / 2.0 * M_PI / 180.0;
+      bp.res_k0 = (float)cos(delta);
+      bp.res_delta_rad = (float)delta;
+      for (int i = 0; i < n_frames; ++i) {
+        const float gx = fixation_xy[2 * i] + 0.5f, gy = fixation_xy[2 * i + 1] + 0.5f;
+        const float xm = (gx - (float)(W / 2.0)) * cfg.display_size_m[0] / (float)W;
+        const float ym = -(gy - (float)(H / 2.0)) * cfg.display_size_m[1] / (float)H;
+        bp.gaze[i][0] = (float)(atan((double)(xm / cfg.distance_m)) * 180.0 / M_PI);
+        bp.gaze[i][1] = (float)(atan((double)(ym / cfg.distance_m)) * 180.0 / M_PI);
+      }
+    }
+    const bool extra = cfg.want_taps || cfg.want_dmap;
+    for (int l = 0; l < ctx->n_bands; ++l) {
+      bp.P = l >= 1 ? ctx->P[l] : nullptr;
+      bp.pitch = ctx->pitch[l];
+      bp.P_slot_stride = 2ll * ctx->lh[l] * ctx->pitch[l];
+      bp.Pn = (l + 1 < ctx->n_bands) ? ctx->P[l + 1] : nullptr;
+      bp.pitch2 = ctx->pitch[l + 1];
+      bp.Pn_slot_stride = 2ll * ctx->lh[l + 1] * ctx->pitch[l + 1];
+      bp.partial = ctx->partial[l];
+      bp.h = ctx->lh[l]; bp.w = ctx->lw[l]; bp.h2 = ctx->lh[l + 1]; bp.w2 = ctx->lw[l + 1];
+      bp.h_odd = bp.h & 1;
+      const int tiles = ctx->tiles_x[l] * ctx->tiles_y[l];
+      bp.ntiles = tiles;
+      // small levels: split the time walk so that the grid still fills the machine (each chunk re-walks fl-1 frames)
+      int nchunks = (4 * 148 + tiles - 1) / tiles;
+      const int max_chunks = (n_frames + 3) / 4;
+      if (nchunks > max_chunks) nchunks = max_chunks;
+      if (nchunks < 1) nchunks = 1;
+      bp.chunk = (n_frames + nchunks - 1) / nchunks;
+      nchunks = (n_frames + bp.chunk - 1) / bp.chunk;
+      bp.cell = ctx->cell + (size_t)l * 256;
+      bp.band_mul = (l == 0) ? 1.0f : 2.0f;  // get_band, fvvdp_lpyr_dec.py:57-63 (the base band is never scored)
+      bp.log2_m = (l == 0) ? 0.0f : 1.0f;
+      bp.rho_band = cfg.band_freq[l];
+      bp.vx = ctx->vx[l]; bp.vy = ctx->vy[l];
+      bp.tapR = (l == 0) ? ctx->G[0] : nullptr;
+      bp.tapG = cfg.want_taps ? ctx->G[l + 1] : nullptr;
+      bp.tapC = ctx->tapC[l]; bp.tapL = ctx->tapL[l]; bp.tapS = ctx->tapS[l]; bp.tapD = ctx->tapD[l];
+      bp.dmap = ctx->dmap[l];
+      const int kind = l == 0 ? (contig ? fused::IN_LEVEL0_CONTIG : fused::IN_LEVEL0_GENERIC) : fused::IN_PYRAMID;
+      dim3 grid(ctx->tiles_x[l], ctx->tiles_y[l], nchunks);
+      ProfScope prof(ctx, 1 + l, st);
+      cudaError_t le2 = fused::launch_band(kind, video, cfg.foveated != 0, extra, bp, grid, st);
+      if (le2 != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "band_kernel[%d] launch: %s", l, cudaGetErrorString(le2));
+      ctx->launches++;
+    }
+  } else {
   // ---- K_front ----
   FrontParams fp;
   memset(&fp, 0, sizeof(fp));
@@ -345,7 +464,6 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
   fp.L_min = cfg.L_min; fp.L_max = cfg.L_max;
   for (int i = 0; i < 3; ++i) fp.rgb2y[i] = cfg.rgb2y[i];
   const bool contig = cfg.in_dtype == FVVDP_B200_F32 && cfg.in_channels == 1 && strides[2] == 1 && aligned;
-  cudaError_t le;
   {
   ProfScope prof(ctx, 0, st);
   if (FLT == 8) {
@@ -414,6 +532,8 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
     ctx->launches++;
   }
 
+  }  // v1 path
+
   // ---- K_final ----
   FinalParams fin;
   memset(&fin, 0, sizeof(fin));
@@ -442,6 +562,10 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
   for (int l = 0; l < ctx->n_bands; ++l) {
     plan += 4.0 * ctx->nch * n_frames * (double)ctx->lh[l] * ctx->lw[l];
     if (l + 1 < ctx->n_bands) plan += 4.0 * ctx->nch * n_frames * (double)ctx->lh[l + 1] * ctx->lw[l + 1];
+  }
+  if (ctx->fused) {  // inputs once per window slot + write and read-back of the 2-plane luminance pyramid
+    plan = 2.0 * P0 * cfg.in_channels * esz * n_slots;
+    for (int l = 1; l < ctx->n_bands; ++l) plan += 2.0 * 4.0 * 2.0 * n_slots * (double)ctx->lh[l] * ctx->pitch[l];
   }
   ctx->bytes_plan = plan;
   return FVVDP_B200_OK;

@@ -1,0 +1,509 @@
+// Fused band kernel of the B200-native FovVideoVDP core (sm_100a): ONE kernel per pyramid level that
+//   * stages the level's luminance tile (+4 px halo) of the next frame into shared memory with cp.async
+//     (level 0: straight from the user's frames, display EOTF applied in shared memory),
+//   * reduces it to the next Gaussian level (separable 5-tap, stride 2; fvvdp_lpyr_dec.py:183-207) and writes that
+//     level out for the next launch,
+//   * keeps the last `fl` frames of both streams ON CHIP while it walks through time: the tile's own pixels in a
+//     register ring, the reduced tile in a shared-memory ring,
+//   * applies the sustained / transient temporal filters (fvvdp.py:294-300) to both rings, expands the filtered
+//     reduced tile (fvvdp_lpyr_dec.py:219-235), forms the contrast bands (:259-269), looks up the CSF
+//     (fvvdp.py:520-537), applies the masking model (:574-596) and accumulates sum D^beta (:467,598-607).
+//
+// The reference filters in time first and then builds one pyramid per temporal channel (4 channels).  Reduce and
+// expand are linear, so  pyr(sum_k w_k L_{t-k}) = sum_k w_k pyr(L_{t-k}):  here the pyramid is built ONCE per
+// luminance frame and stream (2 planes) and the temporal filter is applied to its levels.  Per frame pair this moves
+// 2 input planes + 2 planes per coarser level through HBM instead of the 4-channel R tensor and 4-channel levels.
+//
+// Border semantics follow the reference exactly: zero padding + additive edge terms for the reduce (including the
+// row-parity quirk of fvvdp_lpyr_dec.py:202), index clamping for the expand.
+#pragma once
+#include "fvvdp_common.cuh"
+
+namespace fvvdp {
+namespace fused {
+
+constexpr int TH = 16, TW = 64;                 // output tile of one CTA
+constexpr int LH = TH + 8, LW = TW + 8;         // staged luminance tile: origin (ty0-4, tx0-4)
+constexpr int NH = TH / 2 + 2, NW = TW / 2 + 2; // reduced tile with 1-px halo: origin (jy0-1, jx0-1)
+constexpr int NE = NH * NW;                     // 340
+constexpr int NT = 256;                         // threads: one 2x2 quad each
+constexpr int RING = 8;                         // temporal window kept on chip
+constexpr int MAXCHUNK = 64;                    // output frames walked by one CTA
+constexpr int LV4 = LW / 4;                     // 16-byte chunks per staged row
+constexpr int NLD = (2 * LH * LV4 + NT - 1) / NT;  // cp.async chunks per thread and frame (4)
+constexpr int NCOL = (2 * NE + NT - 1) / NT;       // column-pass outputs per thread (3)
+
+struct BandParams {
+  // ---- input ----
+  const void* slot[2][FVVDP_B200_MAX_SLOTS];  // level 0: [test|ref][slot] frame base pointers
+  const float* P;                             // level >= 1: luminance pyramid planes [slot][2][h][pitch]
+  long long P_slot_stride;                    // floats between slots (= 2 * h * pitch)
+  int pitch;                                  // row pitch of P in floats (multiple of 4; padding is zero)
+  // ---- output ----
+  float* Pn;                                  // [slot][2][h2][pitch2] or nullptr (last scored band)
+  long long Pn_slot_stride;
+  int pitch2;
+  float* partial;                             // [n_frames][2][ntiles]
+  // ---- geometry / schedule ----
+  int h, w, h2, w2, h_odd, ntiles;
+  int n_frames, fl, chunk;                    // output frames; filter taps (<= RING); output frames per CTA
+  float wgt[2][RING];                         // [temporal channel][ring window position], 0 = oldest frame
+  // ---- level-0 input format ----
+  long long sC, sH, sW;
+  int C, dtype, eotf;
+  float Yscale, Y_black, Y_peak, gamma, L_min, L_max;
+  float rgb2y[3];
+  uint32_t* flags;
+  // ---- CSF / masking ----
+  const float* cell;                          // [32][8] per band: Y_log[j], 1/(Y_log[j+1]-Y_log[j]+1e-6), t0[j], t0[j+1]-t0[j], t1[j], t1[j+1]-t1[j]
+  float y0, inv_dy, lg_y_hi;                  // uniform first guess of the Y cell; log2 of the upper clamp
+  float log2_m;                               // log2(band multiplier), fvvdp_lpyr_dec.py:57-63
+  float band_mul;
+  float mask_p, mask_q[2], log2_mask_c, beta, w_transient;
+  // foveated
+  CsfAxes ax;
+  const float* lut3d;
+  float log2_sens_mul, rho_band;
+  const float* vx;
+  const float* vy;
+  float res_k0, res_delta_rad;
+  float gaze[FVVDP_B200_MAX_BLOCK_FRAMES][2];
+  // ---- optional outputs (EXTRA) ----
+  float* tapR;   // level 0: [F][NCH][h][w]
+  float* tapG;   // [F][NCH][h2][w2]  temporally filtered next Gaussian level
+  float* tapC;   // [F][NCH][h][w]
+  float* tapL;   // [F][h][w]
+  float* tapS;   // [F][TC][h][w]
+  float* tapD;   // [F][TC][h][w]
+  float* dmap;   // [F][h][w]
+};
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const void* gsrc, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+__device__ __forceinline__ float eotf_one(float v, const BandParams& p, bool& oor) {
+  switch (p.eotf) {
+    case FVVDP_B200_EOTF_NONE: return v;
+    case FVVDP_B200_EOTF_ABSOLUTE: return fminf(fmaxf(v, p.L_min), p.L_max);
+    case FVVDP_B200_EOTF_LINEAR: return fminf(fmaxf(v, 0.005f), p.Y_peak) + p.Y_black;
+    default: break;
+  }
+  oor |= (v > 1.0f) | (v < 0.0f);
+  v = fminf(fmaxf(v, 0.0f), 1.0f);
+  if (p.eotf == FVVDP_B200_EOTF_SRGB) {
+    const float lin = (v > 0.04045f) ? fast_pow((v + 0.055f) * (1.0f / 1.055f), 2.4f) : v * (1.0f / 12.92f);
+    return fmaf(p.Yscale, lin, p.Y_black);
+  } else if (p.eotf == FVVDP_B200_EOTF_GAMMA) {
+    return fmaf(p.Yscale, fast_pow(v, p.gamma), p.Y_black);
+  } else {
+    const float n_inv = 1.0f / 0.15930175781250000f, m_inv = 1.0f / 78.843750000000000f;
+    const float c1 = 0.83593750000000000f, c2 = 18.851562500000000f, c3 = 18.687500000000000f;
+    const float t = fast_pow(v, m_inv);
+    const float L = 10000.0f * fast_pow(fmaxf(t - c1, 0.0f) / (c2 - c3 * t), n_inv);
+    return fminf(fmaxf(L, 0.005f), p.Y_peak) + p.Y_black;
+  }
+}
+
+__device__ __forceinline__ float lum_generic(const BandParams& p, const void* base, int y, int x, bool& oor) {
+  const long long off = (long long)y * p.sH + (long long)x * p.sW;
+  if (p.C == 3) {
+    const float r = eotf_one(load_sample(base, off, p.dtype), p, oor);
+    const float g = eotf_one(load_sample(base, off + p.sC, p.dtype), p, oor);
+    const float b = eotf_one(load_sample(base, off + 2 * p.sC, p.dtype), p, oor);
+    return r * p.rgb2y[0] + g * p.rgb2y[1] + b * p.rgb2y[2];
+  }
+  return eotf_one(load_sample(base, off, p.dtype), p, oor);
+}
+
+// cell of a 32-point (nearly uniform) axis containing q, and the reference's interpolation fraction
+// (get_interpolants_v1, interp.py:11-20; the fraction uses the stored axis values)
+__device__ __forceinline__ void locate_direct(float q, const float* __restrict__ x, const float* __restrict__ inv, float x0, float inv_dx, int& j,
+                                              float& f) {
+  j = min(max((int)((q - x0) * inv_dx), 0), 30);
+  f = fmaxf((q - __ldg(x + j)) * __ldg(inv + j + 1), 0.0f);
+}
+
+template <int FL>
+struct Ring {
+  float v[2][FL][4];  // [stream][ring slot][pixel of the quad]
+};
+
+// R[cc*2+s][e] = sum_k wgt[cc][k] * ring[s][(J+1+k) % FL][e]   (window position k = 0 is the oldest frame)
+template <int FL, int TC, int J>
+__device__ __forceinline__ void fir_quad(const Ring<FL>& ring, const BandParams& p, float (&R)[2 * TC][4]) {
+#pragma unroll
+  for (int cc = 0; cc < TC; ++cc)
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float a = 0.0f;
+#pragma unroll
+        for (int k = 0; k < FL; ++k) a = fmaf(ring.v[s][(J + 1 + k) % FL][e], FL == 1 ? 1.0f : p.wgt[cc][k], a);
+        R[cc * 2 + s][e] = a;
+      }
+}
+
+template <int FL, int J>
+__device__ __forceinline__ void ring_store(Ring<FL>& ring, const float* __restrict__ sLb, int coff) {
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const float2 a = *reinterpret_cast<const float2*>(sLb + s * LH * LW + coff);
+    const float2 b = *reinterpret_cast<const float2*>(sLb + s * LH * LW + coff + LW);
+    ring.v[s][J][0] = a.x; ring.v[s][J][1] = a.y; ring.v[s][J][2] = b.x; ring.v[s][J][3] = b.y;
+  }
+}
+
+template <bool LEVEL0, bool CONTIG, int FL, int TC, bool FOV, bool EXTRA>
+__global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ BandParams p) {
+  constexpr int NCH = 2 * TC;
+  extern __shared__ __align__(16) float smem[];
+  float* sL = smem;                                  // [2 buffers][2 streams][LH][LW]
+  float* sV = sL + 2 * 2 * LH * LW;                  // [2][NH][LW]   row-reduced
+  float* sNr = sV + 2 * NH * LW;                     // [FL][2][NE]   ring of reduced tiles
+  float* sNc = (FL == 1) ? sNr : sNr + FL * 2 * NE;  // [NCH][NE]     temporally filtered reduced tiles
+  float* sTab = sNr + FL * 2 * NE + (FL == 1 ? 0 : NCH * NE);  // [32][8]
+  float* sRed = sTab + 256;                          // [MAXCHUNK][2][NT/32]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+  const int jx0 = tx0 >> 1, jy0 = ty0 >> 1;
+  const int h = p.h, w = p.w, h2 = p.h2, w2 = p.w2;
+  const int f_lo = blockIdx.z * p.chunk, f_hi = min(f_lo + p.chunk, p.n_frames);
+  const int s_lo = f_lo, s_hi = f_hi + p.fl - 1;  // slots walked by this CTA
+  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+  bool oor = false;
+
+  // ---------------- one-time set-up (all index arithmetic lives here, outside the time loop) ----------------
+  if (tid < 32) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.cell) + 2 * tid);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.cell) + 2 * tid + 1);
+    reinterpret_cast<float4*>(sTab)[2 * tid] = a;
+    reinterpret_cast<float4*>(sTab)[2 * tid + 1] = b;
+  }
+  for (int i = tid; i < FL * 2 * NE; i += NT) sNr[i] = 0.0f;  // window positions that are never loaded must hold finite values
+
+  // staging chunks of this thread: shared offset | stream << 30 (or -1), element offset inside a frame (or -1 = zero fill)
+  int ld_soff[NLD], ld_goff[NLD];
+  if (!LEVEL0 || CONTIG) {
+    const int pitch = LEVEL0 ? (int)p.sH : p.pitch;
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+      const int item = tid + i * NT;
+      ld_soff[i] = -1;
+      ld_goff[i] = -1;
+      if (item < 2 * LH * LV4) {
+        const int s = item / (LH * LV4), rem = item % (LH * LV4), r = rem / LV4, c4 = rem % LV4;
+        const int y = ty0 - 4 + r, x = tx0 - 4 + 4 * c4;
+        ld_soff[i] = ((s * LH + r) * LW + 4 * c4) | (s << 30);
+        // level >= 1: the pitch padding beyond w holds zeros, so a chunk may straddle the right edge
+        if (y >= 0 && y < h && x >= 0 && x < (LEVEL0 ? w : pitch)) ld_goff[i] = y * pitch + x;
+      }
+    }
+  }
+  // column-pass outputs of this thread
+  int cl_src[NCOL], cl_dst[NCOL], cl_g[NCOL];
+#pragma unroll
+  for (int i = 0; i < NCOL; ++i) {
+    const int o = tid + i * NT;
+    cl_src[i] = -1; cl_dst[i] = 0; cl_g[i] = -1;
+    if (o < 2 * NE) {
+      const int s = o / NE, rem = o % NE, a = rem / NW, b = rem % NW;
+      const int ic = min(max(jx0 - 1 + b, 0), w2 - 1);   // expand clamps the coarse index
+      const int flags = (ic == 0 ? 1 : 0) | (ic == w2 - 1 ? 2 : 0);
+      cl_src[i] = ((s * NH + a) * LW + 2 * (ic - jx0) + 2) | (flags << 28);
+      cl_dst[i] = o;
+      const int j = jy0 - 1 + a, ii = jx0 - 1 + b;
+      if (a >= 1 && a <= TH / 2 && b >= 1 && b <= TW / 2 && j < h2 && ii < w2) cl_g[i] = (s * h2 + j) * p.pitch2 + ii;
+    }
+  }
+  // the quad of this thread
+  const int qa = tid >> 5, qb = lane;
+  const int qy = ty0 + 2 * qa, qx = tx0 + 2 * qb;
+  const int coff = (4 + 2 * qa) * LW + 4 + 2 * qb;   // quad's top-left pixel in the staged tile
+  const int noff = qa * NW + qb;                     // top-left of its 3x3 coarse neighbourhood
+  bool valid[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) valid[e] = (qy + (e >> 1) < h) && (qx + (e & 1) < w);
+
+  Ring<FL> ring;
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int k = 0; k < FL; ++k)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ring.v[s][k][e] = 0.0f;
+
+  const float K0 = 0.05f, K1 = 0.25f, K2 = 0.4f, K3 = 0.25f, K4 = 0.05f;
+
+  auto frame_base = [&](int slot, int s) -> const float* {
+    if (LEVEL0) return reinterpret_cast<const float*>(p.slot[s][slot]);
+    return p.P + (long long)slot * p.P_slot_stride + (long long)s * h * p.pitch;
+  };
+  // stage the tile of `slot` into buffer `buf`
+  auto issue_load = [&](int slot, int buf) {
+    float* dst = sL + buf * (2 * LH * LW);
+    if (!LEVEL0 || CONTIG) {
+      const float* b0 = frame_base(slot, 0);
+      const float* b1 = frame_base(slot, 1);
+#pragma unroll
+      for (int i = 0; i < NLD; ++i) {
+        if (ld_soff[i] >= 0) {
+          const float* b = (ld_soff[i] >> 30) ? b1 : b0;
+          const int g = ld_goff[i];
+          cp_async16(dst + (ld_soff[i] & 0xFFFFFF), g >= 0 ? (const void*)(b + g) : (const void*)b, g >= 0 ? 16 : 0);
+        }
+      }
+    } else {
+      for (int item = tid; item < 2 * LH * LW; item += NT) {
+        const int s = item / (LH * LW), rem = item % (LH * LW), r = rem / LW, c = rem % LW;
+        const int y = ty0 - 4 + r, x = tx0 - 4 + c;
+        float v = 0.0f;
+        if (y >= 0 && y < h && x >= 0 && x < w) v = lum_generic(p, p.slot[s][slot], y, x, oor);
+        dst[item] = v;
+      }
+    }
+  };
+  // level 0, contiguous float input: display EOTF in place on this thread's own chunks
+  auto finish_load = [&](int buf) {
+    if (!LEVEL0 || CONTIG) cp_async_commit_wait_all();
+    if (LEVEL0 && CONTIG && p.eotf != FVVDP_B200_EOTF_NONE) {
+      float* dst = sL + buf * (2 * LH * LW);
+#pragma unroll
+      for (int i = 0; i < NLD; ++i) {
+        if (ld_soff[i] >= 0 && ld_goff[i] >= 0) {
+          float4* q = reinterpret_cast<float4*>(dst + (ld_soff[i] & 0xFFFFFF));
+          float4 v = *q;
+          v.x = eotf_one(v.x, p, oor); v.y = eotf_one(v.y, p, oor); v.z = eotf_one(v.z, p, oor); v.w = eotf_one(v.w, p, oor);
+          *q = v;
+        }
+      }
+    }
+  };
+
+  issue_load(s_lo, 0);
+
+  for (int s = s_lo; s < s_hi; ++s) {
+    const int buf = (s - s_lo) & 1;
+    const float* sLb = sL + buf * (2 * LH * LW);
+    finish_load(buf);
+    __syncthreads();  // (1) tile of slot s staged; every reader of the other buffer is done
+    if (s + 1 < s_hi) issue_load(s + 1, buf ^ 1);
+
+    // ---- reduce, rows: sV[st][a][c] = sum_k K[k] L[2j-2+k][c],  j = clamp(jy0-1+a)  (zero padding + edge terms) ----
+    if (tid < 2 * LW) {  // one thread walks down one staged column
+      const int st = tid >= LW ? 1 : 0, c = tid - st * LW;
+      const float* col = sLb + st * LH * LW + c;
+      float* out = sV + st * NH * LW + c;
+#pragma unroll
+      for (int a = 0; a < NH; ++a) {
+        const int jc = min(max(jy0 - 1 + a, 0), h2 - 1);  // expand clamps the coarse index
+        const float* g = col + (2 * (jc - jy0) + 2) * LW;
+        float v = K0 * g[0] + K1 * g[LW] + K2 * g[2 * LW] + K3 * g[3 * LW] + K4 * g[4 * LW];
+        if (jc == 0) v += K1 * g[2 * LW] + K0 * g[3 * LW];     // x[0], x[1]   (fvvdp_lpyr_dec.py:191)
+        if (jc == h2 - 1) {
+          const float* e = col + (h - 1 - ty0 + 4) * LW;       // x[h-1]
+          v += (h & 1) ? (K3 * e[0] + K4 * e[-LW]) : K4 * e[0];  // (:192-195)
+        }
+        out[a * LW] = v;
+      }
+    }
+    __syncthreads();  // (2)
+    // ---- reduce, columns -> ring slot s % FL (+ next level out) ----
+    {
+      float* ring_s = sNr + (s % FL) * (2 * NE);
+      float* gout = (p.Pn != nullptr && s >= s_lo + ((blockIdx.z > 0) ? p.fl - 1 : 0)) ? p.Pn + (long long)s * p.Pn_slot_stride : nullptr;
+#pragma unroll
+      for (int i = 0; i < NCOL; ++i) {
+        if (cl_src[i] >= 0) {
+          const float* v = sV + (cl_src[i] & 0xFFFFFFF);
+          float o = K0 * v[0] + K1 * v[1] + K2 * v[2] + K3 * v[3] + K4 * v[4];
+          if (cl_src[i] & (1 << 28)) o += K1 * v[2] + K0 * v[3];
+          if (cl_src[i] & (2 << 28)) {
+            const float* e = sV + ((cl_src[i] & 0xFFFFFFF) / LW) * LW + (w - 1 - tx0 + 4);  // y[w-1] of this row
+            o += p.h_odd ? (K3 * e[0] + K4 * e[-1]) : K4 * e[0];  // keyed on the ROW count, fvvdp_lpyr_dec.py:202
+          }
+          ring_s[cl_dst[i]] = o;
+          if (gout != nullptr && cl_g[i] >= 0) gout[cl_g[i]] = o;
+        }
+      }
+    }
+    __syncthreads();  // (3)
+
+    const bool emit = s >= f_lo + p.fl - 1;
+    const int fi = s - (p.fl - 1);  // output frame
+    if (FL > 1 && emit) {
+      // ---- temporal filter of the reduced tiles: sNc[cc*2+st][e] = sum_k wgt[cc][k] ring[(s+1+k) % FL][st][e] ----
+#pragma unroll
+      for (int i = 0; i < NCOL; ++i) {
+        const int o = tid + i * NT;
+        if (o < 2 * NE) {
+          float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+          for (int k = 0; k < FL; ++k) {
+            const float v = sNr[((s + 1 + k) % FL) * (2 * NE) + o];
+            a0 = fmaf(v, p.wgt[0][k], a0);
+            if (TC == 2) a1 = fmaf(v, p.wgt[1][k], a1);
+          }
+          const int st = o >= NE ? 1 : 0, e = o - st * NE;
+          sNc[st * NE + e] = a0;
+          if (TC == 2) sNc[(2 + st) * NE + e] = a1;
+        }
+      }
+      __syncthreads();  // (4)
+    }
+
+    // ---- this thread's pixels into the register ring; temporal filter of the full-resolution pixels ----
+    float R[NCH][4];
+    switch (s % FL) {
+#define FVVDP_CASE(J)                                   \
+  case J:                                               \
+    ring_store<FL, (J) % FL>(ring, sLb, coff);          \
+    if (emit) fir_quad<FL, TC, (J) % FL>(ring, p, R);   \
+    break;
+      FVVDP_CASE(0) FVVDP_CASE(1) FVVDP_CASE(2) FVVDP_CASE(3) FVVDP_CASE(4) FVVDP_CASE(5) FVVDP_CASE(6) FVVDP_CASE(7)
+#undef FVVDP_CASE
+    }
+    if (!emit) continue;
+
+    // ---- expand the filtered coarse tile, contrast, CSF, masking, pooling: one 2x2 quad per thread ----
+    float acc[2] = {0.0f, 0.0f};
+    float Lb[4], lgL[4], fj[4];
+    int cj[4];
+    float lsf[TC][4];  // FOV: log2 S per temporal channel
+    float Dsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int cc = 0; cc < TC; ++cc) {
+      float B[2][4];  // band (G_l - E) of the test / reference channel
+      float E1[4];
+#pragma unroll
+      for (int st = 1; st >= 0; --st) {  // reference first: it defines L_bkg
+        const float* n = sNc + (cc * 2 + st) * NE + noff;
+        float ve[3], vo[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float n0 = n[c], n1 = n[NW + c], n2 = n[2 * NW + c];
+          ve[c] = 0.1f * n0 + 0.8f * n1 + 0.1f * n2;  // even row: taps 2K[0], 2K[2], 2K[4]
+          vo[c] = 0.5f * n1 + 0.5f * n2;              // odd row:  taps 2K[1], 2K[3]
+        }
+        float E[4];
+        E[0] = 0.1f * ve[0] + 0.8f * ve[1] + 0.1f * ve[2];
+        E[1] = 0.5f * ve[1] + 0.5f * ve[2];
+        E[2] = 0.1f * vo[0] + 0.8f * vo[1] + 0.1f * vo[2];
+        E[3] = 0.5f * vo[1] + 0.5f * vo[2];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          B[st][e] = R[cc * 2 + st][e] - E[e];
+          if (st == 1) E1[e] = E[e];
+        }
+      }
+      if (cc == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          Lb[e] = fmaxf(E1[e], 0.1f);  // L_bkg = expanded sustained reference (:264-266)
+          lgL[e] = fast_log2(Lb[e]);
+          const float yq = fminf(lgL[e], p.lg_y_hi);
+          if (!FOV) {
+            cj[e] = min(max((int)((yq - p.y0) * p.inv_dy), 0), 30);
+            fj[e] = fmaxf((yq - sTab[cj[e] * 8]) * sTab[cj[e] * 8 + 1], 0.0f);
+          } else {
+            const int x = qx + (e & 1), y = qy + (e >> 1);
+            int jj, ii, kk;
+            float fy, fr, fe;
+            locate_direct(yq, p.ax.x[1], p.ax.inv[1], p.ax.x0[1], p.ax.inv_dx[1], jj, fy);
+            const float vx = __ldg(p.vx + min(x, w - 1)), vy = __ldg(p.vy + min(y, h - 1));
+            const float ex = vx - p.gaze[fi][0], ey = vy - p.gaze[fi][1];
+            const float ecc = sqrtf(ex * ex + ey * ey);
+            const float va = fminf(sqrtf(vx * vx + vy * vy), 89.9f) * 0.017453292519943295f;
+            const float res_mag = p.res_k0 / (__cosf(va) * __cosf(va + p.res_delta_rad));
+            const float rq = fast_log2(fminf(fmaxf(p.rho_band * res_mag, p.ax.lo[0]), p.ax.hi[0]));
+            const float eq = sqrtf(fminf(fmaxf(ecc, p.ax.lo[2]), p.ax.hi[2]));
+            locate_direct(rq, p.ax.x[0], p.ax.inv[0], p.ax.x0[0], p.ax.inv_dx[0], ii, fr);
+            locate_direct(eq, p.ax.x[2], p.ax.inv[2], p.ax.x0[2], p.ax.inv_dx[2], kk, fe);
+#pragma unroll
+            for (int c2 = 0; c2 < TC; ++c2) {
+              const float* v = p.lut3d + c2 * 32768 + (jj * 32 + ii) * 32 + kk;
+              const float a00 = __ldg(v), a01 = __ldg(v + 32), a10 = __ldg(v + 1024), a11 = __ldg(v + 1056);
+              const float b00 = __ldg(v + 1), b01 = __ldg(v + 33), b10 = __ldg(v + 1025), b11 = __ldg(v + 1057);
+              const float lo = (a00 * (1.0f - fr) + a01 * fr) * (1.0f - fy) + (a10 * (1.0f - fr) + a11 * fr) * fy;
+              const float hi = (b00 * (1.0f - fr) + b01 * fr) * (1.0f - fy) + (b10 * (1.0f - fr) + b11 * fr) * fy;
+              lsf[c2][e] = lo * (1.0f - fe) + hi * fe + p.log2_sens_mul;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float lS;  // log2 of (sensitivity x sensitivity_correction)
+        if (!FOV) lS = fmaf(fj[e], sTab[cj[e] * 8 + 3 + 2 * cc], sTab[cj[e] * 8 + 2 + 2 * cc]);
+        else lS = lsf[cc][e];
+        // T_f = min(band/L_bkg, 1000) * m  (:268, :57-63); T/N = T_f * S  (fvvdp.py:583-584)
+        const float lim = 1000.0f * Lb[e];
+        const float bT = fminf(B[0][e], lim), bR = fminf(B[1][e], lim);
+        const float lSL = lS + p.log2_m - lgL[e];
+        const float ld = fast_log2(fabsf(bT - bR)) + lSL;                               // log2 |T' - R'|
+        const float lM = fast_log2(fminf(fabsf(bT), fabsf(bR))) + lSL + p.log2_mask_c;  // log2 M  (:588)
+        const float Mq = fast_exp2(p.mask_q[cc] * lM);
+        const float lD = fminf(fmaf(p.mask_p, ld, -fast_log2(1.0f + Mq)), 13.287712379549449f);  // D <= 1e4 (:593-595)
+        if (valid[e]) acc[cc] += fast_exp2(p.beta * lD);
+        if (EXTRA && valid[e]) {
+          const long long plane = (long long)h * w;
+          const long long pofs = (long long)(qy + (e >> 1)) * w + qx + (e & 1);
+          const float invL = 1.0f / Lb[e];
+          if (p.tapC) {
+            p.tapC[((long long)fi * NCH + cc * 2 + 0) * plane + pofs] = bT * invL * p.band_mul;
+            p.tapC[((long long)fi * NCH + cc * 2 + 1) * plane + pofs] = bR * invL * p.band_mul;
+          }
+          if (p.tapS) p.tapS[((long long)fi * TC + cc) * plane + pofs] = fast_exp2(lS);
+          const float D = fast_exp2(lD);
+          if (p.tapD) p.tapD[((long long)fi * TC + cc) * plane + pofs] = D;
+          Dsum[e] += (cc == 0 ? 1.0f : p.w_transient) * D;
+          if (cc == 0 && p.tapL) p.tapL[(long long)fi * plane + pofs] = Lb[e];
+          if (LEVEL0 && p.tapR) {
+            p.tapR[((long long)fi * NCH + cc * 2 + 0) * plane + pofs] = R[cc * 2 + 0][e];
+            p.tapR[((long long)fi * NCH + cc * 2 + 1) * plane + pofs] = R[cc * 2 + 1][e];
+          }
+          if (cc == TC - 1 && p.dmap) p.dmap[(long long)fi * plane + pofs] = Dsum[e] / p.band_mul;
+        }
+      }
+    }
+    if (EXTRA && p.tapG) {  // temporally filtered next Gaussian level (interior of the coarse tile)
+      for (int o = tid; o < NCH * NE; o += NT) {
+        const int ch = o / NE, rem = o % NE, a = rem / NW, b = rem % NW;
+        const int j = jy0 - 1 + a, ii = jx0 - 1 + b;
+        if (a >= 1 && a <= TH / 2 && b >= 1 && b <= TW / 2 && j < h2 && ii < w2)
+          p.tapG[(((long long)fi * NCH + ch) * h2 + j) * w2 + ii] = sNc[o];
+      }
+    }
+    // ---- per-frame partial sums: warp shuffle now, one pass over the warps at the end ----
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      float v = acc[cc];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) sRed[((fi - f_lo) * 2 + cc) * (NT / 32) + warp] = v;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < (f_hi - f_lo) * 2; i += NT) {
+    float v = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NT / 32; ++k) v += sRed[i * (NT / 32) + k];
+    const int fi = f_lo + (i >> 1), cc = i & 1;
+    p.partial[((long long)fi * 2 + cc) * p.ntiles + tile] = v;
+  }
+  if (LEVEL0 && oor && p.flags) atomicOr(p.flags, 1u);
+}
+
+template <int FL, int TC>
+constexpr size_t band_smem_bytes() {
+  return sizeof(float) * (size_t)(2 * 2 * LH * LW + 2 * NH * LW + FL * 2 * NE + (FL == 1 ? 0 : 2 * TC * NE) + 256 + MAXCHUNK * 2 * (NT / 32));
+}
+
+}  // namespace fused
+}  // namespace fvvdp

@@ -1,0 +1,47 @@
+// Instantiations of the fused band kernel.  Compiled once per (input kind, temporal mode) with
+// -DFUSED_KIND={0,1,2} -DFUSED_VIDEO={0,1} so that the six translation units build in parallel.
+#include "fvvdp_fused.cuh"
+#include "fvvdp_fused_launch.h"
+
+namespace fvvdp {
+namespace fused {
+
+#ifndef FUSED_KIND
+#error "compile with -DFUSED_KIND and -DFUSED_VIDEO"
+#endif
+
+constexpr bool kLevel0 = (FUSED_KIND != 2);
+constexpr bool kContig = (FUSED_KIND == 0);
+constexpr int kFL = FUSED_VIDEO ? RING : 1;
+constexpr int kTC = FUSED_VIDEO ? 2 : 1;
+
+#define FUSED_CAT2(a, b, c) a##b##_##c
+#define FUSED_CAT(a, b, c) FUSED_CAT2(a, b, c)
+#define FUSED_FN(name) FUSED_CAT(name, FUSED_KIND, FUSED_VIDEO)
+
+cudaError_t FUSED_FN(launch_band_)(bool foveated, bool extra, const BandParams& p, dim3 grid, cudaStream_t st) {
+  const size_t smem = band_smem_bytes<kFL, kTC>();
+  if (foveated) {
+    if (extra) band_kernel<kLevel0, kContig, kFL, kTC, true, true><<<grid, NT, smem, st>>>(p);
+    else band_kernel<kLevel0, kContig, kFL, kTC, true, false><<<grid, NT, smem, st>>>(p);
+  } else {
+    if (extra) band_kernel<kLevel0, kContig, kFL, kTC, false, true><<<grid, NT, smem, st>>>(p);
+    else band_kernel<kLevel0, kContig, kFL, kTC, false, false><<<grid, NT, smem, st>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t FUSED_FN(configure_band_)() {
+  const int smem = (int)band_smem_bytes<kFL, kTC>();
+  cudaError_t e;
+  e = cudaFuncSetAttribute(band_kernel<kLevel0, kContig, kFL, kTC, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(band_kernel<kLevel0, kContig, kFL, kTC, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(band_kernel<kLevel0, kContig, kFL, kTC, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(band_kernel<kLevel0, kContig, kFL, kTC, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
+}  // namespace fused
+}  // namespace fvvdp

@@ -5,21 +5,9 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
-#include "../../include/fvvdp_b200.h"
+#include "fvvdp_common.cuh"
 
 namespace fvvdp {
-
-// ------------------------------------------------------------------------------------------------
-// small math helpers (MUFU based: lg2.approx / ex2.approx / rcp.approx)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float fast_log2(float x) { return __log2f(x); }
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float fast_pow(float x, float p) { return fast_exp2(p * fast_log2(x)); }
-__device__ __forceinline__ float fast_rcp(float x) { return __frcp_rn(x); }
 
 // ------------------------------------------------------------------------------------------------
 // K_front: display EOTF -> luminance, sliding temporal window, sustained + transient FIR
@@ -62,13 +50,6 @@ __device__ __forceinline__ float eotf_apply(float v, const FrontParams& p, bool&
     float L = 10000.0f * fast_pow(fmaxf(t - c1, 0.0f) / (c2 - c3 * t), n_inv);
     return fminf(fmaxf(L, 0.005f), p.Y_peak) + p.Y_black;
   }
-}
-
-__device__ __forceinline__ float load_sample(const void* base, long long off, int dtype) {
-  if (dtype == FVVDP_B200_F32) return __ldg(reinterpret_cast<const float*>(base) + off);
-  if (dtype == FVVDP_B200_U8) return static_cast<float>(__ldg(reinterpret_cast<const uint8_t*>(base) + off)) / 255.0f;
-  int v = static_cast<int>(__ldg(reinterpret_cast<const int16_t*>(base) + off)) & 0xFFFF;  // video_source.py:186-196
-  return static_cast<float>(v) / 65535.0f;
 }
 
 // luminance of PX consecutive pixels of one frame
@@ -184,13 +165,6 @@ constexpr int TH = 32, TW = 64, HALO = 4;
 constexpr int SGH = TH + 2 * HALO, SGW = TW + 2 * HALO;  // G_l tile with halo: 40 x 72
 constexpr int NH = TH / 2 + 2, NW = TW / 2 + 2;          // G_{l+1} tile with 1-px halo: 18 x 34
 constexpr int LEVEL_THREADS = 256;
-
-struct CsfAxes {           // device pointers, 32 entries each
-  const float* x[3];       // 0: rho_log, 1: Y_log, 2: ecc_sqrt
-  const float* inv[3];     // 1 / (x[j] - x[j-1] + 1e-6), inv[0] unused
-  float x0[3], inv_dx[3];  // uniform-grid first guess
-  float lo[3], hi[3];      // clamp range in linear units
-};
 
 struct LevelParams {
   const float* G;     // [F][NCH][h][w]
