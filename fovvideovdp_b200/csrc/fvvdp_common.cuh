@@ -11,7 +11,11 @@ namespace fvvdp {
 // ------------------------------------------------------------------------------------------------
 // small math helpers (MUFU based: lg2.approx / ex2.approx / rcp.approx)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float fast_log2(float x) { return __log2f(x); }
+__device__ __forceinline__ float fast_log2(float x) {  // one MUFU.LG2 (no denormal rescaling: tiny inputs flush to -inf)
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

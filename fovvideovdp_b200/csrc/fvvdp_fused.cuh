@@ -86,21 +86,22 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-__device__ __forceinline__ float eotf_one(float v, const BandParams& p, bool& oor) {
-  switch (p.eotf) {
-    case FVVDP_B200_EOTF_NONE: return v;
-    case FVVDP_B200_EOTF_ABSOLUTE: return fminf(fmaxf(v, p.L_min), p.L_max);
-    case FVVDP_B200_EOTF_LINEAR: return fminf(fmaxf(v, 0.005f), p.Y_peak) + p.Y_black;
-    default: break;
-  }
-  oor |= (v > 1.0f) | (v < 0.0f);
-  v = fminf(fmaxf(v, 0.0f), 1.0f);
-  if (p.eotf == FVVDP_B200_EOTF_SRGB) {
-    const float lin = (v > 0.04045f) ? fast_pow((v + 0.055f) * (1.0f / 1.055f), 2.4f) : v * (1.0f / 12.92f);
+// display EOTF -> luminance for one sample (fvvdp_display_model.py:147-165, 203-212).  KIND is a compile-time
+// fvvdp_b200_eotf; the range of the raw values is tracked in vmin/vmax ("Pixel outside the valid range 0-1", :149-151).
+template <int KIND>
+__device__ __forceinline__ float eotf_k(float v, const BandParams& p, float& vmin, float& vmax) {
+  if (KIND == FVVDP_B200_EOTF_NONE) return v;
+  if (KIND == FVVDP_B200_EOTF_ABSOLUTE) return fminf(fmaxf(v, p.L_min), p.L_max);
+  if (KIND == FVVDP_B200_EOTF_LINEAR) return fminf(fmaxf(v, 0.005f), p.Y_peak) + p.Y_black;
+  vmin = fminf(vmin, v);
+  vmax = fmaxf(vmax, v);
+  v = __saturatef(v);
+  if (KIND == FVVDP_B200_EOTF_SRGB) {
+    const float lin = (v > 0.04045f) ? fast_pow(fmaf(v, 1.0f / 1.055f, 0.055f / 1.055f), 2.4f) : v * (1.0f / 12.92f);
     return fmaf(p.Yscale, lin, p.Y_black);
-  } else if (p.eotf == FVVDP_B200_EOTF_GAMMA) {
+  } else if (KIND == FVVDP_B200_EOTF_GAMMA) {
     return fmaf(p.Yscale, fast_pow(v, p.gamma), p.Y_black);
-  } else {
+  } else {  // PQ
     const float n_inv = 1.0f / 0.15930175781250000f, m_inv = 1.0f / 78.843750000000000f;
     const float c1 = 0.83593750000000000f, c2 = 18.851562500000000f, c3 = 18.687500000000000f;
     const float t = fast_pow(v, m_inv);
@@ -109,15 +110,42 @@ __device__ __forceinline__ float eotf_one(float v, const BandParams& p, bool& oo
   }
 }
 
-__device__ __forceinline__ float lum_generic(const BandParams& p, const void* base, int y, int x, bool& oor) {
+__device__ __forceinline__ float eotf_one(float v, const BandParams& p, float& vmin, float& vmax) {
+  switch (p.eotf) {
+    case FVVDP_B200_EOTF_NONE: return v;
+    case FVVDP_B200_EOTF_ABSOLUTE: return eotf_k<FVVDP_B200_EOTF_ABSOLUTE>(v, p, vmin, vmax);
+    case FVVDP_B200_EOTF_LINEAR: return eotf_k<FVVDP_B200_EOTF_LINEAR>(v, p, vmin, vmax);
+    case FVVDP_B200_EOTF_SRGB: return eotf_k<FVVDP_B200_EOTF_SRGB>(v, p, vmin, vmax);
+    case FVVDP_B200_EOTF_GAMMA: return eotf_k<FVVDP_B200_EOTF_GAMMA>(v, p, vmin, vmax);
+    default: return eotf_k<FVVDP_B200_EOTF_PQ>(v, p, vmin, vmax);
+  }
+}
+
+__device__ __forceinline__ float lum_generic(const BandParams& p, const void* base, int y, int x, float& vmin, float& vmax) {
   const long long off = (long long)y * p.sH + (long long)x * p.sW;
   if (p.C == 3) {
-    const float r = eotf_one(load_sample(base, off, p.dtype), p, oor);
-    const float g = eotf_one(load_sample(base, off + p.sC, p.dtype), p, oor);
-    const float b = eotf_one(load_sample(base, off + 2 * p.sC, p.dtype), p, oor);
+    const float r = eotf_one(load_sample(base, off, p.dtype), p, vmin, vmax);
+    const float g = eotf_one(load_sample(base, off + p.sC, p.dtype), p, vmin, vmax);
+    const float b = eotf_one(load_sample(base, off + 2 * p.sC, p.dtype), p, vmin, vmax);
     return r * p.rgb2y[0] + g * p.rgb2y[1] + b * p.rgb2y[2];
   }
-  return eotf_one(load_sample(base, off, p.dtype), p, oor);
+  return eotf_one(load_sample(base, off, p.dtype), p, vmin, vmax);
+}
+
+// in-place EOTF of the 16-byte chunks a thread staged itself (level 0, contiguous float input)
+template <int KIND>
+__device__ __forceinline__ void eotf_chunks(float* dst, const int (&ld_soff)[NLD], const int (&ld_goff)[NLD], const BandParams& p, float& vmin,
+                                            float& vmax) {
+#pragma unroll
+  for (int i = 0; i < NLD; ++i) {
+    if (ld_soff[i] >= 0 && ld_goff[i] >= 0) {
+      float4* q = reinterpret_cast<float4*>(dst + (ld_soff[i] & 0xFFFFFF));
+      float4 v = *q;
+      v.x = eotf_k<KIND>(v.x, p, vmin, vmax); v.y = eotf_k<KIND>(v.y, p, vmin, vmax);
+      v.z = eotf_k<KIND>(v.z, p, vmin, vmax); v.w = eotf_k<KIND>(v.w, p, vmin, vmax);
+      *q = v;
+    }
+  }
 }
 
 // cell of a 32-point (nearly uniform) axis containing q, and the reference's interpolation fraction
@@ -177,7 +205,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
   const int f_lo = blockIdx.z * p.chunk, f_hi = min(f_lo + p.chunk, p.n_frames);
   const int s_lo = f_lo, s_hi = f_hi + p.fl - 1;  // slots walked by this CTA
   const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-  bool oor = false;
+  float vmin = 0.0f, vmax = 1.0f;  // range of the raw level-0 samples this thread converted
 
   // ---------------- one-time set-up (all index arithmetic lives here, outside the time loop) ----------------
   if (tid < 32) {
@@ -240,6 +268,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
       for (int e = 0; e < 4; ++e) ring.v[s][k][e] = 0.0f;
 
   const float K0 = 0.05f, K1 = 0.25f, K2 = 0.4f, K3 = 0.25f, K4 = 0.05f;
+  const bool rows_interior = (jy0 - 1 >= 1) && (jy0 + TH / 2 <= h2 - 2);
 
   auto frame_base = [&](int slot, int s) -> const float* {
     if (LEVEL0) return reinterpret_cast<const float*>(p.slot[s][slot]);
@@ -264,7 +293,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
         const int s = item / (LH * LW), rem = item % (LH * LW), r = rem / LW, c = rem % LW;
         const int y = ty0 - 4 + r, x = tx0 - 4 + c;
         float v = 0.0f;
-        if (y >= 0 && y < h && x >= 0 && x < w) v = lum_generic(p, p.slot[s][slot], y, x, oor);
+        if (y >= 0 && y < h && x >= 0 && x < w) v = lum_generic(p, p.slot[s][slot], y, x, vmin, vmax);
         dst[item] = v;
       }
     }
@@ -272,16 +301,15 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
   // level 0, contiguous float input: display EOTF in place on this thread's own chunks
   auto finish_load = [&](int buf) {
     if (!LEVEL0 || CONTIG) cp_async_commit_wait_all();
-    if (LEVEL0 && CONTIG && p.eotf != FVVDP_B200_EOTF_NONE) {
+    if (LEVEL0 && CONTIG) {
       float* dst = sL + buf * (2 * LH * LW);
-#pragma unroll
-      for (int i = 0; i < NLD; ++i) {
-        if (ld_soff[i] >= 0 && ld_goff[i] >= 0) {
-          float4* q = reinterpret_cast<float4*>(dst + (ld_soff[i] & 0xFFFFFF));
-          float4 v = *q;
-          v.x = eotf_one(v.x, p, oor); v.y = eotf_one(v.y, p, oor); v.z = eotf_one(v.z, p, oor); v.w = eotf_one(v.w, p, oor);
-          *q = v;
-        }
+      switch (p.eotf) {  // uniform; one specialised conversion loop per EOTF
+        case FVVDP_B200_EOTF_NONE: break;
+        case FVVDP_B200_EOTF_SRGB: eotf_chunks<FVVDP_B200_EOTF_SRGB>(dst, ld_soff, ld_goff, p, vmin, vmax); break;
+        case FVVDP_B200_EOTF_GAMMA: eotf_chunks<FVVDP_B200_EOTF_GAMMA>(dst, ld_soff, ld_goff, p, vmin, vmax); break;
+        case FVVDP_B200_EOTF_PQ: eotf_chunks<FVVDP_B200_EOTF_PQ>(dst, ld_soff, ld_goff, p, vmin, vmax); break;
+        case FVVDP_B200_EOTF_LINEAR: eotf_chunks<FVVDP_B200_EOTF_LINEAR>(dst, ld_soff, ld_goff, p, vmin, vmax); break;
+        default: eotf_chunks<FVVDP_B200_EOTF_ABSOLUTE>(dst, ld_soff, ld_goff, p, vmin, vmax); break;
       }
     }
   };
@@ -300,17 +328,27 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
       const int st = tid >= LW ? 1 : 0, c = tid - st * LW;
       const float* col = sLb + st * LH * LW + c;
       float* out = sV + st * NH * LW + c;
+      if (rows_interior) {  // no clamped coarse rows, no edge terms: sliding 5-row window
+        float g0 = col[0], g1 = col[LW], g2 = col[2 * LW];
 #pragma unroll
-      for (int a = 0; a < NH; ++a) {
-        const int jc = min(max(jy0 - 1 + a, 0), h2 - 1);  // expand clamps the coarse index
-        const float* g = col + (2 * (jc - jy0) + 2) * LW;
-        float v = K0 * g[0] + K1 * g[LW] + K2 * g[2 * LW] + K3 * g[3 * LW] + K4 * g[4 * LW];
-        if (jc == 0) v += K1 * g[2 * LW] + K0 * g[3 * LW];     // x[0], x[1]   (fvvdp_lpyr_dec.py:191)
-        if (jc == h2 - 1) {
-          const float* e = col + (h - 1 - ty0 + 4) * LW;       // x[h-1]
-          v += (h & 1) ? (K3 * e[0] + K4 * e[-LW]) : K4 * e[0];  // (:192-195)
+        for (int a = 0; a < NH; ++a) {
+          const float g3 = col[(2 * a + 3) * LW], g4 = col[(2 * a + 4) * LW];
+          out[a * LW] = fmaf(K0, g0 + g4, fmaf(K1, g1 + g3, K2 * g2));
+          g0 = g2; g1 = g3; g2 = g4;
         }
-        out[a * LW] = v;
+      } else {
+#pragma unroll
+        for (int a = 0; a < NH; ++a) {
+          const int jc = min(max(jy0 - 1 + a, 0), h2 - 1);  // expand clamps the coarse index
+          const float* g = col + (2 * (jc - jy0) + 2) * LW;
+          float v = fmaf(K0, g[0] + g[4 * LW], fmaf(K1, g[LW] + g[3 * LW], K2 * g[2 * LW]));
+          if (jc == 0) v += K1 * g[2 * LW] + K0 * g[3 * LW];     // x[0], x[1]   (fvvdp_lpyr_dec.py:191)
+          if (jc == h2 - 1) {
+            const float* e = col + (h - 1 - ty0 + 4) * LW;       // x[h-1]
+            v += (h & 1) ? (K3 * e[0] + K4 * e[-LW]) : K4 * e[0];  // (:192-195)
+          }
+          out[a * LW] = v;
+        }
       }
     }
     __syncthreads();  // (2)
@@ -322,7 +360,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
       for (int i = 0; i < NCOL; ++i) {
         if (cl_src[i] >= 0) {
           const float* v = sV + (cl_src[i] & 0xFFFFFFF);
-          float o = K0 * v[0] + K1 * v[1] + K2 * v[2] + K3 * v[3] + K4 * v[4];
+          float o = fmaf(K0, v[0] + v[4], fmaf(K1, v[1] + v[3], K2 * v[2]));
           if (cl_src[i] & (1 << 28)) o += K1 * v[2] + K0 * v[3];
           if (cl_src[i] & (2 << 28)) {
             const float* e = sV + ((cl_src[i] & 0xFFFFFFF) / LW) * LW + (w - 1 - tx0 + 4);  // y[w-1] of this row
@@ -339,21 +377,21 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
     const int fi = s - (p.fl - 1);  // output frame
     if (FL > 1 && emit) {
       // ---- temporal filter of the reduced tiles: sNc[cc*2+st][e] = sum_k wgt[cc][k] ring[(s+1+k) % FL][st][e] ----
+      if (tid < 2 * NE / 4) {  // four consecutive elements per thread, 16-byte shared loads
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
 #pragma unroll
-      for (int i = 0; i < NCOL; ++i) {
-        const int o = tid + i * NT;
-        if (o < 2 * NE) {
-          float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll
-          for (int k = 0; k < FL; ++k) {
-            const float v = sNr[((s + 1 + k) % FL) * (2 * NE) + o];
-            a0 = fmaf(v, p.wgt[0][k], a0);
-            if (TC == 2) a1 = fmaf(v, p.wgt[1][k], a1);
+        for (int k = 0; k < FL; ++k) {
+          const float4 v = *reinterpret_cast<const float4*>(sNr + ((s + 1 + k) % FL) * (2 * NE) + 4 * tid);
+          a0.x = fmaf(v.x, p.wgt[0][k], a0.x); a0.y = fmaf(v.y, p.wgt[0][k], a0.y);
+          a0.z = fmaf(v.z, p.wgt[0][k], a0.z); a0.w = fmaf(v.w, p.wgt[0][k], a0.w);
+          if (TC == 2) {
+            a1.x = fmaf(v.x, p.wgt[1][k], a1.x); a1.y = fmaf(v.y, p.wgt[1][k], a1.y);
+            a1.z = fmaf(v.z, p.wgt[1][k], a1.z); a1.w = fmaf(v.w, p.wgt[1][k], a1.w);
           }
-          const int st = o >= NE ? 1 : 0, e = o - st * NE;
-          sNc[st * NE + e] = a0;
-          if (TC == 2) sNc[(2 + st) * NE + e] = a1;
         }
+        // element 4*tid of [2][NE] -> stream st = (4*tid >= NE); NE is a multiple of 4
+        *reinterpret_cast<float4*>(sNc + 4 * tid) = a0;                 // channels 0,1 = sustained test / reference
+        if (TC == 2) *reinterpret_cast<float4*>(sNc + 2 * NE + 4 * tid) = a1;  // channels 2,3 = transient
       }
       __syncthreads();  // (4)
     }
@@ -445,12 +483,12 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
         // T_f = min(band/L_bkg, 1000) * m  (:268, :57-63); T/N = T_f * S  (fvvdp.py:583-584)
         const float lim = 1000.0f * Lb[e];
         const float bT = fminf(B[0][e], lim), bR = fminf(B[1][e], lim);
-        const float lSL = lS + p.log2_m - lgL[e];
-        const float ld = fast_log2(fabsf(bT - bR)) + lSL;                               // log2 |T' - R'|
-        const float lM = fast_log2(fminf(fabsf(bT), fabsf(bR))) + lSL + p.log2_mask_c;  // log2 M  (:588)
+        const float lSL = lS + (p.log2_m - lgL[e]);
+        const float ld = fast_log2(valid[e] ? fabsf(bT - bR) : 0.0f) + lSL;               // log2 |T' - R'|
+        const float lM = fast_log2(fminf(fabsf(bT), fabsf(bR))) + (lSL + p.log2_mask_c);  // log2 M  (:588)
         const float Mq = fast_exp2(p.mask_q[cc] * lM);
         const float lD = fminf(fmaf(p.mask_p, ld, -fast_log2(1.0f + Mq)), 13.287712379549449f);  // D <= 1e4 (:593-595)
-        if (valid[e]) acc[cc] += fast_exp2(p.beta * lD);
+        acc[cc] += fast_exp2(p.beta * lD);
         if (EXTRA && valid[e]) {
           const long long plane = (long long)h * w;
           const long long pofs = (long long)(qy + (e >> 1)) * w + qx + (e & 1);
@@ -497,7 +535,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
     const int fi = f_lo + (i >> 1), cc = i & 1;
     p.partial[((long long)fi * 2 + cc) * p.ntiles + tile] = v;
   }
-  if (LEVEL0 && oor && p.flags) atomicOr(p.flags, 1u);
+  if (LEVEL0 && (vmin < 0.0f || vmax > 1.0f) && p.flags) atomicOr(p.flags, 1u);
 }
 
 template <int FL, int TC>
