@@ -26,6 +26,7 @@ struct fvvdp_b200_ctx {
   float* P[FVVDP_B200_MAX_LEVELS] = {};        // fused: luminance pyramid planes, level >= 1: [slots][2][h_l][pitch_l]
   int pitch[FVVDP_B200_MAX_LEVELS] = {};
   float* cell = nullptr;                       // fused: [n_bands][32][8] CSF cells over log2 Y
+  CUtensorMap pmap[FVVDP_B200_MAX_LEVELS];     // fused: TMA descriptors of P[l] (x, y, stream, slot), box = staged tile
   float* G[FVVDP_B200_MAX_LEVELS] = {};        // v1 (and taps): G[0] = R; [T][nch][h_l][w_l]
   float* partial[FVVDP_B200_MAX_LEVELS] = {};  // [T][2][ntiles_l]
   float* tapC[FVVDP_B200_MAX_LEVELS] = {};
@@ -93,6 +94,28 @@ static void free_ctx(fvvdp_b200_ctx* c) {
   cudaFree(c->axes); cudaFree(c->csf1d); cudaFree(c->lut3d);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   delete c;
+}
+
+// cuTensorMapEncodeTiled resolved through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn get_encode_tiled() {
+  static encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (encode_tiled_fn)p;
+  }
+  return fn;
+}
+// float tensor of `rank` dims (dims[0] innermost, strides in bytes for dims 1..), box = staged tile (LW x LH x box2 x 1), zero fill outside
+static bool make_tile_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, int box2) {
+  encode_tiled_fn fn = get_encode_tiled();
+  if (!fn) return false;
+  cuuint32_t box[4] = {(cuuint32_t)fused::LW, (cuuint32_t)fused::LH, (cuuint32_t)box2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 extern "C" int fvvdp_b200_abi_version(void) { return FVVDP_B200_ABI_VERSION; }
@@ -165,6 +188,13 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
       const size_t n = (size_t)(T + cfg->filter_len - 1) * 2 * c->lh[l] * c->pitch[l];
       CUC(cudaMalloc(&c->P[l], sizeof(float) * n));
       CUC(cudaMemset(c->P[l], 0, sizeof(float) * n));
+      const cuuint64_t dims[4] = {(cuuint64_t)c->lw[l], (cuuint64_t)c->lh[l], 2, (cuuint64_t)(T + cfg->filter_len - 1)};
+      const cuuint64_t str[3] = {(cuuint64_t)c->pitch[l] * 4, (cuuint64_t)c->lh[l] * c->pitch[l] * 4, 2ull * c->lh[l] * c->pitch[l] * 4};
+      if (!make_tile_map(&c->pmap[l], c->P[l], 4, dims, str, 2)) {
+        fail(nullptr, FVVDP_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed for pyramid level %d", l);
+        free_ctx(c);
+        return FVVDP_B200_ERR_CUDA;
+      }
     }
     if (l < c->n_bands) {
       CUC(cudaMalloc(&c->partial[l], sizeof(float) * (size_t)T * 2 * c->tiles_x[l] * c->tiles_y[l]));
@@ -361,7 +391,7 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
   cudaError_t le = cudaSuccess;
   if (ctx->fused) {
     // ---- fused band kernels: one launch per pyramid level (fvvdp_fused.cuh) ----
-    static_assert(sizeof(fused::BandParams) <= 4096, "kernel parameter space");
+    static_assert(sizeof(fused::BandParams) <= 4080, "kernel parameter space");
     fused::BandParams bp;
     memset(&bp, 0, sizeof(bp));
     bool aligned = true;
@@ -377,8 +407,37 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
     for (int cc = 0; cc < cfg.temp_ch; ++cc)
       for (int k = 0; k < fused::RING; ++k) {
         const int kk = k - (fused::RING - fl);  // window position within the real filter, 0 = oldest
-        bp.wgt[cc][k] = kk >= 0 ? cfg.filt[cc][fl - 1 - kk] : 0.0f;  // corr_filter = F.flip(0), fvvdp.py:298
+        const float wv = kk >= 0 ? cfg.filt[cc][fl - 1 - kk] : 0.0f;  // corr_filter = F.flip(0), fvvdp.py:298
+        uint32_t bits;
+        memcpy(&bits, &wv, 4);
+        bp.wgt2[cc][k] = ((unsigned long long)bits << 32) | bits;
       }
+    // contiguous float frames at a common stride from one base address: level 0 is staged by TMA as well
+    bool l0_tma = false;
+    if (contig) {
+      uintptr_t base[2], step[2] = {0, 0};
+      const void* const* lists[2] = {test_slots, ref_slots};
+      l0_tma = true;
+      for (int st = 0; st < 2 && l0_tma; ++st) {
+        uintptr_t lo = (uintptr_t)lists[st][0], hi = lo;
+        for (int s = 1; s < n_slots; ++s) { const uintptr_t a = (uintptr_t)lists[st][s]; if (a < lo) lo = a; if (a > hi) hi = a; }
+        uintptr_t g = 0;  // smallest positive distance to the base
+        for (int s = 0; s < n_slots; ++s) { const uintptr_t d = (uintptr_t)lists[st][s] - lo; if (d && (!g || d < g)) g = d; }
+        if (!g) g = (uintptr_t)strides[1] * H * 4;
+        for (int s = 0; s < n_slots; ++s) {
+          const uintptr_t d = (uintptr_t)lists[st][s] - lo;
+          if (d % g || d / g > 65535) l0_tma = false; else bp.slot_frame[st][s] = (unsigned short)(d / g);
+        }
+        if (g % 16 || g < (uintptr_t)strides[1] * (H - 1) * 4 + (uintptr_t)W * 4) l0_tma = false;
+        base[st] = lo; step[st] = g;
+        if (l0_tma) {
+          const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)((hi - lo) / g + 1)};
+          const cuuint64_t str[2] = {(cuuint64_t)strides[1] * 4, (cuuint64_t)g};
+          if (!make_tile_map(&bp.tmap[st], (const void*)lo, 3, dims, str, 1)) l0_tma = false;
+        }
+      }
+      (void)base; (void)step;
+    }
     bp.n_frames = n_frames; bp.fl = fl;
     bp.sC = strides[0]; bp.sH = strides[1]; bp.sW = strides[2];
     bp.C = cfg.in_channels; bp.dtype = cfg.in_dtype; bp.eotf = cfg.eotf;
@@ -431,7 +490,8 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
       bp.tapG = cfg.want_taps ? ctx->G[l + 1] : nullptr;
       bp.tapC = ctx->tapC[l]; bp.tapL = ctx->tapL[l]; bp.tapS = ctx->tapS[l]; bp.tapD = ctx->tapD[l];
       bp.dmap = ctx->dmap[l];
-      const int kind = l == 0 ? (contig ? fused::IN_LEVEL0_CONTIG : fused::IN_LEVEL0_GENERIC) : fused::IN_PYRAMID;
+      const int kind = l == 0 ? (l0_tma ? fused::IN_LEVEL0_TMA : (contig ? fused::IN_LEVEL0_CPASYNC : fused::IN_LEVEL0_GENERIC)) : fused::IN_PYRAMID_TMA;
+      if (l >= 1) bp.tmap[0] = ctx->pmap[l];
       dim3 grid(ctx->tiles_x[l], ctx->tiles_y[l], nchunks);
       ProfScope prof(ctx, 1 + l, st);
       cudaError_t le2 = fused::launch_band(kind, video, cfg.foveated != 0, extra, bp, grid, st);

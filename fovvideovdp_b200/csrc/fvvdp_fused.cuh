@@ -1,7 +1,9 @@
 // Fused band kernel of the B200-native FovVideoVDP core (sm_100a): ONE kernel per pyramid level that
-//   * stages the level's luminance tile (+4 px halo) of the next frame into shared memory with cp.async
-//     (level 0: straight from the user's frames, display EOTF applied in shared memory),
-//   * reduces it to the next Gaussian level (separable 5-tap, stride 2; fvvdp_lpyr_dec.py:183-207) and writes that
+//   * stages the level's luminance tile (+4 px halo) of the NEXT frame into shared memory while the current one is
+//     processed: TMA (cp.async.bulk.tensor, zero fill outside the image, mbarrier completion) for the pyramid levels and
+//     for contiguous float input frames, cp.async / plain loads for everything else (uint8, RGB, strided);
+//     level 0 applies the display EOTF in shared memory,
+//   * reduces the tile to the next Gaussian level (separable 5-tap, stride 2; fvvdp_lpyr_dec.py:183-207) and writes that
 //     level out for the next launch,
 //   * keeps the last `fl` frames of both streams ON CHIP while it walks through time: the tile's own pixels in a
 //     register ring, the reduced tile in a shared-memory ring,
@@ -14,9 +16,15 @@
 // luminance frame and stream (2 planes) and the temporal filter is applied to its levels.  Per frame pair this moves
 // 2 input planes + 2 planes per coarser level through HBM instead of the 4-channel R tensor and 4-channel levels.
 //
+// The kernel is bound by instruction issue, not by HBM, so the arithmetic uses Blackwell's packed
+// fp32x2 instructions (fma/add/mul.rn.f32x2 -> FFMA2/FADD2/FMUL2) wherever two lanes share an operation: pixel pairs
+// in the temporal filter, (test, reference) pairs in the expand.
+//
 // Border semantics follow the reference exactly: zero padding + additive edge terms for the reduce (including the
 // row-parity quirk of fvvdp_lpyr_dec.py:202), index clamping for the expand.
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only; the driver entry point is resolved at run time)
+
 #include "fvvdp_common.cuh"
 
 namespace fvvdp {
@@ -30,15 +38,23 @@ constexpr int NT = 256;                         // threads: one 2x2 quad each
 constexpr int RING = 8;                         // temporal window kept on chip
 constexpr int MAXCHUNK = 64;                    // output frames walked by one CTA
 constexpr int LV4 = LW / 4;                     // 16-byte chunks per staged row
-constexpr int NLD = (2 * LH * LV4 + NT - 1) / NT;  // cp.async chunks per thread and frame (4)
+constexpr int NLD = (2 * LH * LV4 + NT - 1) / NT;  // 16-byte chunks per thread and frame (4)
 constexpr int NCOL = (2 * NE + NT - 1) / NT;       // column-pass outputs per thread (3)
+constexpr int TILE_FLOATS = 2 * LH * LW;           // one staged buffer: [stream][LH][LW]
+
+typedef unsigned long long u64;  // two packed floats (lo, hi)
+
+enum InputKind { IN_LEVEL0_CPASYNC = 0, IN_LEVEL0_GENERIC = 1, IN_PYRAMID_TMA = 2, IN_LEVEL0_TMA = 3 };
 
 struct BandParams {
+  // ---- TMA descriptors: [0] pyramid planes (4-D: x, y, stream, slot) or level-0 test frames (3-D: x, y, frame); [1] level-0 reference frames
+  CUtensorMap tmap[2];
   // ---- input ----
-  const void* slot[2][FVVDP_B200_MAX_SLOTS];  // level 0: [test|ref][slot] frame base pointers
+  const void* slot[2][FVVDP_B200_MAX_SLOTS];   // level 0 without TMA: [test|ref][slot] frame base pointers
+  unsigned short slot_frame[2][FVVDP_B200_MAX_SLOTS];  // level 0 with TMA: frame coordinate of each slot
   const float* P;                             // level >= 1: luminance pyramid planes [slot][2][h][pitch]
   long long P_slot_stride;                    // floats between slots (= 2 * h * pitch)
-  int pitch;                                  // row pitch of P in floats (multiple of 4; padding is zero)
+  int pitch;                                  // row pitch of P in floats (multiple of 4)
   // ---- output ----
   float* Pn;                                  // [slot][2][h2][pitch2] or nullptr (last scored band)
   long long Pn_slot_stride;
@@ -47,7 +63,7 @@ struct BandParams {
   // ---- geometry / schedule ----
   int h, w, h2, w2, h_odd, ntiles;
   int n_frames, fl, chunk;                    // output frames; filter taps (<= RING); output frames per CTA
-  float wgt[2][RING];                         // [temporal channel][ring window position], 0 = oldest frame
+  u64 wgt2[2][RING];                          // [temporal channel][ring window position, 0 = oldest]: (w, w) packed
   // ---- level-0 input format ----
   long long sC, sH, sW;
   int C, dtype, eotf;
@@ -78,16 +94,80 @@ struct BandParams {
   float* dmap;   // [F][h][w]
 };
 
+// ------------------------------------------------------------------------------------------------ packed fp32x2
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float lo_of(u64 v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return lo;
+}
+__device__ __forceinline__ float hi_of(u64 v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return hi;
+}
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) {
+  u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------ async copies
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
 __device__ __forceinline__ void cp_async16(float* smem_dst, const void* gsrc, int src_bytes) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_init(u64* bar, int count) {
+  asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "FVVDP_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra FVVDP_DONE;\n\t"
+      "bra FVVDP_WAIT;\n\t"
+      "FVVDP_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(float* dst, const CUtensorMap* map, u64* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(float* dst, const CUtensorMap* map, u64* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// display EOTF -> luminance for one sample (fvvdp_display_model.py:147-165, 203-212).  KIND is a compile-time
-// fvvdp_b200_eotf; the range of the raw values is tracked in vmin/vmax ("Pixel outside the valid range 0-1", :149-151).
+// ------------------------------------------------------------------------------------------------ display EOTF
+// EOTF -> luminance for one sample (fvvdp_display_model.py:147-165, 203-212).  KIND is a compile-time fvvdp_b200_eotf;
+// the range of the raw values is tracked in vmin/vmax ("Pixel outside the valid range 0-1", :149-151).
 template <int KIND>
 __device__ __forceinline__ float eotf_k(float v, const BandParams& p, float& vmin, float& vmax) {
   if (KIND == FVVDP_B200_EOTF_NONE) return v;
@@ -132,7 +212,7 @@ __device__ __forceinline__ float lum_generic(const BandParams& p, const void* ba
   return eotf_one(load_sample(base, off, p.dtype), p, vmin, vmax);
 }
 
-// in-place EOTF of the 16-byte chunks a thread staged itself (level 0, contiguous float input)
+// in-place EOTF of this thread's 16-byte chunks of the staged tile (level 0, contiguous float input)
 template <int KIND>
 __device__ __forceinline__ void eotf_chunks(float* dst, const int (&ld_soff)[NLD], const int (&ld_goff)[NLD], const BandParams& p, float& vmin,
                                             float& vmax) {
@@ -156,47 +236,76 @@ __device__ __forceinline__ void locate_direct(float q, const float* __restrict__
   f = fmaxf((q - __ldg(x + j)) * __ldg(inv + j + 1), 0.0f);
 }
 
+// ------------------------------------------------------------------------------------------------ temporal rings
 template <int FL>
 struct Ring {
-  float v[2][FL][4];  // [stream][ring slot][pixel of the quad]
+  u64 v[2][FL][2];  // [stream][ring slot][row of the quad] = (left, right) pixel
 };
-
-// R[cc*2+s][e] = sum_k wgt[cc][k] * ring[s][(J+1+k) % FL][e]   (window position k = 0 is the oldest frame)
-template <int FL, int TC, int J>
-__device__ __forceinline__ void fir_quad(const Ring<FL>& ring, const BandParams& p, float (&R)[2 * TC][4]) {
-#pragma unroll
-  for (int cc = 0; cc < TC; ++cc)
-#pragma unroll
-    for (int s = 0; s < 2; ++s)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float a = 0.0f;
-#pragma unroll
-        for (int k = 0; k < FL; ++k) a = fmaf(ring.v[s][(J + 1 + k) % FL][e], FL == 1 ? 1.0f : p.wgt[cc][k], a);
-        R[cc * 2 + s][e] = a;
-      }
-}
 
 template <int FL, int J>
 __device__ __forceinline__ void ring_store(Ring<FL>& ring, const float* __restrict__ sLb, int coff) {
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
-    const float2 a = *reinterpret_cast<const float2*>(sLb + s * LH * LW + coff);
-    const float2 b = *reinterpret_cast<const float2*>(sLb + s * LH * LW + coff + LW);
-    ring.v[s][J][0] = a.x; ring.v[s][J][1] = a.y; ring.v[s][J][2] = b.x; ring.v[s][J][3] = b.y;
+    ring.v[s][J][0] = *reinterpret_cast<const u64*>(sLb + s * LH * LW + coff);
+    ring.v[s][J][1] = *reinterpret_cast<const u64*>(sLb + s * LH * LW + coff + LW);
   }
 }
 
-template <bool LEVEL0, bool CONTIG, int FL, int TC, bool FOV, bool EXTRA>
+// R[cc*2+s][row] = sum_k wgt[cc][k] * ring[s][(J+1+k) % FL][row]   (window position k = 0 is the oldest frame)
+template <int FL, int TC, int J>
+__device__ __forceinline__ void fir_quad(const Ring<FL>& ring, const BandParams& p, u64 (&R)[2 * TC][2]) {
+#pragma unroll
+  for (int cc = 0; cc < TC; ++cc)
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        if (FL == 1) {
+          R[cc * 2 + s][r] = ring.v[s][0][r];
+        } else {
+          u64 a = fmul2(ring.v[s][(J + 1) % FL][r], p.wgt2[cc][0]);
+#pragma unroll
+          for (int k = 1; k < FL; ++k) a = ffma2(ring.v[s][(J + 1 + k) % FL][r], p.wgt2[cc][k], a);
+          R[cc * 2 + s][r] = a;
+        }
+      }
+}
+
+// temporal filter of the reduced tiles: sNc[cc][i] = sum_k wgt[cc][k] sNr[(J+1+k) % FL][i], i over [NE][stream]
+template <int FL, int TC, int J>
+__device__ __forceinline__ void fir_coarse(const float* __restrict__ sNr, float* __restrict__ sNc, const BandParams& p, int tid) {
+  if (tid < 2 * NE / 4) {  // four consecutive floats per thread, 16-byte shared accesses
+    const float* base = sNr + 4 * tid;
+    u64 a[2][2];
+#pragma unroll
+    for (int k = 0; k < FL; ++k) {
+      const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(base + ((J + 1 + k) % FL) * (2 * NE));
+#pragma unroll
+      for (int cc = 0; cc < TC; ++cc) {
+        a[cc][0] = k == 0 ? fmul2(v.x, p.wgt2[cc][0]) : ffma2(v.x, p.wgt2[cc][k], a[cc][0]);
+        a[cc][1] = k == 0 ? fmul2(v.y, p.wgt2[cc][0]) : ffma2(v.y, p.wgt2[cc][k], a[cc][1]);
+      }
+    }
+#pragma unroll
+    for (int cc = 0; cc < TC; ++cc) *reinterpret_cast<ulonglong2*>(sNc + cc * (2 * NE) + 4 * tid) = make_ulonglong2(a[cc][0], a[cc][1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <int KIND, int FL, int TC, bool FOV, bool EXTRA>
 __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ BandParams p) {
+  constexpr bool LEVEL0 = KIND != IN_PYRAMID_TMA;
+  constexpr bool TMA = KIND == IN_PYRAMID_TMA || KIND == IN_LEVEL0_TMA;
+  constexpr bool CHUNKED = KIND != IN_LEVEL0_GENERIC;  // staged as 16-byte chunks of contiguous float rows
   constexpr int NCH = 2 * TC;
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   float* sL = smem;                                  // [2 buffers][2 streams][LH][LW]
-  float* sV = sL + 2 * 2 * LH * LW;                  // [2][NH][LW]   row-reduced
-  float* sNr = sV + 2 * NH * LW;                     // [FL][2][NE]   ring of reduced tiles
-  float* sNc = (FL == 1) ? sNr : sNr + FL * 2 * NE;  // [NCH][NE]     temporally filtered reduced tiles
+  float* sV = sL + 2 * TILE_FLOATS;                  // [2][NH][LW]   row-reduced
+  float* sNr = sV + 2 * NH * LW;                     // [FL][NE][2]   ring of reduced tiles, (test, ref) interleaved
+  float* sNc = (FL == 1) ? sNr : sNr + FL * 2 * NE;  // [TC][NE][2]   temporally filtered reduced tiles
   float* sTab = sNr + FL * 2 * NE + (FL == 1 ? 0 : NCH * NE);  // [32][8]
   float* sRed = sTab + 256;                          // [MAXCHUNK][2][NT/32]
+  __shared__ __align__(8) u64 bars[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
@@ -208,6 +317,11 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
   float vmin = 0.0f, vmax = 1.0f;  // range of the raw level-0 samples this thread converted
 
   // ---------------- one-time set-up (all index arithmetic lives here, outside the time loop) ----------------
+  if (TMA && tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   if (tid < 32) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(p.cell) + 2 * tid);
     const float4 b = __ldg(reinterpret_cast<const float4*>(p.cell) + 2 * tid + 1);
@@ -216,9 +330,10 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
   }
   for (int i = tid; i < FL * 2 * NE; i += NT) sNr[i] = 0.0f;  // window positions that are never loaded must hold finite values
 
-  // staging chunks of this thread: shared offset | stream << 30 (or -1), element offset inside a frame (or -1 = zero fill)
+  // 16-byte chunks of the staged tile owned by this thread: shared offset | stream << 30 (or -1), element offset
+  // inside a frame (or -1 = outside the image: zero fill, no EOTF)
   int ld_soff[NLD], ld_goff[NLD];
-  if (!LEVEL0 || CONTIG) {
+  if (CHUNKED) {
     const int pitch = LEVEL0 ? (int)p.sH : p.pitch;
 #pragma unroll
     for (int i = 0; i < NLD; ++i) {
@@ -229,8 +344,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
         const int s = item / (LH * LV4), rem = item % (LH * LV4), r = rem / LV4, c4 = rem % LV4;
         const int y = ty0 - 4 + r, x = tx0 - 4 + 4 * c4;
         ld_soff[i] = ((s * LH + r) * LW + 4 * c4) | (s << 30);
-        // level >= 1: the pitch padding beyond w holds zeros, so a chunk may straddle the right edge
-        if (y >= 0 && y < h && x >= 0 && x < (LEVEL0 ? w : pitch)) ld_goff[i] = y * pitch + x;
+        if (y >= 0 && y < h && x >= 0 && x < w) ld_goff[i] = y * pitch + x;
       }
     }
   }
@@ -245,7 +359,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
       const int ic = min(max(jx0 - 1 + b, 0), w2 - 1);   // expand clamps the coarse index
       const int flags = (ic == 0 ? 1 : 0) | (ic == w2 - 1 ? 2 : 0);
       cl_src[i] = ((s * NH + a) * LW + 2 * (ic - jx0) + 2) | (flags << 28);
-      cl_dst[i] = o;
+      cl_dst[i] = 2 * rem + s;
       const int j = jy0 - 1 + a, ii = jx0 - 1 + b;
       if (a >= 1 && a <= TH / 2 && b >= 1 && b <= TW / 2 && j < h2 && ii < w2) cl_g[i] = (s * h2 + j) * p.pitch2 + ii;
     }
@@ -254,7 +368,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
   const int qa = tid >> 5, qb = lane;
   const int qy = ty0 + 2 * qa, qx = tx0 + 2 * qb;
   const int coff = (4 + 2 * qa) * LW + 4 + 2 * qb;   // quad's top-left pixel in the staged tile
-  const int noff = qa * NW + qb;                     // top-left of its 3x3 coarse neighbourhood
+  const int noff = 2 * (qa * NW + qb);               // top-left of its 3x3 coarse neighbourhood ((test, ref) interleaved)
   bool valid[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) valid[e] = (qy + (e >> 1) < h) && (qx + (e & 1) < w);
@@ -263,23 +377,28 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
 #pragma unroll
   for (int s = 0; s < 2; ++s)
 #pragma unroll
-    for (int k = 0; k < FL; ++k)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) ring.v[s][k][e] = 0.0f;
+    for (int k = 0; k < FL; ++k) ring.v[s][k][0] = ring.v[s][k][1] = 0ull;
 
   const float K0 = 0.05f, K1 = 0.25f, K2 = 0.4f, K3 = 0.25f, K4 = 0.05f;
   const bool rows_interior = (jy0 - 1 >= 1) && (jy0 + TH / 2 <= h2 - 2);
+  const bool cols_interior = (jx0 - 1 >= 1) && (jx0 + TW / 2 <= w2 - 2);
 
-  auto frame_base = [&](int slot, int s) -> const float* {
-    if (LEVEL0) return reinterpret_cast<const float*>(p.slot[s][slot]);
-    return p.P + (long long)slot * p.P_slot_stride + (long long)s * h * p.pitch;
-  };
   // stage the tile of `slot` into buffer `buf`
   auto issue_load = [&](int slot, int buf) {
-    float* dst = sL + buf * (2 * LH * LW);
-    if (!LEVEL0 || CONTIG) {
-      const float* b0 = frame_base(slot, 0);
-      const float* b1 = frame_base(slot, 1);
+    float* dst = sL + buf * TILE_FLOATS;
+    if (TMA) {
+      if (tid == 0) {
+        mbar_expect_tx(&bars[buf], TILE_FLOATS * 4);
+        if (KIND == IN_PYRAMID_TMA) {
+          tma_load_4d(dst, &p.tmap[0], &bars[buf], tx0 - 4, ty0 - 4, 0, slot);
+        } else {
+          tma_load_3d(dst, &p.tmap[0], &bars[buf], tx0 - 4, ty0 - 4, (int)p.slot_frame[0][slot]);
+          tma_load_3d(dst + LH * LW, &p.tmap[1], &bars[buf], tx0 - 4, ty0 - 4, (int)p.slot_frame[1][slot]);
+        }
+      }
+    } else if (CHUNKED) {
+      const float* b0 = reinterpret_cast<const float*>(p.slot[0][slot]);
+      const float* b1 = reinterpret_cast<const float*>(p.slot[1][slot]);
 #pragma unroll
       for (int i = 0; i < NLD; ++i) {
         if (ld_soff[i] >= 0) {
@@ -289,7 +408,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
         }
       }
     } else {
-      for (int item = tid; item < 2 * LH * LW; item += NT) {
+      for (int item = tid; item < TILE_FLOATS; item += NT) {
         const int s = item / (LH * LW), rem = item % (LH * LW), r = rem / LW, c = rem % LW;
         const int y = ty0 - 4 + r, x = tx0 - 4 + c;
         float v = 0.0f;
@@ -298,11 +417,12 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
       }
     }
   };
-  // level 0, contiguous float input: display EOTF in place on this thread's own chunks
-  auto finish_load = [&](int buf) {
-    if (!LEVEL0 || CONTIG) cp_async_commit_wait_all();
-    if (LEVEL0 && CONTIG) {
-      float* dst = sL + buf * (2 * LH * LW);
+  // wait for the staged tile; level 0 with raw float input: display EOTF in place on this thread's chunks
+  auto finish_load = [&](int buf, unsigned parity) {
+    if (TMA) mbar_wait(&bars[buf], parity);
+    else if (CHUNKED) cp_async_commit_wait_all();
+    if (LEVEL0 && CHUNKED) {
+      float* dst = sL + buf * TILE_FLOATS;
       switch (p.eotf) {  // uniform; one specialised conversion loop per EOTF
         case FVVDP_B200_EOTF_NONE: break;
         case FVVDP_B200_EOTF_SRGB: eotf_chunks<FVVDP_B200_EOTF_SRGB>(dst, ld_soff, ld_goff, p, vmin, vmax); break;
@@ -311,15 +431,17 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
         case FVVDP_B200_EOTF_LINEAR: eotf_chunks<FVVDP_B200_EOTF_LINEAR>(dst, ld_soff, ld_goff, p, vmin, vmax); break;
         default: eotf_chunks<FVVDP_B200_EOTF_ABSOLUTE>(dst, ld_soff, ld_goff, p, vmin, vmax); break;
       }
+      if (TMA) fence_proxy_async_smem();  // these generic-proxy writes precede the next TMA write into this buffer
     }
   };
 
+  if (TMA) __syncthreads();  // barrier initialisation visible before the first wait
   issue_load(s_lo, 0);
 
   for (int s = s_lo; s < s_hi; ++s) {
     const int buf = (s - s_lo) & 1;
-    const float* sLb = sL + buf * (2 * LH * LW);
-    finish_load(buf);
+    const float* sLb = sL + buf * TILE_FLOATS;
+    finish_load(buf, ((s - s_lo) >> 1) & 1);
     __syncthreads();  // (1) tile of slot s staged; every reader of the other buffer is done
     if (s + 1 < s_hi) issue_load(s + 1, buf ^ 1);
 
@@ -358,13 +480,15 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
       float* gout = (p.Pn != nullptr && s >= s_lo + ((blockIdx.z > 0) ? p.fl - 1 : 0)) ? p.Pn + (long long)s * p.Pn_slot_stride : nullptr;
 #pragma unroll
       for (int i = 0; i < NCOL; ++i) {
-        if (cl_src[i] >= 0) {
+        if (i < NCOL - 1 || cl_src[i] >= 0) {  // only the last round is partial
           const float* v = sV + (cl_src[i] & 0xFFFFFFF);
           float o = fmaf(K0, v[0] + v[4], fmaf(K1, v[1] + v[3], K2 * v[2]));
-          if (cl_src[i] & (1 << 28)) o += K1 * v[2] + K0 * v[3];
-          if (cl_src[i] & (2 << 28)) {
-            const float* e = sV + ((cl_src[i] & 0xFFFFFFF) / LW) * LW + (w - 1 - tx0 + 4);  // y[w-1] of this row
-            o += p.h_odd ? (K3 * e[0] + K4 * e[-1]) : K4 * e[0];  // keyed on the ROW count, fvvdp_lpyr_dec.py:202
+          if (!cols_interior) {
+            if (cl_src[i] & (1 << 28)) o += K1 * v[2] + K0 * v[3];
+            if (cl_src[i] & (2 << 28)) {
+              const float* e = sV + ((cl_src[i] & 0xFFFFFFF) / LW) * LW + (w - 1 - tx0 + 4);  // y[w-1] of this row
+              o += p.h_odd ? (K3 * e[0] + K4 * e[-1]) : K4 * e[0];  // keyed on the ROW count, fvvdp_lpyr_dec.py:202
+            }
           }
           ring_s[cl_dst[i]] = o;
           if (gout != nullptr && cl_g[i] >= 0) gout[cl_g[i]] = o;
@@ -375,39 +499,23 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
 
     const bool emit = s >= f_lo + p.fl - 1;
     const int fi = s - (p.fl - 1);  // output frame
-    if (FL > 1 && emit) {
-      // ---- temporal filter of the reduced tiles: sNc[cc*2+st][e] = sum_k wgt[cc][k] ring[(s+1+k) % FL][st][e] ----
-      if (tid < 2 * NE / 4) {  // four consecutive elements per thread, 16-byte shared loads
-        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-#pragma unroll
-        for (int k = 0; k < FL; ++k) {
-          const float4 v = *reinterpret_cast<const float4*>(sNr + ((s + 1 + k) % FL) * (2 * NE) + 4 * tid);
-          a0.x = fmaf(v.x, p.wgt[0][k], a0.x); a0.y = fmaf(v.y, p.wgt[0][k], a0.y);
-          a0.z = fmaf(v.z, p.wgt[0][k], a0.z); a0.w = fmaf(v.w, p.wgt[0][k], a0.w);
-          if (TC == 2) {
-            a1.x = fmaf(v.x, p.wgt[1][k], a1.x); a1.y = fmaf(v.y, p.wgt[1][k], a1.y);
-            a1.z = fmaf(v.z, p.wgt[1][k], a1.z); a1.w = fmaf(v.w, p.wgt[1][k], a1.w);
-          }
-        }
-        // element 4*tid of [2][NE] -> stream st = (4*tid >= NE); NE is a multiple of 4
-        *reinterpret_cast<float4*>(sNc + 4 * tid) = a0;                 // channels 0,1 = sustained test / reference
-        if (TC == 2) *reinterpret_cast<float4*>(sNc + 2 * NE + 4 * tid) = a1;  // channels 2,3 = transient
-      }
-      __syncthreads();  // (4)
-    }
-
-    // ---- this thread's pixels into the register ring; temporal filter of the full-resolution pixels ----
-    float R[NCH][4];
+    // ---- this thread's pixels into the register ring; temporal filters of the coarse tiles and of the pixels.
+    //      The ring position is a compile-time constant inside each case: no address arithmetic, no register moves.
+    u64 R[NCH][2];
     switch (s % FL) {
-#define FVVDP_CASE(J)                                   \
-  case J:                                               \
-    ring_store<FL, (J) % FL>(ring, sLb, coff);          \
-    if (emit) fir_quad<FL, TC, (J) % FL>(ring, p, R);   \
+#define FVVDP_CASE(J)                                          \
+  case J:                                                      \
+    ring_store<FL, (J) % FL>(ring, sLb, coff);                 \
+    if (emit) {                                                \
+      if (FL > 1) fir_coarse<FL, TC, (J) % FL>(sNr, sNc, p, tid); \
+      fir_quad<FL, TC, (J) % FL>(ring, p, R);                  \
+    }                                                          \
     break;
       FVVDP_CASE(0) FVVDP_CASE(1) FVVDP_CASE(2) FVVDP_CASE(3) FVVDP_CASE(4) FVVDP_CASE(5) FVVDP_CASE(6) FVVDP_CASE(7)
 #undef FVVDP_CASE
     }
     if (!emit) continue;
+    if (FL > 1) __syncthreads();  // (4) filtered coarse tiles visible
 
     // ---- expand the filtered coarse tile, contrast, CSF, masking, pooling: one 2x2 quad per thread ----
     float acc[2] = {0.0f, 0.0f};
@@ -415,40 +523,41 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
     int cj[4];
     float lsf[TC][4];  // FOV: log2 S per temporal channel
     float Dsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const u64 c01 = pk(0.1f, 0.1f), c08 = pk(0.8f, 0.8f), c05 = pk(0.5f, 0.5f);
 #pragma unroll
     for (int cc = 0; cc < TC; ++cc) {
+      // expand both streams at once: every value below is a (test, reference) pair
+      const float* n = sNc + cc * (2 * NE) + noff;
+      u64 ve[3], vo[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const u64 n0 = *reinterpret_cast<const u64*>(n + 2 * c), n1 = *reinterpret_cast<const u64*>(n + 2 * (NW + c)),
+                  n2 = *reinterpret_cast<const u64*>(n + 2 * (2 * NW + c));
+        ve[c] = ffma2(c08, n1, fmul2(c01, fadd2(n0, n2)));  // even row: taps 2K[0], 2K[2], 2K[4]
+        vo[c] = fmul2(c05, fadd2(n1, n2));                  // odd row:  taps 2K[1], 2K[3]
+      }
+      u64 E[4];
+      E[0] = ffma2(c08, ve[1], fmul2(c01, fadd2(ve[0], ve[2])));
+      E[1] = fmul2(c05, fadd2(ve[1], ve[2]));
+      E[2] = ffma2(c08, vo[1], fmul2(c01, fadd2(vo[0], vo[2])));
+      E[3] = fmul2(c05, fadd2(vo[1], vo[2]));
       float B[2][4];  // band (G_l - E) of the test / reference channel
-      float E1[4];
 #pragma unroll
-      for (int st = 1; st >= 0; --st) {  // reference first: it defines L_bkg
-        const float* n = sNc + (cc * 2 + st) * NE + noff;
-        float ve[3], vo[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float n0 = n[c], n1 = n[NW + c], n2 = n[2 * NW + c];
-          ve[c] = 0.1f * n0 + 0.8f * n1 + 0.1f * n2;  // even row: taps 2K[0], 2K[2], 2K[4]
-          vo[c] = 0.5f * n1 + 0.5f * n2;              // odd row:  taps 2K[1], 2K[3]
-        }
-        float E[4];
-        E[0] = 0.1f * ve[0] + 0.8f * ve[1] + 0.1f * ve[2];
-        E[1] = 0.5f * ve[1] + 0.5f * ve[2];
-        E[2] = 0.1f * vo[0] + 0.8f * vo[1] + 0.1f * vo[2];
-        E[3] = 0.5f * vo[1] + 0.5f * vo[2];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          B[st][e] = R[cc * 2 + st][e] - E[e];
-          if (st == 1) E1[e] = E[e];
-        }
+      for (int e = 0; e < 4; ++e) {
+        const u64 rt = R[cc * 2 + 0][e >> 1], rr = R[cc * 2 + 1][e >> 1];
+        B[0][e] = ((e & 1) ? hi_of(rt) : lo_of(rt)) - lo_of(E[e]);
+        B[1][e] = ((e & 1) ? hi_of(rr) : lo_of(rr)) - hi_of(E[e]);
       }
       if (cc == 0) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          Lb[e] = fmaxf(E1[e], 0.1f);  // L_bkg = expanded sustained reference (:264-266)
+          Lb[e] = fmaxf(hi_of(E[e]), 0.1f);  // L_bkg = expanded sustained reference (:264-266)
           lgL[e] = fast_log2(Lb[e]);
           const float yq = fminf(lgL[e], p.lg_y_hi);
           if (!FOV) {
             cj[e] = min(max((int)((yq - p.y0) * p.inv_dy), 0), 30);
-            fj[e] = fmaxf((yq - sTab[cj[e] * 8]) * sTab[cj[e] * 8 + 1], 0.0f);
+            const float2 xi = *reinterpret_cast<const float2*>(sTab + cj[e] * 8);
+            fj[e] = fmaxf((yq - xi.x) * xi.y, 0.0f);
           } else {
             const int x = qx + (e & 1), y = qy + (e >> 1);
             int jj, ii, kk;
@@ -478,8 +587,12 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float lS;  // log2 of (sensitivity x sensitivity_correction)
-        if (!FOV) lS = fmaf(fj[e], sTab[cj[e] * 8 + 3 + 2 * cc], sTab[cj[e] * 8 + 2 + 2 * cc]);
-        else lS = lsf[cc][e];
+        if (!FOV) {
+          const float2 td = *reinterpret_cast<const float2*>(sTab + cj[e] * 8 + 2 + 2 * cc);
+          lS = fmaf(fj[e], td.y, td.x);
+        } else {
+          lS = lsf[cc][e];
+        }
         // T_f = min(band/L_bkg, 1000) * m  (:268, :57-63); T/N = T_f * S  (fvvdp.py:583-584)
         const float lim = 1000.0f * Lb[e];
         const float bT = fminf(B[0][e], lim), bR = fminf(B[1][e], lim);
@@ -503,8 +616,9 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
           Dsum[e] += (cc == 0 ? 1.0f : p.w_transient) * D;
           if (cc == 0 && p.tapL) p.tapL[(long long)fi * plane + pofs] = Lb[e];
           if (LEVEL0 && p.tapR) {
-            p.tapR[((long long)fi * NCH + cc * 2 + 0) * plane + pofs] = R[cc * 2 + 0][e];
-            p.tapR[((long long)fi * NCH + cc * 2 + 1) * plane + pofs] = R[cc * 2 + 1][e];
+            const u64 rt = R[cc * 2 + 0][e >> 1], rr = R[cc * 2 + 1][e >> 1];
+            p.tapR[((long long)fi * NCH + cc * 2 + 0) * plane + pofs] = (e & 1) ? hi_of(rt) : lo_of(rt);
+            p.tapR[((long long)fi * NCH + cc * 2 + 1) * plane + pofs] = (e & 1) ? hi_of(rr) : lo_of(rr);
           }
           if (cc == TC - 1 && p.dmap) p.dmap[(long long)fi * plane + pofs] = Dsum[e] / p.band_mul;
         }
@@ -512,10 +626,10 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
     }
     if (EXTRA && p.tapG) {  // temporally filtered next Gaussian level (interior of the coarse tile)
       for (int o = tid; o < NCH * NE; o += NT) {
-        const int ch = o / NE, rem = o % NE, a = rem / NW, b = rem % NW;
+        const int cc = o / (2 * NE), rem = o % (2 * NE), el = rem >> 1, st = rem & 1, a = el / NW, b = el % NW;
         const int j = jy0 - 1 + a, ii = jx0 - 1 + b;
         if (a >= 1 && a <= TH / 2 && b >= 1 && b <= TW / 2 && j < h2 && ii < w2)
-          p.tapG[(((long long)fi * NCH + ch) * h2 + j) * w2 + ii] = sNc[o];
+          p.tapG[(((long long)fi * NCH + cc * 2 + st) * h2 + j) * w2 + ii] = sNc[o];
       }
     }
     // ---- per-frame partial sums: warp shuffle now, one pass over the warps at the end ----
@@ -540,7 +654,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
 
 template <int FL, int TC>
 constexpr size_t band_smem_bytes() {
-  return sizeof(float) * (size_t)(2 * 2 * LH * LW + 2 * NH * LW + FL * 2 * NE + (FL == 1 ? 0 : 2 * TC * NE) + 256 + MAXCHUNK * 2 * (NT / 32));
+  return sizeof(float) * (size_t)(2 * TILE_FLOATS + 2 * NH * LW + FL * 2 * NE + (FL == 1 ? 0 : 2 * TC * NE) + 256 + MAXCHUNK * 2 * (NT / 32));
 }
 
 }  // namespace fused

@@ -1,4 +1,4 @@
-// Dispatch over the six fused-kernel translation units.
+// Dispatch over the eight fused-kernel translation units.
 #include "fvvdp_fused_launch.h"
 
 namespace fvvdp {
@@ -7,7 +7,7 @@ namespace fused {
 #define DECL(k, v)                                                                                          \
   cudaError_t launch_band_##k##_##v(bool foveated, bool extra, const BandParams& p, dim3 grid, cudaStream_t st); \
   cudaError_t configure_band_##k##_##v();
-DECL(0, 0) DECL(0, 1) DECL(1, 0) DECL(1, 1) DECL(2, 0) DECL(2, 1)
+DECL(0, 0) DECL(0, 1) DECL(1, 0) DECL(1, 1) DECL(2, 0) DECL(2, 1) DECL(3, 0) DECL(3, 1)
 #undef DECL
 
 cudaError_t launch_band(int kind, bool video, bool foveated, bool extra, const BandParams& p, dim3 grid, cudaStream_t st) {
@@ -18,6 +18,8 @@ cudaError_t launch_band(int kind, bool video, bool foveated, bool extra, const B
     case 3: return launch_band_1_1(foveated, extra, p, grid, st);
     case 4: return launch_band_2_0(foveated, extra, p, grid, st);
     case 5: return launch_band_2_1(foveated, extra, p, grid, st);
+    case 6: return launch_band_3_0(foveated, extra, p, grid, st);
+    case 7: return launch_band_3_1(foveated, extra, p, grid, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -29,7 +31,9 @@ cudaError_t configure_band_kernels() {
   if ((e = configure_band_1_0()) != cudaSuccess) return e;
   if ((e = configure_band_1_1()) != cudaSuccess) return e;
   if ((e = configure_band_2_0()) != cudaSuccess) return e;
-  return configure_band_2_1();
+  if ((e = configure_band_2_1()) != cudaSuccess) return e;
+  if ((e = configure_band_3_0()) != cudaSuccess) return e;
+  return configure_band_3_1();
 }
 
 }  // namespace fused

@@ -1,5 +1,5 @@
 // Instantiations of the fused band kernel.  Compiled once per (input kind, temporal mode) with
-// -DFUSED_KIND={0,1,2} -DFUSED_VIDEO={0,1} so that the six translation units build in parallel.
+// -DFUSED_KIND={0,1,2,3} (fused::InputKind) -DFUSED_VIDEO={0,1} so that the eight translation units build in parallel.
 #include "fvvdp_fused.cuh"
 #include "fvvdp_fused_launch.h"
 
@@ -10,8 +10,6 @@ namespace fused {
 #error "compile with -DFUSED_KIND and -DFUSED_VIDEO"
 #endif
 
-constexpr bool kLevel0 = (FUSED_KIND != 2);
-constexpr bool kContig = (FUSED_KIND == 0);
 constexpr int kFL = FUSED_VIDEO ? RING : 1;
 constexpr int kTC = FUSED_VIDEO ? 2 : 1;
 
@@ -22,11 +20,11 @@ constexpr int kTC = FUSED_VIDEO ? 2 : 1;
 cudaError_t FUSED_FN(launch_band_)(bool foveated, bool extra, const BandParams& p, dim3 grid, cudaStream_t st) {
   const size_t smem = band_smem_bytes<kFL, kTC>();
   if (foveated) {
-    if (extra) band_kernel<kLevel0, kContig, kFL, kTC, true, true><<<grid, NT, smem, st>>>(p);
-    else band_kernel<kLevel0, kContig, kFL, kTC, true, false><<<grid, NT, smem, st>>>(p);
+    if (extra) band_kernel<FUSED_KIND, kFL, kTC, true, true><<<grid, NT, smem, st>>>(p);
+    else band_kernel<FUSED_KIND, kFL, kTC, true, false><<<grid, NT, smem, st>>>(p);
   } else {
-    if (extra) band_kernel<kLevel0, kContig, kFL, kTC, false, true><<<grid, NT, smem, st>>>(p);
-    else band_kernel<kLevel0, kContig, kFL, kTC, false, false><<<grid, NT, smem, st>>>(p);
+    if (extra) band_kernel<FUSED_KIND, kFL, kTC, false, true><<<grid, NT, smem, st>>>(p);
+    else band_kernel<FUSED_KIND, kFL, kTC, false, false><<<grid, NT, smem, st>>>(p);
   }
   return cudaGetLastError();
 }
@@ -34,13 +32,13 @@ cudaError_t FUSED_FN(launch_band_)(bool foveated, bool extra, const BandParams& 
 cudaError_t FUSED_FN(configure_band_)() {
   const int smem = (int)band_smem_bytes<kFL, kTC>();
   cudaError_t e;
-  e = cudaFuncSetAttribute(band_kernel<kLevel0, kContig, kFL, kTC, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  e = cudaFuncSetAttribute(band_kernel<FUSED_KIND, kFL, kTC, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(band_kernel<kLevel0, kContig, kFL, kTC, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  e = cudaFuncSetAttribute(band_kernel<FUSED_KIND, kFL, kTC, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(band_kernel<kLevel0, kContig, kFL, kTC, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  e = cudaFuncSetAttribute(band_kernel<FUSED_KIND, kFL, kTC, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(band_kernel<kLevel0, kContig, kFL, kTC, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  return cudaFuncSetAttribute(band_kernel<FUSED_KIND, kFL, kTC, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 }  // namespace fused

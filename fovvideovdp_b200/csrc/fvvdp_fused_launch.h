@@ -5,7 +5,7 @@
 namespace fvvdp {
 namespace fused {
 struct BandParams;
-enum InputKind { IN_LEVEL0_CONTIG = 0, IN_LEVEL0_GENERIC = 1, IN_PYRAMID = 2 };
+// input_kind: fused::InputKind (fvvdp_fused.cuh)
 // video = 8-slot temporal ring, 2 temporal channels; image = single frame, 1 temporal channel
 cudaError_t launch_band(int input_kind, bool video, bool foveated, bool extra, const BandParams& p, dim3 grid, cudaStream_t st);
 cudaError_t configure_band_kernels();
