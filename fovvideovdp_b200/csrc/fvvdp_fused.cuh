@@ -166,20 +166,22 @@ __device__ __forceinline__ void tma_load_3d(float* dst, const CUtensorMap* map, 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ display EOTF
-// EOTF -> luminance for one sample (fvvdp_display_model.py:147-165, 203-212).  KIND is a compile-time fvvdp_b200_eotf;
-// the range of the raw values is tracked in vmin/vmax ("Pixel outside the valid range 0-1", :149-151).
+// EOTF -> luminance for one sample (fvvdp_display_model.py:147-165, 203-212).  KIND is a compile-time fvvdp_b200_eotf.
+// The callers track the range of the raw values in vmin/vmax ("Pixel outside the valid range 0-1", :149-151).
 template <int KIND>
-__device__ __forceinline__ float eotf_k(float v, const BandParams& p, float& vmin, float& vmax) {
+__device__ __forceinline__ float eotf_k(float v, const BandParams& p) {
   if (KIND == FVVDP_B200_EOTF_NONE) return v;
   if (KIND == FVVDP_B200_EOTF_ABSOLUTE) return fminf(fmaxf(v, p.L_min), p.L_max);
   if (KIND == FVVDP_B200_EOTF_LINEAR) return fminf(fmaxf(v, 0.005f), p.Y_peak) + p.Y_black;
-  vmin = fminf(vmin, v);
-  vmax = fmaxf(vmax, v);
-  v = __saturatef(v);
   if (KIND == FVVDP_B200_EOTF_SRGB) {
-    const float lin = (v > 0.04045f) ? fast_pow(fmaf(v, 1.0f / 1.055f, 0.055f / 1.055f), 2.4f) : v * (1.0f / 12.92f);
+    // clamp(v,0,1) folded into saturating arithmetic: (v + 0.055)/1.055 maps [0,1] into [0.052,1], and values below
+    // 0.04045 take the linear branch, so saturating the affine result / the linear product is the same clamp
+    const float t = __saturatef(fmaf(v, 1.0f / 1.055f, 0.055f / 1.055f));
+    const float lin = (v > 0.04045f) ? fast_exp2(2.4f * fast_log2(t)) : __saturatef(v * (1.0f / 12.92f));
     return fmaf(p.Yscale, lin, p.Y_black);
-  } else if (KIND == FVVDP_B200_EOTF_GAMMA) {
+  }
+  v = __saturatef(v);
+  if (KIND == FVVDP_B200_EOTF_GAMMA) {
     return fmaf(p.Yscale, fast_pow(v, p.gamma), p.Y_black);
   } else {  // PQ
     const float n_inv = 1.0f / 0.15930175781250000f, m_inv = 1.0f / 78.843750000000000f;
@@ -189,15 +191,21 @@ __device__ __forceinline__ float eotf_k(float v, const BandParams& p, float& vmi
     return fminf(fmaxf(L, 0.005f), p.Y_peak) + p.Y_black;
   }
 }
+// EOTFs that expect display-encoded values in [0,1] and report anything outside ("Pixel outside the valid range 0-1")
+__device__ __forceinline__ bool eotf_checks_range(int kind) {
+  return kind == FVVDP_B200_EOTF_SRGB || kind == FVVDP_B200_EOTF_GAMMA || kind == FVVDP_B200_EOTF_PQ;
+}
 
 __device__ __forceinline__ float eotf_one(float v, const BandParams& p, float& vmin, float& vmax) {
+  vmin = fminf(vmin, v);
+  vmax = fmaxf(vmax, v);
   switch (p.eotf) {
     case FVVDP_B200_EOTF_NONE: return v;
-    case FVVDP_B200_EOTF_ABSOLUTE: return eotf_k<FVVDP_B200_EOTF_ABSOLUTE>(v, p, vmin, vmax);
-    case FVVDP_B200_EOTF_LINEAR: return eotf_k<FVVDP_B200_EOTF_LINEAR>(v, p, vmin, vmax);
-    case FVVDP_B200_EOTF_SRGB: return eotf_k<FVVDP_B200_EOTF_SRGB>(v, p, vmin, vmax);
-    case FVVDP_B200_EOTF_GAMMA: return eotf_k<FVVDP_B200_EOTF_GAMMA>(v, p, vmin, vmax);
-    default: return eotf_k<FVVDP_B200_EOTF_PQ>(v, p, vmin, vmax);
+    case FVVDP_B200_EOTF_ABSOLUTE: return eotf_k<FVVDP_B200_EOTF_ABSOLUTE>(v, p);
+    case FVVDP_B200_EOTF_LINEAR: return eotf_k<FVVDP_B200_EOTF_LINEAR>(v, p);
+    case FVVDP_B200_EOTF_SRGB: return eotf_k<FVVDP_B200_EOTF_SRGB>(v, p);
+    case FVVDP_B200_EOTF_GAMMA: return eotf_k<FVVDP_B200_EOTF_GAMMA>(v, p);
+    default: return eotf_k<FVVDP_B200_EOTF_PQ>(v, p);
   }
 }
 
@@ -221,8 +229,9 @@ __device__ __forceinline__ void eotf_chunks(float* dst, const int (&ld_soff)[NLD
     if (ld_soff[i] >= 0 && ld_goff[i] >= 0) {
       float4* q = reinterpret_cast<float4*>(dst + (ld_soff[i] & 0xFFFFFF));
       float4 v = *q;
-      v.x = eotf_k<KIND>(v.x, p, vmin, vmax); v.y = eotf_k<KIND>(v.y, p, vmin, vmax);
-      v.z = eotf_k<KIND>(v.z, p, vmin, vmax); v.w = eotf_k<KIND>(v.w, p, vmin, vmax);
+      vmin = fminf(vmin, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));  // 3-input min/max on sm_100
+      vmax = fmaxf(vmax, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+      v.x = eotf_k<KIND>(v.x, p); v.y = eotf_k<KIND>(v.y, p); v.z = eotf_k<KIND>(v.z, p); v.w = eotf_k<KIND>(v.w, p);
       *q = v;
     }
   }
@@ -382,6 +391,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
   const float K0 = 0.05f, K1 = 0.25f, K2 = 0.4f, K3 = 0.25f, K4 = 0.05f;
   const bool rows_interior = (jy0 - 1 >= 1) && (jy0 + TH / 2 <= h2 - 2);
   const bool cols_interior = (jx0 - 1 >= 1) && (jx0 + TW / 2 <= w2 - 2);
+  const bool tile_full = (ty0 + TH <= h) && (tx0 + TW <= w);
 
   // stage the tile of `slot` into buffer `buf`
   auto issue_load = [&](int slot, int buf) {
@@ -555,9 +565,9 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
           lgL[e] = fast_log2(Lb[e]);
           const float yq = fminf(lgL[e], p.lg_y_hi);
           if (!FOV) {
-            cj[e] = min(max((int)((yq - p.y0) * p.inv_dy), 0), 30);
-            const float2 xi = *reinterpret_cast<const float2*>(sTab + cj[e] * 8);
-            fj[e] = fmaxf((yq - xi.x) * xi.y, 0.0f);
+            cj[e] = min((int)((yq - p.y0) * p.inv_dy), 30) * 8;  // L_bkg >= 0.1 lies above the first axis point: no lower clamp
+            const float2 xi = *reinterpret_cast<const float2*>(sTab + cj[e]);
+            fj[e] = (yq - xi.x) * xi.y;
           } else {
             const int x = qx + (e & 1), y = qy + (e >> 1);
             int jj, ii, kk;
@@ -588,7 +598,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
       for (int e = 0; e < 4; ++e) {
         float lS;  // log2 of (sensitivity x sensitivity_correction)
         if (!FOV) {
-          const float2 td = *reinterpret_cast<const float2*>(sTab + cj[e] * 8 + 2 + 2 * cc);
+          const float2 td = *reinterpret_cast<const float2*>(sTab + cj[e] + 2 + 2 * cc);
           lS = fmaf(fj[e], td.y, td.x);
         } else {
           lS = lsf[cc][e];
@@ -597,7 +607,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
         const float lim = 1000.0f * Lb[e];
         const float bT = fminf(B[0][e], lim), bR = fminf(B[1][e], lim);
         const float lSL = lS + (p.log2_m - lgL[e]);
-        const float ld = fast_log2(valid[e] ? fabsf(bT - bR) : 0.0f) + lSL;               // log2 |T' - R'|
+        const float ld = fast_log2((tile_full || valid[e]) ? fabsf(bT - bR) : 0.0f) + lSL;  // log2 |T' - R'|
         const float lM = fast_log2(fminf(fabsf(bT), fabsf(bR))) + (lSL + p.log2_mask_c);  // log2 M  (:588)
         const float Mq = fast_exp2(p.mask_q[cc] * lM);
         const float lD = fminf(fmaf(p.mask_p, ld, -fast_log2(1.0f + Mq)), 13.287712379549449f);  // D <= 1e4 (:593-595)
@@ -632,13 +642,14 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
           p.tapG[(((long long)fi * NCH + cc * 2 + st) * h2 + j) * w2 + ii] = sNc[o];
       }
     }
-    // ---- per-frame partial sums: warp shuffle now, one pass over the warps at the end ----
+    // ---- per-frame partial sums: warp shuffle now, one pass over the warps at the end.  The two channel sums share
+    //      the butterfly: after the first exchange the lower half-warp carries channel 0, the upper half channel 1.
+    {
+      const bool up = lane >= 16;
+      float v = (up ? acc[1] : acc[0]) + __shfl_xor_sync(0xffffffffu, up ? acc[0] : acc[1], 16);
 #pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-      float v = acc[cc];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) sRed[((fi - f_lo) * 2 + cc) * (NT / 32) + warp] = v;
+      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((lane & 15) == 0) sRed[((fi - f_lo) * 2 + (up ? 1 : 0)) * (NT / 32) + warp] = v;
     }
   }
   __syncthreads();
@@ -649,7 +660,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
     const int fi = f_lo + (i >> 1), cc = i & 1;
     p.partial[((long long)fi * 2 + cc) * p.ntiles + tile] = v;
   }
-  if (LEVEL0 && (vmin < 0.0f || vmax > 1.0f) && p.flags) atomicOr(p.flags, 1u);
+  if (LEVEL0 && eotf_checks_range(p.eotf) && (vmin < 0.0f || vmax > 1.0f) && p.flags) atomicOr(p.flags, 1u);
 }
 
 template <int FL, int TC>
