@@ -15,7 +15,7 @@ UNITS = [("fvvdp_b200", "fvvdp_b200.cu", []), ("fused_dispatch", "fvvdp_fused_di
     [(f"fused_{k}_{v}", "fvvdp_fused_inst.cu", [f"-DFUSED_KIND={k}", f"-DFUSED_VIDEO={v}"]) for k in range(4) for v in range(2)]
 DEPS = HEADERS + [os.path.join(CSRC, u[1]) for u in UNITS]
 OBJ_DIR = os.path.join(PKG, "_lib", "obj")
-LIB = os.path.join(PKG, "_lib", "libfvvdp_b200.so")
+LIB = os.environ.get("FVVDP_B200_LIB") or os.path.join(PKG, "_lib", "libfvvdp_b200.so")  # override: experiment builds
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
@@ -28,6 +28,8 @@ def nvcc_path():
 
 
 def is_stale():
+    if os.environ.get("FVVDP_B200_LIB"):
+        return False
     if not os.path.isfile(LIB):
         return True
     t = os.path.getmtime(LIB)

@@ -224,17 +224,52 @@ __device__ __forceinline__ float lum_generic(const BandParams& p, const void* ba
 template <int KIND>
 __device__ __forceinline__ void eotf_chunks(float* dst, const int (&ld_soff)[NLD], const int (&ld_goff)[NLD], const BandParams& p, float& vmin,
                                             float& vmax) {
+  // all loads first, then the arithmetic of all 16 samples, then all stores: written as one load-convert-store per
+  // chunk the stores could alias the next load and the chunks would serialise
+  float4 v[NLD];
+  bool ok[NLD];
 #pragma unroll
   for (int i = 0; i < NLD; ++i) {
-    if (ld_soff[i] >= 0 && ld_goff[i] >= 0) {
-      float4* q = reinterpret_cast<float4*>(dst + (ld_soff[i] & 0xFFFFFF));
-      float4 v = *q;
-      vmin = fminf(vmin, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));  // 3-input min/max on sm_100
-      vmax = fmaxf(vmax, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
-      v.x = eotf_k<KIND>(v.x, p); v.y = eotf_k<KIND>(v.y, p); v.z = eotf_k<KIND>(v.z, p); v.w = eotf_k<KIND>(v.w, p);
-      *q = v;
+    ok[i] = ld_soff[i] >= 0 && ld_goff[i] >= 0;
+    if (ok[i]) v[i] = *reinterpret_cast<const float4*>(dst + (ld_soff[i] & 0xFFFFFF));
+    else v[i] = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+  }
+#pragma unroll
+  for (int i = 0; i < NLD; ++i) {
+    vmin = fminf(vmin, fminf(fminf(v[i].x, v[i].y), fminf(v[i].z, v[i].w)));  // 3-input min/max on sm_100
+    vmax = fmaxf(vmax, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+  }
+  if (KIND == FVVDP_B200_EOTF_SRGB || KIND == FVVDP_B200_EOTF_GAMMA) {
+    // stage-wise over the 16 samples with volatile MUFU ops: all lg2 back to back, then all ex2.  Left to itself the
+    // compiler predicates the MUFU pair of every sample on its own (v > 0.04045) test and serialises the 16 chains.
+    float* x = reinterpret_cast<float*>(v);
+    float t[4 * NLD];
+    const float gam = KIND == FVVDP_B200_EOTF_SRGB ? 2.4f : p.gamma;
+#pragma unroll
+    for (int j = 0; j < 4 * NLD; ++j) {
+      const float a = KIND == FVVDP_B200_EOTF_SRGB ? __saturatef(fmaf(x[j], 1.0f / 1.055f, 0.055f / 1.055f)) : __saturatef(x[j]);
+      asm volatile("lg2.approx.ftz.f32 %0, %1;" : "=f"(t[j]) : "f"(a));
+    }
+#pragma unroll
+    for (int j = 0; j < 4 * NLD; ++j) {
+      const float a = t[j] * gam;
+      asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(t[j]) : "f"(a));
+    }
+#pragma unroll
+    for (int j = 0; j < 4 * NLD; ++j) {
+      float lin = t[j];
+      if (KIND == FVVDP_B200_EOTF_SRGB) lin = (x[j] > 0.04045f) ? lin : __saturatef(x[j] * (1.0f / 12.92f));
+      x[j] = fmaf(p.Yscale, lin, p.Y_black);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+      v[i].x = eotf_k<KIND>(v[i].x, p); v[i].y = eotf_k<KIND>(v[i].y, p); v[i].z = eotf_k<KIND>(v[i].z, p); v[i].w = eotf_k<KIND>(v[i].w, p);
     }
   }
+#pragma unroll
+  for (int i = 0; i < NLD; ++i)
+    if (ok[i]) *reinterpret_cast<float4*>(dst + (ld_soff[i] & 0xFFFFFF)) = v[i];
 }
 
 // cell of a 32-point (nearly uniform) axis containing q, and the reference's interpolation fraction
