@@ -108,6 +108,10 @@ class _FrameSet:
             v = tv[0, :, 0]
             if self.resident and self.same_layout:
                 self.strides = tuple(v.stride())
+                # frame k of a resident clip sits at base + k * frame stride: pointers by arithmetic, no tensor views
+                self._base = (tv.data_ptr(), rv.data_ptr())
+                self._frame_bytes = tv.stride(2) * tv.element_size()
+                self._n_local = tv.shape[2]
             else:
                 self._order = sorted(range(3), key=lambda d: -v.stride(d))
                 vp = v.permute(self._order)
@@ -136,7 +140,9 @@ class _FrameSet:
             tv, rv = self.vs.test_video, self.vs.reference_video
             k = self.vs.local_index(idx) if hasattr(self.vs, "local_index") else idx
             if self.resident:
-                self.held[idx] = (tv[0, :, k], rv[0, :, k])
+                if k < 0 or k >= self._n_local:
+                    raise RuntimeError(f"frame {idx} is not held by this process")
+                self.held[idx] = k
             else:
                 self.held[idx] = (self._upload(tv[0, :, k]), self._upload(rv[0, :, k]))
         else:
@@ -149,10 +155,16 @@ class _FrameSet:
                 self.strides = (0, t.stride(0), t.stride(1))
 
     def pointers(self, idx):
+        if self.raw and self.resident:
+            off = self.held[idx] * self._frame_bytes
+            return self._base[0] + off, self._base[1] + off
         t, r = self.held[idx]
         return t.data_ptr(), r.data_ptr()
 
     def retain_only(self, keep):
+        if self.raw and self.resident:
+            self.held.clear()
+            return
         for idx in [k for k in self.held if k not in keep]:
             t, r = self.held.pop(idx)
             if self.raw and not self.resident:
