@@ -24,6 +24,7 @@ from .video_source import fvvdp_video_source_array, is_array_source
 
 _DTYPES = {torch.float32: _native.DTYPE_F32, torch.uint8: _native.DTYPE_U8, torch.int16: _native.DTYPE_U16}
 _WORKSPACE_BUDGET_BYTES = 16e9  # device memory a scoring context may take for its per-block pyramids
+_HOST_BLOCK_FRAMES = 8          # clips in host memory: frames per block, so that uploads and kernels overlap block by block
 
 
 def pyramid_layout(width, height, ppd):
@@ -94,8 +95,9 @@ class _FrameSet:
         self.device = device
         self.raw = raw
         self.held = {}      # frame index -> (test tensor, ref tensor) on the device
-        self.free = []      # recycled upload buffers
+        self.free = []      # recycled upload buffers: (buffer, event after which the kernels no longer read it), oldest first
         self.h2d_bytes = 0
+        self.up_stream = None   # host-resident array sources: uploads run on their own stream, one block ahead of the kernels
         if raw:
             tv, rv = vid_source.test_video, vid_source.reference_video
             if tv.shape[0] != 1:
@@ -123,15 +125,32 @@ class _FrameSet:
                 self._inv = inv
                 self.strides = tuple(torch.empty(self._buf_shape, dtype=self.dtype, device="meta").permute(inv).stride())
                 self.resident = False
+                self.up_stream = torch.cuda.Stream(device=device)
         else:
             self.dtype = torch.float32
             self.strides = None
 
     def _upload(self, src):
-        buf = self.free.pop() if self.free else torch.empty(self._buf_shape, dtype=self.dtype, device=self.device)
-        buf.copy_(src.permute(self._order), non_blocking=True)
+        if self.free:
+            buf, reusable = self.free.pop(0)
+            if reusable is not None:
+                self.up_stream.wait_event(reusable)  # the block that read this buffer last has been scored
+        else:
+            buf = torch.empty(self._buf_shape, dtype=self.dtype, device=self.device)
+            # the allocator may hand out memory that work queued on the current stream still reads
+            self.up_stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.up_stream):
+            buf.copy_(src.permute(self._order), non_blocking=True)
         self.h2d_bytes += buf.numel() * buf.element_size()
         return buf
+
+    def uploaded(self):
+        """Event on the upload stream after everything fetched so far (None when nothing is uploaded asynchronously)."""
+        if self.up_stream is None:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self.up_stream)
+        return ev
 
     def fetch(self, idx):
         if idx in self.held:
@@ -161,14 +180,15 @@ class _FrameSet:
         t, r = self.held[idx]
         return t.data_ptr(), r.data_ptr()
 
-    def retain_only(self, keep):
+    def retain_only(self, keep, scored=None):
+        """Drop every held frame that is not in `keep`; `scored` = event after the kernels that read them."""
         if self.raw and self.resident:
             self.held.clear()
             return
         for idx in [k for k in self.held if k not in keep]:
             t, r = self.held.pop(idx)
             if self.raw and not self.resident:
-                self.free.extend((t, r))
+                self.free.extend(((t, scored), (r, scored)))
 
 
 class fvvdp:
@@ -355,6 +375,8 @@ class fvvdp:
 
         per_frame_bytes = 4.0 * (2 * temp_ch) * height * width * 4.0 / 3.0 * (3.0 if self.debug_taps else 1.0)
         T = self.block_frames or int(max(1, min(_native.MAX_BLOCK_FRAMES, _WORKSPACE_BUDGET_BYTES // per_frame_bytes)))
+        if frames.up_stream is not None and not self.block_frames and not self.debug_taps:
+            T = min(T, _HOST_BLOCK_FRAMES)
         T = max(1, min(T, _native.MAX_BLOCK_FRAMES, f_end - f_begin))
 
         geo = self.display_geometry
@@ -375,13 +397,30 @@ class fvvdp:
         def frame_at(t):  # frame shown at time t (t <= 0 falls into the temporal padding)
             return t if t >= 1 else first[fl - 1 + t]
 
+        def block_slots(f0):
+            n = min(T, f_end - f0)
+            return n, [frame_at(f0 - (fl - 1) + s) for s in range(n + fl - 1)]
+
+        def prefetch(f0):  # frames of the block starting at f0 -> device (host sources: on the upload stream)
+            for idx in block_slots(f0)[1]:
+                frames.fetch(idx)
+            return frames.uploaded()
+
         launches0 = ctx.launch_count()
         with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream(dev)
+            ahead = frames.up_stream is not None
+            ready = prefetch(f_begin) if ahead else None
             for f0 in range(f_begin, f_end, T):
-                n = min(T, f_end - f0)
-                slots = [frame_at(f0 - (fl - 1) + s) for s in range(n + fl - 1)]
-                for idx in slots:
-                    frames.fetch(idx)
+                n, slots = block_slots(f0)
+                nxt = f0 + n
+                if not ahead:
+                    prefetch(f0)
+                # host-resident clips: the next block's uploads are queued before this block's kernels; they only take
+                # buffers that were released before this block, so they run while this block is scored
+                ready_next = prefetch(nxt) if (ahead and nxt < f_end) else None
+                if ready is not None:
+                    cur.wait_event(ready)
                 ptrs = [frames.pointers(idx) for idx in slots]
                 fix = None
                 if self.foveated:
@@ -393,9 +432,12 @@ class fvvdp:
                     for i in range(n):
                         ctx.heatmap(i, beta_jod, abs(self.jod_a), hm_dev.data_ptr(), stream)
                         heatmap[0, 0, f0 + i].copy_(hm_dev)
-                nxt = f0 + n
-                keep = set(frame_at(nxt - (fl - 1) + s) for s in range(fl - 1)) if nxt < f_end else set()
-                frames.retain_only(keep)
+                scored = None
+                if frames.up_stream is not None:
+                    scored = torch.cuda.Event()
+                    scored.record(cur)
+                frames.retain_only(set(block_slots(nxt)[1]) if nxt < f_end else set(), scored)
+                ready = ready_next
             if world > 1:
                 torch.distributed.all_reduce(Q_per_ch)  # every column has exactly one non-zero contributor
             out = torch.empty(2, dtype=torch.float32, device=dev)
