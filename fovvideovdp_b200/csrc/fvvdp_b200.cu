@@ -23,10 +23,10 @@ struct fvvdp_b200_ctx {
   int lh[FVVDP_B200_MAX_LEVELS], lw[FVVDP_B200_MAX_LEVELS];
   int tiles_x[FVVDP_B200_MAX_LEVELS], tiles_y[FVVDP_B200_MAX_LEVELS];
   bool fused = false;                          // fused band kernels (filter_len <= 8) or the general v1 path
-  float* P[FVVDP_B200_MAX_LEVELS] = {};        // fused: luminance pyramid planes, level >= 1: [slots][2][h_l][pitch_l]
+  float* P[FVVDP_B200_MAX_LEVELS] = {};        // fused: luminance pyramid, level >= 1: [slots][h_l][pitch_l], (test, ref) interleaved
   int pitch[FVVDP_B200_MAX_LEVELS] = {};
   float* cell = nullptr;                       // fused: [n_bands][32][8] CSF cells over log2 Y
-  CUtensorMap pmap[FVVDP_B200_MAX_LEVELS];     // fused: TMA descriptors of P[l] (x, y, stream, slot), box = staged tile
+  CUtensorMap pmap[FVVDP_B200_MAX_LEVELS];     // fused: TMA descriptors of P[l] (2x + stream, y, slot), box = staged tile
   float* G[FVVDP_B200_MAX_LEVELS] = {};        // v1 (and taps): G[0] = R; [T][nch][h_l][w_l]
   float* partial[FVVDP_B200_MAX_LEVELS] = {};  // [T][2][ntiles_l]
   float* tapC[FVVDP_B200_MAX_LEVELS] = {};
@@ -108,11 +108,11 @@ static encode_tiled_fn get_encode_tiled() {
   }
   return fn;
 }
-// float tensor of `rank` dims (dims[0] innermost, strides in bytes for dims 1..), box = staged tile (LW x LH x box2 x 1), zero fill outside
-static bool make_tile_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, int box2) {
+// 3-D float tensor (dims[0] innermost, strides in bytes for dims 1..), box = staged tile (box0 x LH x 1), zero fill outside
+static bool make_tile_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, int box0) {
   encode_tiled_fn fn = get_encode_tiled();
   if (!fn) return false;
-  cuuint32_t box[4] = {(cuuint32_t)fused::LW, (cuuint32_t)fused::LH, (cuuint32_t)box2, 1};
+  cuuint32_t box[4] = {(cuuint32_t)box0, (cuuint32_t)fused::LH, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -176,7 +176,7 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
   for (int l = 0; l < cfg->n_levels; ++l) {
     c->lh[l] = hh; c->lw[l] = ww;
     c->tiles_x[l] = (ww + tile_w - 1) / tile_w; c->tiles_y[l] = (hh + tile_h - 1) / tile_h;
-    c->pitch[l] = (ww + 3) & ~3;
+    c->pitch[l] = (2 * ww + 3) & ~3;  // floats per row of the interleaved (test, ref) pyramid planes
     hh = (hh + 1) / 2; ww = (ww + 1) / 2;
   }
   for (int l = 0; l < cfg->n_levels; ++l) {
@@ -185,12 +185,12 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
     if (l < c->n_bands && (!c->fused || cfg->want_taps)) CUC(cudaMalloc(&c->G[l], sizeof(float) * px * nch * T));
     // fused: 2-plane luminance pyramid per window slot; the row padding must stay zero (it is read as zero padding)
     if (c->fused && l >= 1 && l < c->n_bands) {
-      const size_t n = (size_t)(T + cfg->filter_len - 1) * 2 * c->lh[l] * c->pitch[l];
+      const size_t n = (size_t)(T + cfg->filter_len - 1) * c->lh[l] * c->pitch[l];
       CUC(cudaMalloc(&c->P[l], sizeof(float) * n));
       CUC(cudaMemset(c->P[l], 0, sizeof(float) * n));
-      const cuuint64_t dims[4] = {(cuuint64_t)c->lw[l], (cuuint64_t)c->lh[l], 2, (cuuint64_t)(T + cfg->filter_len - 1)};
-      const cuuint64_t str[3] = {(cuuint64_t)c->pitch[l] * 4, (cuuint64_t)c->lh[l] * c->pitch[l] * 4, 2ull * c->lh[l] * c->pitch[l] * 4};
-      if (!make_tile_map(&c->pmap[l], c->P[l], 4, dims, str, 2)) {
+      const cuuint64_t dims[3] = {(cuuint64_t)(2 * c->lw[l]), (cuuint64_t)c->lh[l], (cuuint64_t)(T + cfg->filter_len - 1)};
+      const cuuint64_t str[2] = {(cuuint64_t)c->pitch[l] * 4, (cuuint64_t)c->lh[l] * c->pitch[l] * 4};
+      if (!make_tile_map(&c->pmap[l], c->P[l], 3, dims, str, 2 * fused::LW)) {
         fail(nullptr, FVVDP_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed for pyramid level %d", l);
         free_ctx(c);
         return FVVDP_B200_ERR_CUDA;
@@ -433,7 +433,7 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
         if (l0_tma) {
           const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)((hi - lo) / g + 1)};
           const cuuint64_t str[2] = {(cuuint64_t)strides[1] * 4, (cuuint64_t)g};
-          if (!make_tile_map(&bp.tmap[st], (const void*)lo, 3, dims, str, 1)) l0_tma = false;
+          if (!make_tile_map(&bp.tmap[st], (const void*)lo, 3, dims, str, fused::LW)) l0_tma = false;
         }
       }
       (void)base; (void)step;
@@ -463,12 +463,9 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
     }
     const bool extra = cfg.want_taps || cfg.want_dmap;
     for (int l = 0; l < ctx->n_bands; ++l) {
-      bp.P = l >= 1 ? ctx->P[l] : nullptr;
-      bp.pitch = ctx->pitch[l];
-      bp.P_slot_stride = 2ll * ctx->lh[l] * ctx->pitch[l];
       bp.Pn = (l + 1 < ctx->n_bands) ? ctx->P[l + 1] : nullptr;
       bp.pitch2 = ctx->pitch[l + 1];
-      bp.Pn_slot_stride = 2ll * ctx->lh[l + 1] * ctx->pitch[l + 1];
+      bp.Pn_slot_stride = (long long)ctx->lh[l + 1] * ctx->pitch[l + 1];
       bp.partial = ctx->partial[l];
       bp.h = ctx->lh[l]; bp.w = ctx->lw[l]; bp.h2 = ctx->lh[l + 1]; bp.w2 = ctx->lw[l + 1];
       bp.h_odd = bp.h & 1;
@@ -625,7 +622,7 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
   }
   if (ctx->fused) {  // inputs once per window slot + write and read-back of the 2-plane luminance pyramid
     plan = 2.0 * P0 * cfg.in_channels * esz * n_slots;
-    for (int l = 1; l < ctx->n_bands; ++l) plan += 2.0 * 4.0 * 2.0 * n_slots * (double)ctx->lh[l] * ctx->pitch[l];
+    for (int l = 1; l < ctx->n_bands; ++l) plan += 2.0 * 4.0 * n_slots * (double)ctx->lh[l] * ctx->pitch[l];
   }
   ctx->bytes_plan = plan;
   return FVVDP_B200_OK;

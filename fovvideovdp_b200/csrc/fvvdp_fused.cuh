@@ -1,8 +1,8 @@
 // Fused band kernel of the B200-native FovVideoVDP core (sm_100a): ONE kernel per pyramid level that
-//   * stages the level's luminance tile (+4 px halo) of the NEXT frame into shared memory while the current one is
+//   * stages the level's luminance tile (+4 px halo) of the NEXT frames into shared memory while the current one is
 //     processed: TMA (cp.async.bulk.tensor, zero fill outside the image, mbarrier completion) for the pyramid levels and
 //     for contiguous float input frames, cp.async / plain loads for everything else (uint8, RGB, strided);
-//     level 0 applies the display EOTF in shared memory,
+//     level 0 applies the display EOTF on the way from the landing buffer to the luminance tile,
 //   * reduces the tile to the next Gaussian level (separable 5-tap, stride 2; fvvdp_lpyr_dec.py:183-207) and writes that
 //     level out for the next launch,
 //   * keeps the last `fl` frames of both streams ON CHIP while it walks through time: the tile's own pixels in a
@@ -13,12 +13,12 @@
 //
 // The reference filters in time first and then builds one pyramid per temporal channel (4 channels).  Reduce and
 // expand are linear, so  pyr(sum_k w_k L_{t-k}) = sum_k w_k pyr(L_{t-k}):  here the pyramid is built ONCE per
-// luminance frame and stream (2 planes) and the temporal filter is applied to its levels.  Per frame pair this moves
-// 2 input planes + 2 planes per coarser level through HBM instead of the 4-channel R tensor and 4-channel levels.
+// luminance frame and stream and the temporal filter is applied to its levels.
 //
-// The kernel is bound by instruction issue, not by HBM, so the arithmetic uses Blackwell's packed
-// fp32x2 instructions (fma/add/mul.rn.f32x2 -> FFMA2/FADD2/FMUL2) wherever two lanes share an operation: pixel pairs
-// in the temporal filter, (test, reference) pairs in the expand.
+// Data layout: everything after the EOTF is a (test, reference) PAIR of floats per pixel -- the luminance tile, the
+// row-reduced tile, both rings, the pyramid planes in HBM ([slot][row][2 * column + stream]).  The kernel is bound by
+// instruction issue, not by HBM, and both streams go through exactly the same stencils and filters, so
+// one packed fp32x2 instruction (fma/add/mul.rn.f32x2 -> FFMA2/FADD2/FMUL2) does the work of two.
 //
 // Border semantics follow the reference exactly: zero padding + additive edge terms for the reduce (including the
 // row-parity quirk of fvvdp_lpyr_dec.py:202), index clamping for the expand.
@@ -37,28 +37,29 @@ constexpr int NE = NH * NW;                     // 340
 constexpr int NT = 256;                         // threads: one 2x2 quad each
 constexpr int RING = 8;                         // temporal window kept on chip
 constexpr int MAXCHUNK = 64;                    // output frames walked by one CTA
-constexpr int LV4 = LW / 4;                     // 16-byte chunks per staged row
-constexpr int NLD = (2 * LH * LV4 + NT - 1) / NT;  // 16-byte chunks per thread and frame (4)
-constexpr int NCOL = (2 * NE + NT - 1) / NT;       // column-pass outputs per thread (3)
-constexpr int TILE_FLOATS = 2 * LH * LW;           // one staged buffer: [stream][LH][LW]
+constexpr int LV4 = LW / 4;                     // 4-pixel chunks per staged row
+constexpr int NPC = LH * LV4;                   // 4-pixel position chunks of a staged tile (432)
+constexpr int NLD = (NPC + NT - 1) / NT;        // position chunks per thread and frame (2; the second round is ragged)
+constexpr int NCOL = (NE + NT - 1) / NT;        // column-pass outputs ((test, ref) pairs) per thread (2)
+constexpr int PLANE = LH * LW;                  // one stream of a landing buffer
+constexpr int TILE_FLOATS = 2 * PLANE;          // one staged tile, both streams
+constexpr int ROW_SEGS = 3;                     // row pass: the NH coarse rows are split 4 + 3 + 3 over three threads per column
+constexpr int ROW_THREADS = ROW_SEGS * LW;      // 216
 
-typedef unsigned long long u64;  // two packed floats (lo, hi)
+typedef unsigned long long u64;  // two packed floats (lo = test, hi = reference)
 
 enum InputKind { IN_LEVEL0_CPASYNC = 0, IN_LEVEL0_GENERIC = 1, IN_PYRAMID_TMA = 2, IN_LEVEL0_TMA = 3 };
 
 struct BandParams {
-  // ---- TMA descriptors: [0] pyramid planes (4-D: x, y, stream, slot) or level-0 test frames (3-D: x, y, frame); [1] level-0 reference frames
+  // ---- TMA descriptors: [0] pyramid planes (3-D: 2x+stream, y, slot) or level-0 test frames (3-D: x, y, frame); [1] level-0 reference frames
   CUtensorMap tmap[2];
   // ---- input ----
   const void* slot[2][FVVDP_B200_MAX_SLOTS];   // level 0 without TMA: [test|ref][slot] frame base pointers
   unsigned short slot_frame[2][FVVDP_B200_MAX_SLOTS];  // level 0 with TMA: frame coordinate of each slot
-  const float* P;                             // level >= 1: luminance pyramid planes [slot][2][h][pitch]
-  long long P_slot_stride;                    // floats between slots (= 2 * h * pitch)
-  int pitch;                                  // row pitch of P in floats (multiple of 4)
   // ---- output ----
-  float* Pn;                                  // [slot][2][h2][pitch2] or nullptr (last scored band)
-  long long Pn_slot_stride;
-  int pitch2;
+  float* Pn;                                  // next level: [slot][h2][pitch2] floats, (test, ref) interleaved, or nullptr (last scored band)
+  long long Pn_slot_stride;                   // floats between slots (= h2 * pitch2)
+  int pitch2;                                 // row pitch of Pn in floats (multiple of 4, >= 2 * w2)
   float* partial;                             // [n_frames][2][ntiles]
   // ---- geometry / schedule ----
   int h, w, h2, w2, h_odd, ntiles;
@@ -125,45 +126,50 @@ __device__ __forceinline__ u64 fadd2(u64 a, u64 b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+// separable 5-tap [.05 .25 .4 .25 .05] on pairs, in the operation order of the scalar fmaf(K0, g0+g4, fmaf(K1, g1+g3, K2*g2))
+__device__ __forceinline__ u64 tap5(u64 g0, u64 g1, u64 g2, u64 g3, u64 g4) {
+  const u64 k0 = pk(0.05f, 0.05f), k1 = pk(0.25f, 0.25f), k2 = pk(0.4f, 0.4f);
+  return ffma2(k0, fadd2(g0, g4), ffma2(k1, fadd2(g1, g3), fmul2(k2, g2)));
+}
 
-// ------------------------------------------------------------------------------------------------ async copies
+// ------------------------------------------------------------------------------------------------ shared memory / async copies
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds128(unsigned a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(unsigned a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
 
-__device__ __forceinline__ void cp_async16(float* smem_dst, const void* gsrc, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+__device__ __forceinline__ void cp_async16(unsigned smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+  asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_init(u64* bar, int count) {
-  asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(u64* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64* bar, unsigned parity) {
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "FVVDP_WAIT:\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra FVVDP_DONE;\n\t"
       "bra FVVDP_WAIT;\n\t"
-      "FVVDP_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      "FVVDP_DONE:\n\t}" ::"r"(bar), "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(float* dst, const CUtensorMap* map, u64* bar, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-                   smem_u32(dst)),
-               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(float* dst, const CUtensorMap* map, u64* bar, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-                   smem_u32(dst)),
-               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ display EOTF
 // EOTF -> luminance for one sample (fvvdp_display_model.py:147-165, 203-212).  KIND is a compile-time fvvdp_b200_eotf.
@@ -220,56 +226,52 @@ __device__ __forceinline__ float lum_generic(const BandParams& p, const void* ba
   return eotf_one(load_sample(base, off, p.dtype), p, vmin, vmax);
 }
 
-// in-place EOTF of this thread's 16-byte chunks of the staged tile (level 0, contiguous float input)
+// EOTF of 8 raw samples in place (4 pixels of the test stream, 4 of the reference stream)
 template <int KIND>
-__device__ __forceinline__ void eotf_chunks(float* dst, const int (&ld_soff)[NLD], const int (&ld_goff)[NLD], const BandParams& p, float& vmin,
-                                            float& vmax) {
-  // all loads first, then the arithmetic of all 16 samples, then all stores: written as one load-convert-store per
-  // chunk the stores could alias the next load and the chunks would serialise
-  float4 v[NLD];
-  bool ok[NLD];
-#pragma unroll
-  for (int i = 0; i < NLD; ++i) {
-    ok[i] = ld_soff[i] >= 0 && ld_goff[i] >= 0;
-    if (ok[i]) v[i] = *reinterpret_cast<const float4*>(dst + (ld_soff[i] & 0xFFFFFF));
-    else v[i] = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
-  }
-#pragma unroll
-  for (int i = 0; i < NLD; ++i) {
-    vmin = fminf(vmin, fminf(fminf(v[i].x, v[i].y), fminf(v[i].z, v[i].w)));  // 3-input min/max on sm_100
-    vmax = fmaxf(vmax, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
-  }
+__device__ __forceinline__ void eotf8(float (&x)[8], const BandParams& p) {
+  if (KIND == FVVDP_B200_EOTF_NONE) return;
   if (KIND == FVVDP_B200_EOTF_SRGB || KIND == FVVDP_B200_EOTF_GAMMA) {
-    // stage-wise over the 16 samples with volatile MUFU ops: all lg2 back to back, then all ex2.  Left to itself the
-    // compiler predicates the MUFU pair of every sample on its own (v > 0.04045) test and serialises the 16 chains.
-    float* x = reinterpret_cast<float*>(v);
-    float t[4 * NLD];
+    // stage-wise with volatile MUFU ops: all lg2 back to back, then all ex2.  Left to itself the compiler predicates
+    // the MUFU pair of every sample on its own (v > 0.04045) test and serialises the chains.
+    float t[8];
     const float gam = KIND == FVVDP_B200_EOTF_SRGB ? 2.4f : p.gamma;
 #pragma unroll
-    for (int j = 0; j < 4 * NLD; ++j) {
+    for (int j = 0; j < 8; ++j) {
       const float a = KIND == FVVDP_B200_EOTF_SRGB ? __saturatef(fmaf(x[j], 1.0f / 1.055f, 0.055f / 1.055f)) : __saturatef(x[j]);
       asm volatile("lg2.approx.ftz.f32 %0, %1;" : "=f"(t[j]) : "f"(a));
     }
 #pragma unroll
-    for (int j = 0; j < 4 * NLD; ++j) {
+    for (int j = 0; j < 8; ++j) {
       const float a = t[j] * gam;
       asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(t[j]) : "f"(a));
     }
 #pragma unroll
-    for (int j = 0; j < 4 * NLD; ++j) {
+    for (int j = 0; j < 8; ++j) {
       float lin = t[j];
       if (KIND == FVVDP_B200_EOTF_SRGB) lin = (x[j] > 0.04045f) ? lin : __saturatef(x[j] * (1.0f / 12.92f));
       x[j] = fmaf(p.Yscale, lin, p.Y_black);
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < NLD; ++i) {
-      v[i].x = eotf_k<KIND>(v[i].x, p); v[i].y = eotf_k<KIND>(v[i].y, p); v[i].z = eotf_k<KIND>(v[i].z, p); v[i].w = eotf_k<KIND>(v[i].w, p);
-    }
+    for (int j = 0; j < 8; ++j) x[j] = eotf_k<KIND>(x[j], p);
   }
+}
+
+// One 4-pixel position chunk: landing buffer (two planes) -> EOTF -> luminance tile ((test, ref) interleaved).
+// `inside` = the chunk lies in the image (outside it the tile holds the zero padding of the reduce).
+template <int KIND>
+__device__ __forceinline__ void eotf_chunk(unsigned raw, unsigned lum, bool inside, const BandParams& p, float& vmin, float& vmax) {
+  const float4 a = lds128(raw), b = lds128(raw + PLANE * 4);
+  float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  vmin = fminf(vmin, fminf(fminf(fminf(x[0], x[1]), fminf(x[2], x[3])), fminf(fminf(x[4], x[5]), fminf(x[6], x[7]))));
+  vmax = fmaxf(vmax, fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7]))));
+  eotf8<KIND>(x, p);
+  if (!inside) {
 #pragma unroll
-  for (int i = 0; i < NLD; ++i)
-    if (ok[i]) *reinterpret_cast<float4*>(dst + (ld_soff[i] & 0xFFFFFF)) = v[i];
+    for (int j = 0; j < 8; ++j) x[j] = 0.0f;
+  }
+  sts128(lum, x[0], x[4], x[1], x[5]);
+  sts128(lum + 16, x[2], x[6], x[3], x[7]);
 }
 
 // cell of a 32-point (nearly uniform) axis containing q, and the reference's interpolation fraction
@@ -283,55 +285,52 @@ __device__ __forceinline__ void locate_direct(float q, const float* __restrict__
 // ------------------------------------------------------------------------------------------------ temporal rings
 template <int FL>
 struct Ring {
-  u64 v[2][FL][2];  // [stream][ring slot][row of the quad] = (left, right) pixel
+  u64 v[FL][4];  // [ring slot][pixel of the 2x2 quad] = (test, reference)
 };
 
 template <int FL, int J>
 __device__ __forceinline__ void ring_store(Ring<FL>& ring, const float* __restrict__ sLb, int coff) {
-#pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    ring.v[s][J][0] = *reinterpret_cast<const u64*>(sLb + s * LH * LW + coff);
-    ring.v[s][J][1] = *reinterpret_cast<const u64*>(sLb + s * LH * LW + coff + LW);
-  }
+  const ulonglong2 r0 = *reinterpret_cast<const ulonglong2*>(sLb + coff);
+  const ulonglong2 r1 = *reinterpret_cast<const ulonglong2*>(sLb + coff + 2 * LW);
+  ring.v[J][0] = r0.x; ring.v[J][1] = r0.y; ring.v[J][2] = r1.x; ring.v[J][3] = r1.y;
 }
 
-// R[cc*2+s][row] = sum_k wgt[cc][k] * ring[s][(J+1+k) % FL][row]   (window position k = 0 is the oldest frame)
+// R[cc][e] = sum_k wgt[cc][k] * ring[(J+1+k) % FL][e]   (window position k = 0 is the oldest frame)
 template <int FL, int TC, int J>
-__device__ __forceinline__ void fir_quad(const Ring<FL>& ring, const BandParams& p, u64 (&R)[2 * TC][2]) {
+__device__ __forceinline__ void fir_quad(const Ring<FL>& ring, const BandParams& p, u64 (&R)[TC][4]) {
 #pragma unroll
   for (int cc = 0; cc < TC; ++cc)
 #pragma unroll
-    for (int s = 0; s < 2; ++s)
+    for (int e = 0; e < 4; ++e) {
+      if (FL == 1) {
+        R[cc][e] = ring.v[0][e];
+      } else {
+        u64 a = fmul2(ring.v[(J + 1) % FL][e], p.wgt2[cc][0]);
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        if (FL == 1) {
-          R[cc * 2 + s][r] = ring.v[s][0][r];
-        } else {
-          u64 a = fmul2(ring.v[s][(J + 1) % FL][r], p.wgt2[cc][0]);
-#pragma unroll
-          for (int k = 1; k < FL; ++k) a = ffma2(ring.v[s][(J + 1 + k) % FL][r], p.wgt2[cc][k], a);
-          R[cc * 2 + s][r] = a;
-        }
-      }
-}
-
-// temporal filter of the reduced tiles: sNc[cc][i] = sum_k wgt[cc][k] sNr[(J+1+k) % FL][i], i over [NE][stream]
-template <int FL, int TC, int J>
-__device__ __forceinline__ void fir_coarse(const float* __restrict__ sNr, float* __restrict__ sNc, const BandParams& p, int tid) {
-  if (tid < 2 * NE / 4) {  // four consecutive floats per thread, 16-byte shared accesses
-    const float* base = sNr + 4 * tid;
-    u64 a[2][2];
-#pragma unroll
-    for (int k = 0; k < FL; ++k) {
-      const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(base + ((J + 1 + k) % FL) * (2 * NE));
-#pragma unroll
-      for (int cc = 0; cc < TC; ++cc) {
-        a[cc][0] = k == 0 ? fmul2(v.x, p.wgt2[cc][0]) : ffma2(v.x, p.wgt2[cc][k], a[cc][0]);
-        a[cc][1] = k == 0 ? fmul2(v.y, p.wgt2[cc][0]) : ffma2(v.y, p.wgt2[cc][k], a[cc][1]);
+        for (int k = 1; k < FL; ++k) a = ffma2(ring.v[(J + 1 + k) % FL][e], p.wgt2[cc][k], a);
+        R[cc][e] = a;
       }
     }
+}
+
+// temporal filter of this thread's own elements of the reduced-tile ring (written by the same thread, so no barrier is
+// needed between the column pass and this): sNc[cc][o] = sum_k wgt[cc][k] sNr[(J+1+k) % FL][o]
+template <int FL, int TC, int J>
+__device__ __forceinline__ void fir_coarse(const float* __restrict__ sNr, float* __restrict__ sNc, const BandParams& p, int tid) {
 #pragma unroll
-    for (int cc = 0; cc < TC; ++cc) *reinterpret_cast<ulonglong2*>(sNc + cc * (2 * NE) + 4 * tid) = make_ulonglong2(a[cc][0], a[cc][1]);
+  for (int i = 0; i < NCOL; ++i) {
+    const int o = tid + i * NT;
+    if (i < NCOL - 1 || o < NE) {
+      u64 a[TC];
+#pragma unroll
+      for (int k = 0; k < FL; ++k) {
+        const u64 v = *reinterpret_cast<const u64*>(sNr + ((J + 1 + k) % FL) * (2 * NE) + 2 * o);
+#pragma unroll
+        for (int cc = 0; cc < TC; ++cc) a[cc] = k == 0 ? fmul2(v, p.wgt2[cc][0]) : ffma2(v, p.wgt2[cc][k], a[cc]);
+      }
+#pragma unroll
+      for (int cc = 0; cc < TC; ++cc) *reinterpret_cast<u64*>(sNc + cc * (2 * NE) + 2 * o) = a[cc];
+    }
   }
 }
 
@@ -340,12 +339,14 @@ template <int KIND, int FL, int TC, bool FOV, bool EXTRA>
 __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ BandParams p) {
   constexpr bool LEVEL0 = KIND != IN_PYRAMID_TMA;
   constexpr bool TMA = KIND == IN_PYRAMID_TMA || KIND == IN_LEVEL0_TMA;
-  constexpr bool CHUNKED = KIND != IN_LEVEL0_GENERIC;  // staged as 16-byte chunks of contiguous float rows
+  constexpr bool LANDING = KIND == IN_LEVEL0_TMA || KIND == IN_LEVEL0_CPASYNC;  // raw planes land first, the EOTF pass interleaves them
+  constexpr int NLUM = KIND == IN_PYRAMID_TMA ? 2 : 1;  // the pyramid planes are interleaved in HBM: TMA lands them as luminance tiles
   constexpr int NCH = 2 * TC;
   extern __shared__ __align__(128) float smem[];
-  float* sL = smem;                                  // [2 buffers][2 streams][LH][LW]
-  float* sV = sL + 2 * TILE_FLOATS;                  // [2][NH][LW]   row-reduced
-  float* sNr = sV + 2 * NH * LW;                     // [FL][NE][2]   ring of reduced tiles, (test, ref) interleaved
+  float* sL = smem;                                  // [NLUM][LH][LW][2]   luminance tile, (test, ref) interleaved
+  float* sRaw = sL + NLUM * TILE_FLOATS;             // LANDING: [2 buffers][2 streams][LH][LW]
+  float* sV = sRaw + (LANDING ? 2 * TILE_FLOATS : 0);  // [NH][LW][2]   row-reduced
+  float* sNr = sV + 2 * NH * LW;                     // [FL][NE][2]   ring of reduced tiles
   float* sNc = (FL == 1) ? sNr : sNr + FL * 2 * NE;  // [TC][NE][2]   temporally filtered reduced tiles
   float* sTab = sNr + FL * 2 * NE + (FL == 1 ? 0 : NCH * NE);  // [32][8]
   float* sRed = sTab + 256;                          // [MAXCHUNK][2][NT/32]
@@ -359,11 +360,13 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
   const int s_lo = f_lo, s_hi = f_hi + p.fl - 1;  // slots walked by this CTA
   const int tile = blockIdx.y * gridDim.x + blockIdx.x;
   float vmin = 0.0f, vmax = 1.0f;  // range of the raw level-0 samples this thread converted
+  const unsigned bar0 = smem_u32(&bars[0]);
+  const unsigned sL_u32 = smem_u32(sL), sRaw_u32 = smem_u32(sRaw);
 
   // ---------------- one-time set-up (all index arithmetic lives here, outside the time loop) ----------------
   if (TMA && tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 32) {
@@ -374,147 +377,170 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
   }
   for (int i = tid; i < FL * 2 * NE; i += NT) sNr[i] = 0.0f;  // window positions that are never loaded must hold finite values
 
-  // 16-byte chunks of the staged tile owned by this thread: shared offset | stream << 30 (or -1), element offset
-  // inside a frame (or -1 = outside the image: zero fill, no EOTF)
-  int ld_soff[NLD], ld_goff[NLD];
-  if (CHUNKED) {
-    const int pitch = LEVEL0 ? (int)p.sH : p.pitch;
+  // LANDING: the 4-pixel position chunks of this thread are chunk tid (and tid + NT): 16 * chunk bytes into a landing plane,
+  // 32 * chunk bytes into the luminance tile.  ld_goff = element offset inside a frame, or -1 = outside the image.
+  const bool halo_inside = (ty0 >= 4) && (ty0 + TH + 4 <= h) && (tx0 >= 4) && (tx0 + TW + 4 <= w);
+  int ld_goff[NLD];
+  if (LANDING) {
 #pragma unroll
     for (int i = 0; i < NLD; ++i) {
-      const int item = tid + i * NT;
-      ld_soff[i] = -1;
+      const int pc = tid + i * NT;
       ld_goff[i] = -1;
-      if (item < 2 * LH * LV4) {
-        const int s = item / (LH * LV4), rem = item % (LH * LV4), r = rem / LV4, c4 = rem % LV4;
+      if (pc < NPC) {
+        const int r = pc / LV4, c4 = pc % LV4;
         const int y = ty0 - 4 + r, x = tx0 - 4 + 4 * c4;
-        ld_soff[i] = ((s * LH + r) * LW + 4 * c4) | (s << 30);
-        if (y >= 0 && y < h && x >= 0 && x < w) ld_goff[i] = y * pitch + x;
+        if (y >= 0 && y < h && x >= 0 && x < w) ld_goff[i] = y * (int)p.sH + x;
       }
     }
   }
-  // column-pass outputs of this thread
-  int cl_src[NCOL], cl_dst[NCOL], cl_g[NCOL];
+  // column-pass outputs of this thread: source offset in sV (floats) | edge flags << 28, global offset in Pn or -1
+  int cl_src[NCOL], cl_g[NCOL];
 #pragma unroll
   for (int i = 0; i < NCOL; ++i) {
     const int o = tid + i * NT;
-    cl_src[i] = -1; cl_dst[i] = 0; cl_g[i] = -1;
-    if (o < 2 * NE) {
-      const int s = o / NE, rem = o % NE, a = rem / NW, b = rem % NW;
+    cl_src[i] = -1; cl_g[i] = -1;
+    if (o < NE) {
+      const int a = o / NW, b = o % NW;
       const int ic = min(max(jx0 - 1 + b, 0), w2 - 1);   // expand clamps the coarse index
       const int flags = (ic == 0 ? 1 : 0) | (ic == w2 - 1 ? 2 : 0);
-      cl_src[i] = ((s * NH + a) * LW + 2 * (ic - jx0) + 2) | (flags << 28);
-      cl_dst[i] = 2 * rem + s;
+      cl_src[i] = (2 * (a * LW + 2 * (ic - jx0) + 2)) | (flags << 28);
       const int j = jy0 - 1 + a, ii = jx0 - 1 + b;
-      if (a >= 1 && a <= TH / 2 && b >= 1 && b <= TW / 2 && j < h2 && ii < w2) cl_g[i] = (s * h2 + j) * p.pitch2 + ii;
+      if (a >= 1 && a <= TH / 2 && b >= 1 && b <= TW / 2 && j < h2 && ii < w2) cl_g[i] = j * p.pitch2 + 2 * ii;
     }
   }
+  // row pass: column and first coarse row of this thread (tid < ROW_THREADS)
+  const int rw_c = tid % LW, rw_seg = tid / LW;
+  const int rw_a0 = rw_seg == 0 ? 0 : (rw_seg == 1 ? 4 : 7), rw_n = rw_seg == 0 ? 4 : 3;
   // the quad of this thread
   const int qa = tid >> 5, qb = lane;
   const int qy = ty0 + 2 * qa, qx = tx0 + 2 * qb;
-  const int coff = (4 + 2 * qa) * LW + 4 + 2 * qb;   // quad's top-left pixel in the staged tile
-  const int noff = 2 * (qa * NW + qb);               // top-left of its 3x3 coarse neighbourhood ((test, ref) interleaved)
+  const int coff = 2 * ((4 + 2 * qa) * LW + 4 + 2 * qb);   // quad's top-left pixel in the luminance tile (floats)
+  const int noff = 2 * (qa * NW + qb);                     // top-left of its 3x3 coarse neighbourhood
   bool valid[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) valid[e] = (qy + (e >> 1) < h) && (qx + (e & 1) < w);
 
   Ring<FL> ring;
 #pragma unroll
-  for (int s = 0; s < 2; ++s)
+  for (int k = 0; k < FL; ++k)
 #pragma unroll
-    for (int k = 0; k < FL; ++k) ring.v[s][k][0] = ring.v[s][k][1] = 0ull;
+    for (int e = 0; e < 4; ++e) ring.v[k][e] = 0ull;
 
-  const float K0 = 0.05f, K1 = 0.25f, K2 = 0.4f, K3 = 0.25f, K4 = 0.05f;
+  const float K0 = 0.05f, K1 = 0.25f, K3 = 0.25f, K4 = 0.05f;
   const bool rows_interior = (jy0 - 1 >= 1) && (jy0 + TH / 2 <= h2 - 2);
   const bool cols_interior = (jx0 - 1 >= 1) && (jx0 + TW / 2 <= w2 - 2);
   const bool tile_full = (ty0 + TH <= h) && (tx0 + TW <= w);
 
-  // stage the tile of `slot` into buffer `buf`
+  // start staging the tile of `slot` into buffer `buf` (landing buffer, or luminance buffer for the pyramid levels)
   auto issue_load = [&](int slot, int buf) {
-    float* dst = sL + buf * TILE_FLOATS;
     if (TMA) {
       if (tid == 0) {
-        mbar_expect_tx(&bars[buf], TILE_FLOATS * 4);
+        mbar_expect_tx(bar0 + 8 * buf, TILE_FLOATS * 4);
         if (KIND == IN_PYRAMID_TMA) {
-          tma_load_4d(dst, &p.tmap[0], &bars[buf], tx0 - 4, ty0 - 4, 0, slot);
+          tma_load_3d(sL_u32 + buf * (TILE_FLOATS * 4), &p.tmap[0], bar0 + 8 * buf, 2 * (tx0 - 4), ty0 - 4, slot);
         } else {
-          tma_load_3d(dst, &p.tmap[0], &bars[buf], tx0 - 4, ty0 - 4, (int)p.slot_frame[0][slot]);
-          tma_load_3d(dst + LH * LW, &p.tmap[1], &bars[buf], tx0 - 4, ty0 - 4, (int)p.slot_frame[1][slot]);
+          const unsigned dst = sRaw_u32 + buf * (TILE_FLOATS * 4);
+          tma_load_3d(dst, &p.tmap[0], bar0 + 8 * buf, tx0 - 4, ty0 - 4, (int)p.slot_frame[0][slot]);
+          tma_load_3d(dst + PLANE * 4, &p.tmap[1], bar0 + 8 * buf, tx0 - 4, ty0 - 4, (int)p.slot_frame[1][slot]);
         }
       }
-    } else if (CHUNKED) {
+    } else if (KIND == IN_LEVEL0_CPASYNC) {
       const float* b0 = reinterpret_cast<const float*>(p.slot[0][slot]);
       const float* b1 = reinterpret_cast<const float*>(p.slot[1][slot]);
+      const unsigned dst = sRaw_u32 + buf * (TILE_FLOATS * 4) + 16 * tid;
 #pragma unroll
       for (int i = 0; i < NLD; ++i) {
-        if (ld_soff[i] >= 0) {
-          const float* b = (ld_soff[i] >> 30) ? b1 : b0;
+        if (i < NLD - 1 || tid + i * NT < NPC) {
           const int g = ld_goff[i];
-          cp_async16(dst + (ld_soff[i] & 0xFFFFFF), g >= 0 ? (const void*)(b + g) : (const void*)b, g >= 0 ? 16 : 0);
+          cp_async16(dst + i * (NT * 16), g >= 0 ? (const void*)(b0 + g) : (const void*)b0, g >= 0 ? 16 : 0);
+          cp_async16(dst + i * (NT * 16) + PLANE * 4, g >= 0 ? (const void*)(b1 + g) : (const void*)b1, g >= 0 ? 16 : 0);
         }
       }
-    } else {
-      for (int item = tid; item < TILE_FLOATS; item += NT) {
-        const int s = item / (LH * LW), rem = item % (LH * LW), r = rem / LW, c = rem % LW;
-        const int y = ty0 - 4 + r, x = tx0 - 4 + c;
-        float v = 0.0f;
-        if (y >= 0 && y < h && x >= 0 && x < w) v = lum_generic(p, p.slot[s][slot], y, x, vmin, vmax);
-        dst[item] = v;
-      }
+      cp_async_commit();
     }
   };
-  // wait for the staged tile; level 0 with raw float input: display EOTF in place on this thread's chunks
-  auto finish_load = [&](int buf, unsigned parity) {
-    if (TMA) mbar_wait(&bars[buf], parity);
-    else if (CHUNKED) cp_async_commit_wait_all();
-    if (LEVEL0 && CHUNKED) {
-      float* dst = sL + buf * TILE_FLOATS;
-      switch (p.eotf) {  // uniform; one specialised conversion loop per EOTF
-        case FVVDP_B200_EOTF_NONE: break;
-        case FVVDP_B200_EOTF_SRGB: eotf_chunks<FVVDP_B200_EOTF_SRGB>(dst, ld_soff, ld_goff, p, vmin, vmax); break;
-        case FVVDP_B200_EOTF_GAMMA: eotf_chunks<FVVDP_B200_EOTF_GAMMA>(dst, ld_soff, ld_goff, p, vmin, vmax); break;
-        case FVVDP_B200_EOTF_PQ: eotf_chunks<FVVDP_B200_EOTF_PQ>(dst, ld_soff, ld_goff, p, vmin, vmax); break;
-        case FVVDP_B200_EOTF_LINEAR: eotf_chunks<FVVDP_B200_EOTF_LINEAR>(dst, ld_soff, ld_goff, p, vmin, vmax); break;
-        default: eotf_chunks<FVVDP_B200_EOTF_ABSOLUTE>(dst, ld_soff, ld_goff, p, vmin, vmax); break;
-      }
-      if (TMA) fence_proxy_async_smem();  // these generic-proxy writes precede the next TMA write into this buffer
+  // level 0: landing buffer -> display EOTF -> luminance tile
+  auto convert = [&](int buf) {
+    const unsigned raw = sRaw_u32 + buf * (TILE_FLOATS * 4) + 16 * tid, lum = sL_u32 + 32 * tid;
+#define FVVDP_EOTF_PASS(K)                                                                                          \
+  {                                                                                                                 \
+    eotf_chunk<K>(raw, lum, halo_inside || ld_goff[0] >= 0, p, vmin, vmax);                                         \
+    if (tid < NPC - NT) eotf_chunk<K>(raw + NT * 16, lum + NT * 32, halo_inside || ld_goff[1] >= 0, p, vmin, vmax); \
+  }
+    switch (p.eotf) {  // uniform; one specialised conversion loop per EOTF
+      case FVVDP_B200_EOTF_NONE: FVVDP_EOTF_PASS(FVVDP_B200_EOTF_NONE) break;
+      case FVVDP_B200_EOTF_SRGB: FVVDP_EOTF_PASS(FVVDP_B200_EOTF_SRGB) break;
+      case FVVDP_B200_EOTF_GAMMA: FVVDP_EOTF_PASS(FVVDP_B200_EOTF_GAMMA) break;
+      case FVVDP_B200_EOTF_PQ: FVVDP_EOTF_PASS(FVVDP_B200_EOTF_PQ) break;
+      case FVVDP_B200_EOTF_LINEAR: FVVDP_EOTF_PASS(FVVDP_B200_EOTF_LINEAR) break;
+      default: FVVDP_EOTF_PASS(FVVDP_B200_EOTF_ABSOLUTE) break;
     }
+#undef FVVDP_EOTF_PASS
   };
 
+  static_assert(NLD == 2, "EOTF pass: chunk tid and, for tid < NPC - NT, chunk tid + NT");
   if (TMA) __syncthreads();  // barrier initialisation visible before the first wait
   issue_load(s_lo, 0);
+  if (LANDING && s_lo + 1 < s_hi) issue_load(s_lo + 1, 1);
 
   for (int s = s_lo; s < s_hi; ++s) {
     const int buf = (s - s_lo) & 1;
-    const float* sLb = sL + buf * TILE_FLOATS;
-    finish_load(buf, ((s - s_lo) >> 1) & 1);
-    __syncthreads();  // (1) tile of slot s staged; every reader of the other buffer is done
-    if (s + 1 < s_hi) issue_load(s + 1, buf ^ 1);
+    const float* sLb = sL + (NLUM == 2 ? buf * TILE_FLOATS : 0);
+    // ---- the staged tile of slot s ----
+    if (KIND == IN_LEVEL0_GENERIC) {
+      for (int pos = tid; pos < PLANE; pos += NT) {
+        const int r = pos / LW, c = pos % LW;
+        const int y = ty0 - 4 + r, x = tx0 - 4 + c;
+        float2 v = make_float2(0.0f, 0.0f);
+        if (y >= 0 && y < h && x >= 0 && x < w) {
+          v.x = lum_generic(p, p.slot[0][s], y, x, vmin, vmax);
+          v.y = lum_generic(p, p.slot[1][s], y, x, vmin, vmax);
+        }
+        reinterpret_cast<float2*>(sL)[pos] = v;
+      }
+    } else {
+      if (TMA) mbar_wait(bar0 + 8 * buf, ((s - s_lo) >> 1) & 1);
+      else if (s + 1 < s_hi) cp_async_wait<1>();
+      else cp_async_wait<0>();
+      if (LANDING) {
+        if (!TMA) __syncthreads();  // cp.async: the chunks of other threads
+        convert(buf);
+      }
+    }
+    __syncthreads();  // (1) luminance tile of slot s complete; every reader of the buffers refilled below is done
+    if (LANDING) { if (s + 2 < s_hi) issue_load(s + 2, buf); }
+    else if (KIND == IN_PYRAMID_TMA) { if (s + 1 < s_hi) issue_load(s + 1, buf ^ 1); }
 
-    // ---- reduce, rows: sV[st][a][c] = sum_k K[k] L[2j-2+k][c],  j = clamp(jy0-1+a)  (zero padding + edge terms) ----
-    if (tid < 2 * LW) {  // one thread walks down one staged column
-      const int st = tid >= LW ? 1 : 0, c = tid - st * LW;
-      const float* col = sLb + st * LH * LW + c;
-      float* out = sV + st * NH * LW + c;
+    // ---- reduce, rows: sV[a][c] = sum_k K[k] L[2j-2+k][c],  j = clamp(jy0-1+a)  (zero padding + edge terms) ----
+    if (tid < ROW_THREADS) {  // one thread walks down a third of one staged column, (test, ref) pairs
+      const float* col = sLb + 2 * rw_c;
+      float* out = sV + 2 * rw_c;
       if (rows_interior) {  // no clamped coarse rows, no edge terms: sliding 5-row window
-        float g0 = col[0], g1 = col[LW], g2 = col[2 * LW];
+        const float* g = col + (2 * rw_a0) * (2 * LW);
+        u64 g0 = *reinterpret_cast<const u64*>(g), g1 = *reinterpret_cast<const u64*>(g + 2 * LW), g2 = *reinterpret_cast<const u64*>(g + 4 * LW);
 #pragma unroll
-        for (int a = 0; a < NH; ++a) {
-          const float g3 = col[(2 * a + 3) * LW], g4 = col[(2 * a + 4) * LW];
-          out[a * LW] = fmaf(K0, g0 + g4, fmaf(K1, g1 + g3, K2 * g2));
-          g0 = g2; g1 = g3; g2 = g4;
+        for (int j = 0; j < 4; ++j) {
+          if (j < 3 || rw_n == 4) {
+            const u64 g3 = *reinterpret_cast<const u64*>(g + (2 * j + 3) * (2 * LW)), g4 = *reinterpret_cast<const u64*>(g + (2 * j + 4) * (2 * LW));
+            *reinterpret_cast<u64*>(out + (rw_a0 + j) * (2 * LW)) = tap5(g0, g1, g2, g3, g4);
+            g0 = g2; g1 = g3; g2 = g4;
+          }
         }
       } else {
-#pragma unroll
-        for (int a = 0; a < NH; ++a) {
+        for (int j = 0; j < rw_n; ++j) {
+          const int a = rw_a0 + j;
           const int jc = min(max(jy0 - 1 + a, 0), h2 - 1);  // expand clamps the coarse index
-          const float* g = col + (2 * (jc - jy0) + 2) * LW;
-          float v = fmaf(K0, g[0] + g[4 * LW], fmaf(K1, g[LW] + g[3 * LW], K2 * g[2 * LW]));
-          if (jc == 0) v += K1 * g[2 * LW] + K0 * g[3 * LW];     // x[0], x[1]   (fvvdp_lpyr_dec.py:191)
-          if (jc == h2 - 1) {
-            const float* e = col + (h - 1 - ty0 + 4) * LW;       // x[h-1]
-            v += (h & 1) ? (K3 * e[0] + K4 * e[-LW]) : K4 * e[0];  // (:192-195)
+          const float* g = col + (2 * (jc - jy0) + 2) * (2 * LW);
+#pragma unroll
+          for (int st = 0; st < 2; ++st) {
+            float v = fmaf(K0, g[st] + g[8 * LW + st], fmaf(K1, g[2 * LW + st] + g[6 * LW + st], 0.4f * g[4 * LW + st]));
+            if (jc == 0) v += K1 * g[4 * LW + st] + K0 * g[6 * LW + st];     // x[0], x[1]   (fvvdp_lpyr_dec.py:191)
+            if (jc == h2 - 1) {
+              const float* e = col + (h - 1 - ty0 + 4) * (2 * LW) + st;      // x[h-1]
+              v += (h & 1) ? (K3 * e[0] + K4 * e[-2 * LW]) : K4 * e[0];      // (:192-195)
+            }
+            out[a * (2 * LW) + st] = v;
           }
-          out[a * LW] = v;
         }
       }
     }
@@ -527,40 +553,43 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
       for (int i = 0; i < NCOL; ++i) {
         if (i < NCOL - 1 || cl_src[i] >= 0) {  // only the last round is partial
           const float* v = sV + (cl_src[i] & 0xFFFFFFF);
-          float o = fmaf(K0, v[0] + v[4], fmaf(K1, v[1] + v[3], K2 * v[2]));
+          const ulonglong2 v01 = *reinterpret_cast<const ulonglong2*>(v), v23 = *reinterpret_cast<const ulonglong2*>(v + 4);
+          const u64 v4 = *reinterpret_cast<const u64*>(v + 8);
+          u64 o = tap5(v01.x, v01.y, v23.x, v23.y, v4);
           if (!cols_interior) {
-            if (cl_src[i] & (1 << 28)) o += K1 * v[2] + K0 * v[3];
+            float ot = lo_of(o), orf = hi_of(o);
+            if (cl_src[i] & (1 << 28)) { ot += K1 * v[4] + K0 * v[6]; orf += K1 * v[5] + K0 * v[7]; }
             if (cl_src[i] & (2 << 28)) {
-              const float* e = sV + ((cl_src[i] & 0xFFFFFFF) / LW) * LW + (w - 1 - tx0 + 4);  // y[w-1] of this row
-              o += p.h_odd ? (K3 * e[0] + K4 * e[-1]) : K4 * e[0];  // keyed on the ROW count, fvvdp_lpyr_dec.py:202
+              const float* e = sV + ((cl_src[i] & 0xFFFFFFF) / (2 * LW)) * (2 * LW) + 2 * (w - 1 - tx0 + 4);  // y[w-1] of this row
+              // keyed on the ROW count, fvvdp_lpyr_dec.py:202
+              ot += p.h_odd ? (K3 * e[0] + K4 * e[-2]) : K4 * e[0];
+              orf += p.h_odd ? (K3 * e[1] + K4 * e[-1]) : K4 * e[1];
             }
+            o = pk(ot, orf);
           }
-          ring_s[cl_dst[i]] = o;
-          if (gout != nullptr && cl_g[i] >= 0) gout[cl_g[i]] = o;
+          *reinterpret_cast<u64*>(ring_s + 2 * (tid + i * NT)) = o;
+          if (gout != nullptr && cl_g[i] >= 0) *reinterpret_cast<u64*>(gout + cl_g[i]) = o;
         }
       }
     }
-    __syncthreads();  // (3)
 
     const bool emit = s >= f_lo + p.fl - 1;
     const int fi = s - (p.fl - 1);  // output frame
-    // ---- this thread's pixels into the register ring; temporal filters of the coarse tiles and of the pixels.
+    // ---- temporal filter of the thread's own coarse elements; its pixels into the register ring and their filter.
     //      The ring position is a compile-time constant inside each case: no address arithmetic, no register moves.
-    u64 R[NCH][2];
+    u64 R[TC][4];
     switch (s % FL) {
-#define FVVDP_CASE(J)                                          \
-  case J:                                                      \
-    ring_store<FL, (J) % FL>(ring, sLb, coff);                 \
-    if (emit) {                                                \
-      if (FL > 1) fir_coarse<FL, TC, (J) % FL>(sNr, sNc, p, tid); \
-      fir_quad<FL, TC, (J) % FL>(ring, p, R);                  \
-    }                                                          \
+#define FVVDP_CASE(J)                                             \
+  case J:                                                         \
+    if (emit && FL > 1) fir_coarse<FL, TC, (J) % FL>(sNr, sNc, p, tid); \
+    ring_store<FL, (J) % FL>(ring, sLb, coff);                    \
+    if (emit) fir_quad<FL, TC, (J) % FL>(ring, p, R);             \
     break;
       FVVDP_CASE(0) FVVDP_CASE(1) FVVDP_CASE(2) FVVDP_CASE(3) FVVDP_CASE(4) FVVDP_CASE(5) FVVDP_CASE(6) FVVDP_CASE(7)
 #undef FVVDP_CASE
     }
+    if (NLUM == 1 || emit) __syncthreads();  // (3) filtered coarse tiles visible; the single luminance tile may be rewritten
     if (!emit) continue;
-    if (FL > 1) __syncthreads();  // (4) filtered coarse tiles visible
 
     // ---- expand the filtered coarse tile, contrast, CSF, masking, pooling: one 2x2 quad per thread ----
     float acc[2] = {0.0f, 0.0f};
@@ -568,7 +597,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
     int cj[4];
     float lsf[TC][4];  // FOV: log2 S per temporal channel
     float Dsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    const u64 c01 = pk(0.1f, 0.1f), c08 = pk(0.8f, 0.8f), c05 = pk(0.5f, 0.5f);
+    const u64 c01 = pk(0.1f, 0.1f), c08 = pk(0.8f, 0.8f), c05 = pk(0.5f, 0.5f), cm1 = pk(-1.0f, -1.0f);
 #pragma unroll
     for (int cc = 0; cc < TC; ++cc) {
       // expand both streams at once: every value below is a (test, reference) pair
@@ -589,9 +618,9 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
       float B[2][4];  // band (G_l - E) of the test / reference channel
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const u64 rt = R[cc * 2 + 0][e >> 1], rr = R[cc * 2 + 1][e >> 1];
-        B[0][e] = ((e & 1) ? hi_of(rt) : lo_of(rt)) - lo_of(E[e]);
-        B[1][e] = ((e & 1) ? hi_of(rr) : lo_of(rr)) - hi_of(E[e]);
+        const u64 b = ffma2(E[e], cm1, R[cc][e]);  // R - E, rounded once like the scalar subtraction
+        B[0][e] = lo_of(b);
+        B[1][e] = hi_of(b);
       }
       if (cc == 0) {
 #pragma unroll
@@ -661,9 +690,8 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
           Dsum[e] += (cc == 0 ? 1.0f : p.w_transient) * D;
           if (cc == 0 && p.tapL) p.tapL[(long long)fi * plane + pofs] = Lb[e];
           if (LEVEL0 && p.tapR) {
-            const u64 rt = R[cc * 2 + 0][e >> 1], rr = R[cc * 2 + 1][e >> 1];
-            p.tapR[((long long)fi * NCH + cc * 2 + 0) * plane + pofs] = (e & 1) ? hi_of(rt) : lo_of(rt);
-            p.tapR[((long long)fi * NCH + cc * 2 + 1) * plane + pofs] = (e & 1) ? hi_of(rr) : lo_of(rr);
+            p.tapR[((long long)fi * NCH + cc * 2 + 0) * plane + pofs] = lo_of(R[cc][e]);
+            p.tapR[((long long)fi * NCH + cc * 2 + 1) * plane + pofs] = hi_of(R[cc][e]);
           }
           if (cc == TC - 1 && p.dmap) p.dmap[(long long)fi * plane + pofs] = Dsum[e] / p.band_mul;
         }
@@ -698,9 +726,10 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
   if (LEVEL0 && eotf_checks_range(p.eotf) && (vmin < 0.0f || vmax > 1.0f) && p.flags) atomicOr(p.flags, 1u);
 }
 
-template <int FL, int TC>
+template <int KIND, int FL, int TC>
 constexpr size_t band_smem_bytes() {
-  return sizeof(float) * (size_t)(2 * TILE_FLOATS + 2 * NH * LW + FL * 2 * NE + (FL == 1 ? 0 : 2 * TC * NE) + 256 + MAXCHUNK * 2 * (NT / 32));
+  return sizeof(float) * (size_t)((KIND == IN_PYRAMID_TMA ? 2 : 1) * TILE_FLOATS + ((KIND == IN_LEVEL0_TMA || KIND == IN_LEVEL0_CPASYNC) ? 2 * TILE_FLOATS : 0) +
+                                  2 * NH * LW + FL * 2 * NE + (FL == 1 ? 0 : 2 * TC * NE) + 256 + MAXCHUNK * 2 * (NT / 32));
 }
 
 }  // namespace fused

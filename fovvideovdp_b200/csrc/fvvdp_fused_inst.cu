@@ -18,7 +18,7 @@ constexpr int kTC = FUSED_VIDEO ? 2 : 1;
 #define FUSED_FN(name) FUSED_CAT(name, FUSED_KIND, FUSED_VIDEO)
 
 cudaError_t FUSED_FN(launch_band_)(bool foveated, bool extra, const BandParams& p, dim3 grid, cudaStream_t st) {
-  const size_t smem = band_smem_bytes<kFL, kTC>();
+  const size_t smem = band_smem_bytes<FUSED_KIND, kFL, kTC>();
   if (foveated) {
     if (extra) band_kernel<FUSED_KIND, kFL, kTC, true, true><<<grid, NT, smem, st>>>(p);
     else band_kernel<FUSED_KIND, kFL, kTC, true, false><<<grid, NT, smem, st>>>(p);
@@ -30,7 +30,7 @@ cudaError_t FUSED_FN(launch_band_)(bool foveated, bool extra, const BandParams& 
 }
 
 cudaError_t FUSED_FN(configure_band_)() {
-  const int smem = (int)band_smem_bytes<kFL, kTC>();
+  const int smem = (int)band_smem_bytes<FUSED_KIND, kFL, kTC>();
   cudaError_t e;
   e = cudaFuncSetAttribute(band_kernel<FUSED_KIND, kFL, kTC, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
