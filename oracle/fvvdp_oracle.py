@@ -336,14 +336,18 @@ def resolution_magnification(geo, vx, vy):
 
 
 def foveation_maps(geo, band_hw, frame_hw, fixation_xy):
+    """fvvdp.py:416-436.  A geometry dict may carry its own "pix2view_direction"(geo, res_wh, x, y) and
+    "resolution_magnification"(geo, vx, vy) callables: the numpy twin of a fvvdp_display_geometry subclass
+    (pytorch_examples/ex_custom_ppd.py:38-57)."""
     h, w = band_hw
     xv = np.linspace(0.5, w - 0.5, w, dtype=np.float64).astype(_F)
     yv = np.linspace(0.5, h - 0.5, h, dtype=np.float64).astype(_F)
     xx, yy = np.meshgrid(xv, yv, indexing="xy")
-    vx, vy = pix2view_direction(geo, (w, h), xx, yy)
-    gx, gy = pix2view_direction(geo, (frame_hw[1], frame_hw[0]), _F(fixation_xy[0]) + _F(0.5), _F(fixation_xy[1]) + _F(0.5))
+    p2v = geo.get("pix2view_direction", pix2view_direction)
+    vx, vy = p2v(geo, (w, h), xx, yy)
+    gx, gy = p2v(geo, (frame_hw[1], frame_hw[0]), _F(fixation_xy[0]) + _F(0.5), _F(fixation_xy[1]) + _F(0.5))
     ecc = np.sqrt((vx - gx) ** 2 + (vy - gy) ** 2).astype(_F)
-    return ecc, resolution_magnification(geo, vx, vy)
+    return ecc, geo.get("resolution_magnification", resolution_magnification)(geo, vx, vy)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -383,6 +387,63 @@ def pool_to_jod(Q_per_ch, p, is_video=True):
     beta_jod = 10.0 ** p["log_jod_exp"]
     sign = -1.0 if p["jod_a"] < 0 else 1.0
     return sign * ((abs(p["jod_a"]) ** (1.0 / beta_jod)) * Qv) ** beta_jod + 10.0
+
+
+# ----------------------------------------------------------------------------------------------
+# heat-map visualisation (visualize_diff_map.py:9-107, interp.py:72-80)
+# ----------------------------------------------------------------------------------------------
+_COLOR_MAPS = {  # visualize_diff_map.py:66-82
+    "threshold": ([[0.2, 0.2, 1.0], [0.2, 1.0, 1.0], [0.2, 1.0, 0.2], [1.0, 1.0, 0.2], [1.0, 0.2, 0.2]], [0.00, 0.25, 0.50, 0.75, 1.00]),
+    "supra-threshold": ([[0.2, 1.0, 1.0], [1.0, 1.0, 1.0], [1.0, 1.0, 0.2]], [0.0, 0.5, 1.0]),
+}
+
+
+def linspace_f32(lo, hi, n):
+    """torch.linspace in float32: start + step*i in the first half, end - step*(n-1-i) in the second."""
+    lo, hi = _F(lo), _F(hi)
+    step = _F((hi - lo) / _F(n - 1))
+    i = np.arange(n)
+    return np.where(i < n // 2, lo + step * i.astype(_F), hi - step * (n - 1 - i).astype(_F)).astype(_F)
+
+
+def interp1(x, v, q):
+    """interp.py:72-80."""
+    imin, imax, frc = _interpolants(q.ravel().astype(_F), x)
+    return (v[imin] * (_F(1) - frc) + v[imax] * frc).astype(_F).reshape(q.shape)
+
+
+def vis_tonemap(b, dr):
+    """visualize_diff_map.py:26-50: histogram-equalising tone curve with exponent 1/3 over 1024 bins."""
+    dr = _F(dr)
+    b_min, b_max = b.min(), b.max()
+    if b_max - b_min < dr:
+        return ((b - b_min) / (b_max - b_min + _F(1e-3)) * dr + (_F(1) - dr) / _F(2)).astype(_F)
+    b_scale = linspace_f32(b_min, b_max, 1024)
+    # torch.histc: bin = (int)((x - min) / (max - min) * bins), the maximum goes into the last bin
+    pos = ((b.ravel() - b_min) / (b_max - b_min) * _F(1024)).astype(np.int64)
+    pos = np.minimum(pos, 1023)
+    b_p = np.bincount(pos, minlength=1024).astype(_F)
+    b_p = b_p / np.sum(b_p, dtype=_F)
+    pw = np.power(b_p, _F(1.0 / 3.0)).astype(_F)
+    dy = pw / np.sum(pw, dtype=_F)
+    v = (np.cumsum(dy, dtype=_F) * dr + (_F(1) - dr) / _F(2)).astype(_F)
+    return interp1(b_scale, v, b)
+
+
+def visualize_diff_map(diff_map, context, colormap_type):
+    """visualize_diff_map.py:58-107 for a single-channel context image.  diff_map, context (H,W) float32
+    -> (3,H,W) float32 in [0,1]."""
+    d = np.clip(diff_map.astype(_F), _F(0), _F(1))
+    y = context.astype(_F)
+    clampval = y[y > 0].min()
+    tmo = vis_tonemap(np.log(np.maximum(y, clampval)).astype(_F), 0.6)
+    cm, cm_in = _COLOR_MAPS[colormap_type]
+    cm = np.array(cm, _F)
+    cm_in = np.array(cm_in, _F)
+    cm_l = cm[:, 0:1] * _F(0.212656) + cm[:, 1:2] * _F(0.715158) + cm[:, 2:3] * _F(0.072186)
+    cm_ch = cm / (cm_l + _F(0.0001))
+    out = np.stack([interp1(cm_in, cm_ch[:, c], d) for c in range(3)], 0)
+    return np.clip(out * tmo[None], _F(0), _F(1)).astype(_F)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -436,7 +497,7 @@ def score_frame(R4, height, freqs, p, is_image, foveated=False, geo=None, frame_
     if want_heatmap:
         beta_jod = 10.0 ** p["log_jod_exp"]
         rec = reconstruct(hm_bands + [np.zeros(gpyr[height].shape[-2:], _F)])
-        dmap = (np.power(rec, _F(beta_jod)) * _F(abs(p["jod_a"]))).astype(np.float16)
+        dmap = (np.power(rec, _F(beta_jod)) * _F(abs(p["jod_a"]))).astype(_F)
     return Q, dmap
 
 
@@ -467,7 +528,7 @@ def predict(test, ref, dim_order="BCFHW", frames_per_second=0, display_name="sta
     score = list(range(N)) if frames is None else list(frames)
     Q_per_ch = np.zeros((height, 2, N), _F)
     want_hm = heatmap not in (None, "none")
-    hm = np.zeros((1, 1, N, H, W), np.float16) if want_hm else None
+    hm = np.zeros((1, 1 if heatmap == "raw" else 3, N, H, W), np.float16) if want_hm else None
     taps = None
     lum_cache = {} if lum_cache is None else lum_cache
 
@@ -506,7 +567,10 @@ def predict(test, ref, dim_order="BCFHW", frames_per_second=0, display_name="sta
             taps = t
         Q_per_ch[:, :, ff] = Q
         if want_hm:
-            hm[0, 0, ff] = dmap
+            if heatmap == "raw":
+                hm[0, 0, ff] = dmap.astype(np.float16)
+            else:  # the context image is R[:,0], the sustained channel of the TEST stream (fvvdp.py:475)
+                hm[0, :, ff] = visualize_diff_map(dmap, R4[0], heatmap).astype(np.float16)
         if frame_times is not None:
             frame_times.append(time.perf_counter() - t_start)
     sel = Q_per_ch if frames is None else Q_per_ch[:, :, score]

@@ -195,6 +195,55 @@ def test_heatmap_raw(golden):
     assert abs(hm.mean() - float(g["hm_mean"])) < 1e-4
 
 
+@pytest.mark.parametrize("mode", ["threshold", "supra-threshold"])
+def test_heatmap_colour_maps(golden, mode):
+    """visualize_diff_map (visualize_diff_map.py:58-107): colour map of the difference map over the tone-mapped
+    sustained test frame."""
+    g = golden(f"video_fhd_heatmap_{mode}")
+    t, r = synth_pair_numpy(4, 270, 480)
+    jod, st = O.predict(t, r, frames_per_second=30, display_name="standard_fhd", heatmap=mode)
+    assert abs(jod - float(g["jod"])) / float(g["jod"]) < JOD_RTOL
+    hm = st["heatmap"].astype(np.float32)
+    assert hm.shape == (1, 3, 4, 270, 480)
+    np.testing.assert_allclose(hm[0, :, :, ::SY, ::SX], g["heatmap_sub"], rtol=2e-3, atol=2e-3)  # fp16 storage
+    np.testing.assert_allclose(hm.mean(axis=(0, 2, 3, 4)), g["hm_mean"], atol=2e-4)
+
+
+def test_heatmap_colour_map_low_dynamic_range(golden):
+    """Luminance range of the context image below 0.6 log units: the linear branch of vis_tonemap (:32-34)."""
+    g = golden("image_fhd_heatmap_threshold_lowdr")
+    t, r = synth_pair_numpy(1, 270, 480)
+    ti, ri = 0.5 + 0.1 * t[0, :, 0:1], 0.5 + 0.1 * r[0, :, 0:1]
+    jod, st = O.predict(ti, ri, dim_order="CFHW", display_name="standard_fhd", heatmap="threshold")
+    assert abs(jod - float(g["jod"])) / float(g["jod"]) < JOD_RTOL
+    hm = st["heatmap"].astype(np.float32)
+    np.testing.assert_allclose(hm[0, :, :, ::SY, ::SX], g["heatmap_sub"], rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(hm.mean(axis=(0, 2, 3, 4)), g["hm_mean"], atol=2e-4)
+
+
+def custom_geometry_oracle():
+    """numpy twin of the fvvdp_display_geometry subclass in pytorch_examples/ex_custom_ppd.py:38-57
+    (ppd = ppd_centre / (view_angle / 20 + 1)) on a 480x270, 24-inch display seen from 0.6 m."""
+    geo = O.geometry((480, 270), distance_m=0.6, diagonal_size_inches=24)
+
+    def res_mag(geo_, vx, vy):
+        va = np.sqrt(vx * vx + vy * vy).astype(np.float32)
+        return (np.float32(geo_["ppd_centre"]) / (va / np.float32(20.0) + np.float32(1.0)) / np.float32(geo_["ppd_centre"])).astype(np.float32)
+
+    geo["resolution_magnification"] = res_mag
+    return geo
+
+
+def test_custom_geometry_foveated(golden):
+    g = golden("video_custom_geometry_foveated")
+    t, r = synth_pair_numpy(12, 270, 480)
+    jod, st = O.predict(t[:, :, :6], r[:, :, :6], frames_per_second=30, display_name="standard_fhd", geometry_=custom_geometry_oracle(),
+                        foveated=True, fixation_point=g["gaze"])
+    assert abs(jod - float(g["jod"])) / float(g["jod"]) < JOD_RTOL
+    np.testing.assert_allclose(st["rho_band"], g["rho_band"], rtol=1e-6)
+    _check_q(st["Q_per_ch"], g["Q_per_ch"], tol=1e-3)
+
+
 @pytest.mark.parametrize("hw", [(135, 240), (136, 241), (67, 97), (64, 64)])
 def test_odd_sizes(golden, hw):
     H, W = hw

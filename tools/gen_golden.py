@@ -4,6 +4,7 @@
 CUDA path).  Inputs are analytic / seeded so only outputs (and small inputs) are stored.
 
     python tools/gen_golden.py            # rewrites every fixture
+    python tools/gen_golden.py widen      # only the fixtures of the widened surface (heat-map colour maps, custom geometry)
 
 Large tap tensors are stored as strided sub-samples ([::SY, ::SX]) to keep the fixtures small.
 """
@@ -276,9 +277,45 @@ def gen_known_answer():
     save("known_answer_wavy_facade", **out)
 
 
+class custom_display_geometry(fvvdp_display_geometry):
+    """The custom geometry of pytorch_examples/ex_custom_ppd.py:38-57: ppd falls off with the view angle."""
+
+    def get_ppd(self, view_dir=None):
+        if view_dir is None:
+            return self.ppd_centre
+        view_angle = torch.sqrt(torch.sum((view_dir) ** 2, dim=0, keepdim=False))
+        return self.ppd_centre / (view_angle / 20. + 1.)
+
+
+def gen_widened_cases():
+    test, ref = synth_pair_numpy(12, 270, 480)
+    # heat-map visualisation: colour maps over the tone-mapped test frame (visualize_diff_map.py)
+    for mode in ("threshold", "supra-threshold"):
+        fv = pyfvvdp.fvvdp(display_name="standard_fhd", device=CPU, heatmap=mode)
+        q, st = fv.predict(torch.tensor(test[:, :, :4]), torch.tensor(ref[:, :, :4]), dim_order="BCFHW", frames_per_second=30)
+        hm = st["heatmap"].float().numpy()
+        save(f"video_fhd_heatmap_{mode}", jod=float(q), heatmap_sub=hm[0, :, :, ::SY, ::SX], hm_mean=hm.mean(axis=(0, 2, 3, 4)))
+    # the same on an image whose luminance range is below the tone-mapping threshold (linear branch of vis_tonemap)
+    fv = pyfvvdp.fvvdp(display_name="standard_fhd", device=CPU, heatmap="threshold")
+    ti, ri = 0.5 + 0.1 * test[0, :, 0:1], 0.5 + 0.1 * ref[0, :, 0:1]
+    q, st = fv.predict(torch.tensor(ti), torch.tensor(ri), dim_order="CFHW")
+    hm = st["heatmap"].float().numpy()
+    save("image_fhd_heatmap_threshold_lowdr", jod=float(q), heatmap_sub=hm[0, :, :, ::SY, ::SX], hm_mean=hm.mean(axis=(0, 2, 3, 4)))
+    # foveated scoring with a custom fvvdp_display_geometry subclass (ex_custom_ppd.py), moving gaze
+    gaze = np.stack([np.linspace(0, 479, 6), np.linspace(269, 0, 6)], 1).astype(np.float32)
+    geo = custom_display_geometry([480, 270], distance_m=0.6, diagonal_size_inches=24)
+    fv = pyfvvdp.fvvdp(display_name="standard_fhd", display_geometry=geo, device=CPU, foveated=True)
+    q, st = fv.predict(torch.tensor(test[:, :, :6]), torch.tensor(ref[:, :, :6]), dim_order="BCFHW", frames_per_second=30, fixation_point=gaze)
+    save("video_custom_geometry_foveated", jod=float(q), Q_per_ch=st["Q_per_ch"], gaze=gaze, rho_band=st["rho_band"])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_grad_enabled(False)
+    if len(sys.argv) > 1 and sys.argv[1] == "widen":
+        gen_widened_cases()
+        sys.exit(0)
     gen_unit_cases()
     gen_metric_cases()
     gen_known_answer()
+    gen_widened_cases()
