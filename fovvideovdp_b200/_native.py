@@ -19,7 +19,8 @@ TAP_R, TAP_GAUSS, TAP_CONTRAST, TAP_LBKG, TAP_S, TAP_D, TAP_DMAP_BAND = range(7)
 EXPORTS = ["fvvdp_b200_create", "fvvdp_b200_score_block", "fvvdp_b200_heatmap", "fvvdp_b200_read_tap",
            "fvvdp_b200_level_size", "fvvdp_b200_launch_count", "fvvdp_b200_traffic_model", "fvvdp_b200_destroy",
            "fvvdp_b200_last_error", "fvvdp_b200_abi_version", "fvvdp_b200_pool_jod",
-           "fvvdp_b200_profile", "fvvdp_b200_profile_read"]
+           "fvvdp_b200_profile", "fvvdp_b200_profile_read", "fvvdp_b200_heatmap_visualize", "fvvdp_b200_set_foveation_maps"]
+COLORMAPS = {"threshold": 0, "supra-threshold": 1}
 PROFILE_CLASSES = MAX_LEVELS + 2
 
 
@@ -81,6 +82,10 @@ def load_library():
     lib.fvvdp_b200_score_block.restype = C.c_int
     lib.fvvdp_b200_heatmap.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
     lib.fvvdp_b200_heatmap.restype = C.c_int
+    lib.fvvdp_b200_heatmap_visualize.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    lib.fvvdp_b200_heatmap_visualize.restype = C.c_int
+    lib.fvvdp_b200_set_foveation_maps.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.fvvdp_b200_set_foveation_maps.restype = C.c_int
     lib.fvvdp_b200_read_tap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
     lib.fvvdp_b200_read_tap.restype = C.c_int64
     lib.fvvdp_b200_level_size.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
@@ -153,6 +158,14 @@ class Context:
     def heatmap(self, frame, beta_jod, jod_a_abs, out_ptr, stream):
         self._check(self._lib.fvvdp_b200_heatmap(self.handle, int(frame), float(beta_jod), float(jod_a_abs), C.c_void_p(out_ptr),
                                                  C.c_void_p(stream)), "fvvdp_b200_heatmap")
+
+    def heatmap_visualize(self, frame, beta_jod, jod_a_abs, colormap, out_ptr, stream):
+        self._check(self._lib.fvvdp_b200_heatmap_visualize(self.handle, int(frame), float(beta_jod), float(jod_a_abs), COLORMAPS[colormap],
+                                                           C.c_void_p(out_ptr), C.c_void_p(stream)), "fvvdp_b200_heatmap_visualize")
+
+    def set_foveation_maps(self, level, view_ptr, log2_rho_ptr):
+        self._check(self._lib.fvvdp_b200_set_foveation_maps(self.handle, int(level), C.c_void_p(view_ptr), C.c_void_p(log2_rho_ptr)),
+                    "fvvdp_b200_set_foveation_maps")
 
     def read_tap(self, tap, level, frame, dst_ptr, capacity, stream):
         return self._check(self._lib.fvvdp_b200_read_tap(self.handle, int(tap), int(level), int(frame), C.c_void_p(dst_ptr),

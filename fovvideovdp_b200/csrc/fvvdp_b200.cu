@@ -35,6 +35,10 @@ struct fvvdp_b200_ctx {
   float* tapD[FVVDP_B200_MAX_LEVELS] = {};
   float* dmap[FVVDP_B200_MAX_LEVELS] = {};
   float* recon[2] = {};                        // ping-pong buffers for the heat-map reconstruction
+  float* ctxmap = nullptr;                     // fused, want_dmap == 2: [T][H][W] sustained test frames (context of the visualisation)
+  VisWork* vis = nullptr;                      // want_dmap == 2: scratch of the heat-map visualisation
+  const float* fov_view[FVVDP_B200_MAX_LEVELS] = {};  // custom display geometry (caller-owned): [2][h_l][w_l] view directions
+  const float* fov_rq[FVVDP_B200_MAX_LEVELS] = {};    //   and [h_l][w_l] log2(clamped rho)
   float* axes = nullptr;                       // x[3][32], inv[3][32]
   float* csf1d = nullptr;                      // [n_bands][2][32]
   float* lut3d = nullptr;                      // [2][32][32][32]
@@ -91,6 +95,7 @@ static void free_ctx(fvvdp_b200_ctx* c) {
   }
   cudaFree(c->cell);
   cudaFree(c->recon[0]); cudaFree(c->recon[1]);
+  cudaFree(c->ctxmap); cudaFree(c->vis);
   cudaFree(c->axes); cudaFree(c->csf1d); cudaFree(c->lut3d);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   delete c;
@@ -215,6 +220,10 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
     CUC(cudaMalloc(&c->recon[0], sizeof(float) * (size_t)cfg->height * cfg->width));
     CUC(cudaMalloc(&c->recon[1], sizeof(float) * (size_t)cfg->height * cfg->width));
   }
+  if (cfg->want_dmap >= 2) {
+    CUC(cudaMalloc(&c->vis, sizeof(VisWork)));
+    if (c->fused && !cfg->want_taps) CUC(cudaMalloc(&c->ctxmap, sizeof(float) * (size_t)cfg->height * cfg->width * T));
+  }
 
   // ---- CSF tables ----
   float hax[6][32];
@@ -271,7 +280,7 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
     CUC(cudaMalloc(&c->cell, sizeof(float) * cell.size()));
     CUC(cudaMemcpy(c->cell, cell.data(), sizeof(float) * cell.size(), cudaMemcpyHostToDevice));
   }
-  if (cfg->foveated) {
+  if (cfg->foveated == 1) {
     // pix2view_direction of each band's pixel centres, the band spanning the whole display
     // (fvvdp.py:422-428, fvvdp_display_model.py:498-510)
     for (int l = 0; l < c->n_bands; ++l) {
@@ -374,6 +383,27 @@ static cudaError_t launch_front(const FrontParams& fp, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// gaze view direction [deg]: foveated == 1: pix2view_direction at frame resolution of fixation + 0.5 (fvvdp.py:429-431,
+// fvvdp_display_model.py:498-510); foveated == 2 (custom geometry): the caller's plugin already converted it
+static void gaze_direction(const fvvdp_b200_config& cfg, const float* fix, float out[2]) {
+  if (cfg.foveated == 2) { out[0] = fix[0]; out[1] = fix[1]; return; }
+  const float gx = fix[0] + 0.5f, gy = fix[1] + 0.5f;
+  const float xm = (gx - (float)(cfg.width / 2.0)) * cfg.display_size_m[0] / (float)cfg.width;
+  const float ym = -(gy - (float)(cfg.height / 2.0)) * cfg.display_size_m[1] / (float)cfg.height;
+  out[0] = (float)(atan((double)(xm / cfg.distance_m)) * 180.0 / M_PI);
+  out[1] = (float)(atan((double)(ym / cfg.distance_m)) * 180.0 / M_PI);
+}
+
+extern "C" int fvvdp_b200_set_foveation_maps(fvvdp_b200_ctx* ctx, int level, const float* view_xy, const float* log2_rho) {
+  if (!ctx) return FVVDP_B200_ERR_INVALID;
+  if (ctx->cfg.foveated != 2) return fail(ctx, FVVDP_B200_ERR_INVALID, "ctx was not created with foveated = 2 (custom display geometry)");
+  if (level < 0 || level >= ctx->n_bands) return fail(ctx, FVVDP_B200_ERR_INVALID, "level %d is not a scored band", level);
+  if (!view_xy || !log2_rho) return fail(ctx, FVVDP_B200_ERR_INVALID, "null map");
+  ctx->fov_view[level] = view_xy;
+  ctx->fov_rq[level] = log2_rho;
+  return FVVDP_B200_OK;
+}
+
 extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* test_slots, const void* const* ref_slots,
                                       const int64_t strides[3], int n_frames, const float* fixation_xy, float* q_out,
                                       int64_t q_stride, int64_t q_col0, uint32_t* flags_out, void* cuda_stream) {
@@ -383,6 +413,9 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
   if (n_frames < 1 || n_frames > ctx->T) return fail(ctx, FVVDP_B200_ERR_INVALID, "n_frames %d not in 1..%d", n_frames, ctx->T);
   if (q_col0 < 0 || q_col0 + n_frames > q_stride) return fail(ctx, FVVDP_B200_ERR_INVALID, "q_out columns out of range");
   if (cfg.foveated && !fixation_xy) return fail(ctx, FVVDP_B200_ERR_INVALID, "foveated scoring needs fixation points");
+  if (cfg.foveated == 2)
+    for (int l = 0; l < ctx->n_bands; ++l)
+      if (!ctx->fov_view[l]) return fail(ctx, FVVDP_B200_ERR_INVALID, "custom display geometry: no foveation maps set for band %d", l);
   cudaStream_t st = (cudaStream_t)cuda_stream;
   CU(cudaSetDevice(ctx->dev));
   const int fl = cfg.filter_len, n_slots = n_frames + fl - 1;
@@ -453,13 +486,7 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
       const double delta = (1.0 / cfg.ppd_centre) / 2.0 * M_PI / 180.0;
       bp.res_k0 = (float)cos(delta);
       bp.res_delta_rad = (float)delta;
-      for (int i = 0; i < n_frames; ++i) {
-        const float gx = fixation_xy[2 * i] + 0.5f, gy = fixation_xy[2 * i + 1] + 0.5f;
-        const float xm = (gx - (float)(W / 2.0)) * cfg.display_size_m[0] / (float)W;
-        const float ym = -(gy - (float)(H / 2.0)) * cfg.display_size_m[1] / (float)H;
-        bp.gaze[i][0] = (float)(atan((double)(xm / cfg.distance_m)) * 180.0 / M_PI);
-        bp.gaze[i][1] = (float)(atan((double)(ym / cfg.distance_m)) * 180.0 / M_PI);
-      }
+      for (int i = 0; i < n_frames; ++i) gaze_direction(cfg, fixation_xy + 2 * i, bp.gaze[i]);
     }
     const bool extra = cfg.want_taps || cfg.want_dmap;
     for (int l = 0; l < ctx->n_bands; ++l) {
@@ -483,6 +510,8 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
       bp.log2_m = (l == 0) ? 0.0f : 1.0f;
       bp.rho_band = cfg.band_freq[l];
       bp.vx = ctx->vx[l]; bp.vy = ctx->vy[l];
+      bp.vmap = ctx->fov_view[l]; bp.rqmap = ctx->fov_rq[l];
+      bp.ctxmap = (l == 0) ? ctx->ctxmap : nullptr;
       bp.tapR = (l == 0) ? ctx->G[0] : nullptr;
       bp.tapG = cfg.want_taps ? ctx->G[l + 1] : nullptr;
       bp.tapC = ctx->tapC[l]; bp.tapL = ctx->tapL[l]; bp.tapS = ctx->tapS[l]; bp.tapD = ctx->tapD[l];
@@ -563,14 +592,8 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
       const double delta = (1.0 / cfg.ppd_centre) / 2.0 * M_PI / 180.0;
       lp.res_k0 = (float)cos(delta);
       lp.res_delta_rad = (float)delta;
-      for (int i = 0; i < n_frames; ++i) {
-        // gaze view direction at frame resolution, fixation + 0.5 (fvvdp.py:429-431)
-        const float gx = fixation_xy[2 * i] + 0.5f, gy = fixation_xy[2 * i + 1] + 0.5f;
-        const float xm = (gx - (float)(W / 2.0)) * cfg.display_size_m[0] / (float)W;
-        const float ym = -(gy - (float)(H / 2.0)) * cfg.display_size_m[1] / (float)H;
-        lp.gaze[i][0] = (float)(atan((double)(xm / cfg.distance_m)) * 180.0 / M_PI);
-        lp.gaze[i][1] = (float)(atan((double)(ym / cfg.distance_m)) * 180.0 / M_PI);
-      }
+      lp.vmap = ctx->fov_view[l]; lp.rqmap = ctx->fov_rq[l];
+      for (int i = 0; i < n_frames; ++i) gaze_direction(cfg, fixation_xy + 2 * i, lp.gaze[i]);
     }
     lp.tapC = ctx->tapC[l]; lp.tapL = ctx->tapL[l]; lp.tapS = ctx->tapS[l]; lp.tapD = ctx->tapD[l];
     lp.dmap = ctx->dmap[l];
@@ -654,14 +677,9 @@ extern "C" int64_t fvvdp_b200_read_tap(fvvdp_b200_ctx* ctx, int tap, int level, 
   return (int64_t)n;
 }
 
-extern "C" int fvvdp_b200_heatmap(fvvdp_b200_ctx* ctx, int frame, float beta_jod, float jod_a_abs, void* dmap_out_f16, void* cuda_stream) {
-  if (!ctx) return FVVDP_B200_ERR_INVALID;
-  if (!ctx->cfg.want_dmap) return fail(ctx, FVVDP_B200_ERR_INVALID, "ctx was created without want_dmap");
-  if (!dmap_out_f16) return fail(ctx, FVVDP_B200_ERR_INVALID, "null destination");
-  if (frame < 0 || frame >= ctx->last_n_frames) return fail(ctx, FVVDP_B200_ERR_INVALID, "frame %d not in the last block", frame);
-  cudaStream_t st = (cudaStream_t)cuda_stream;
-  CU(cudaSetDevice(ctx->dev));
-  // reconstruct (fvvdp_lpyr_dec.py:94-101) with a zero base band: coarse -> fine, expand + add
+// reconstruct (fvvdp_lpyr_dec.py:94-101) with a zero base band: coarse -> fine, expand + add.  The level-0 result goes to
+// out16 as |jod_a| recon^beta_jod, or (out16 == nullptr) stays in ctx->recon[0] as the plain reconstruction.
+static int reconstruct_dmap(fvvdp_b200_ctx* ctx, int frame, float beta_jod, float jod_a_abs, __half* out16, cudaStream_t st) {
   const float* coarse = nullptr;
   int ch = 0, cw = 0;
   for (int l = ctx->n_bands - 1; l >= 0; --l) {
@@ -669,12 +687,60 @@ extern "C" int fvvdp_b200_heatmap(fvvdp_b200_ctx* ctx, int frame, float beta_jod
     const float* band = ctx->dmap[l] + (size_t)frame * h * w;
     float* out = ctx->recon[l & 1];
     dim3 grid((w + 31) / 32, (h + 7) / 8);
-    recon_kernel<<<grid, 256, 0, st>>>(coarse, ch, cw, band, out, l == 0 ? (__half*)dmap_out_f16 : nullptr, h, w, beta_jod, jod_a_abs);
+    recon_kernel<<<grid, 256, 0, st>>>(coarse, ch, cw, band, out, l == 0 ? out16 : nullptr, h, w, beta_jod, jod_a_abs);
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "recon_kernel launch: %s", cudaGetErrorString(le));
     ctx->launches++;
     coarse = out; ch = h; cw = w;
   }
+  return FVVDP_B200_OK;
+}
+
+extern "C" int fvvdp_b200_heatmap(fvvdp_b200_ctx* ctx, int frame, float beta_jod, float jod_a_abs, void* dmap_out_f16, void* cuda_stream) {
+  if (!ctx) return FVVDP_B200_ERR_INVALID;
+  if (!ctx->cfg.want_dmap) return fail(ctx, FVVDP_B200_ERR_INVALID, "ctx was created without want_dmap");
+  if (!dmap_out_f16) return fail(ctx, FVVDP_B200_ERR_INVALID, "null destination");
+  if (frame < 0 || frame >= ctx->last_n_frames) return fail(ctx, FVVDP_B200_ERR_INVALID, "frame %d not in the last block", frame);
+  CU(cudaSetDevice(ctx->dev));
+  return reconstruct_dmap(ctx, frame, beta_jod, jod_a_abs, (__half*)dmap_out_f16, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int fvvdp_b200_heatmap_visualize(fvvdp_b200_ctx* ctx, int frame, float beta_jod, float jod_a_abs, int colormap, void* rgb_out_f16,
+                                            void* cuda_stream) {
+  if (!ctx) return FVVDP_B200_ERR_INVALID;
+  if (ctx->cfg.want_dmap < 2) return fail(ctx, FVVDP_B200_ERR_INVALID, "ctx was created without want_dmap = 2");
+  if (!rgb_out_f16) return fail(ctx, FVVDP_B200_ERR_INVALID, "null destination");
+  if (frame < 0 || frame >= ctx->last_n_frames) return fail(ctx, FVVDP_B200_ERR_INVALID, "frame %d not in the last block", frame);
+  // colour maps of visualize_diff_map.py:66-82
+  static const float kThr[5][3] = {{0.2f, 0.2f, 1.0f}, {0.2f, 1.0f, 1.0f}, {0.2f, 1.0f, 0.2f}, {1.0f, 1.0f, 0.2f}, {1.0f, 0.2f, 0.2f}};
+  static const float kSup[3][3] = {{0.2f, 1.0f, 1.0f}, {1.0f, 1.0f, 1.0f}, {1.0f, 1.0f, 0.2f}};
+  VisColorMap cm;
+  memset(&cm, 0, sizeof(cm));
+  const float (*src)[3];
+  if (colormap == FVVDP_B200_CMAP_THRESHOLD) { cm.n = 5; src = kThr; }
+  else if (colormap == FVVDP_B200_CMAP_SUPRA_THRESHOLD) { cm.n = 3; src = kSup; }
+  else return fail(ctx, FVVDP_B200_ERR_INVALID, "Unknown colormap: %d", colormap);
+  for (int i = 0; i < cm.n; ++i) {
+    cm.in[i] = (float)i / (float)(cm.n - 1);
+    const float lum = src[i][0] * 0.212656f + src[i][1] * 0.715158f + src[i][2] * 0.072186f;
+    for (int c = 0; c < 3; ++c) cm.ch[i][c] = src[i][c] / (lum + 0.0001f);
+  }
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  CU(cudaSetDevice(ctx->dev));
+  int rc = reconstruct_dmap(ctx, frame, beta_jod, jod_a_abs, nullptr, st);
+  if (rc != FVVDP_B200_OK) return rc;
+  const long long n = (long long)ctx->cfg.height * ctx->cfg.width;
+  // context image = R[:,0], the sustained (or, for an image, the only) channel of the TEST stream (fvvdp.py:475)
+  const float* y = ctx->ctxmap ? ctx->ctxmap + (size_t)frame * n : ctx->G[0] + (size_t)frame * ctx->nch * n;
+  const unsigned blocks = (unsigned)((n + 255) / 256), rblocks = blocks < 1184u ? blocks : 1184u;
+  vis_reset_kernel<<<1, 1024, 0, st>>>(ctx->vis);
+  vis_range_kernel<<<rblocks, 256, 0, st>>>(y, n, ctx->vis);
+  vis_hist_kernel<<<rblocks, 256, 0, st>>>(y, n, ctx->vis);
+  vis_curve_kernel<<<1, 1024, 0, st>>>(ctx->vis, (float)n);
+  vis_apply_kernel<<<blocks, 256, 0, st>>>(ctx->recon[0], y, n, ctx->vis, cm, beta_jod, jod_a_abs, (__half*)rgb_out_f16);
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "heat-map visualisation launch: %s", cudaGetErrorString(le));
+  ctx->launches += 5;
   return FVVDP_B200_OK;
 }
 

@@ -83,6 +83,8 @@ struct BandParams {
   float log2_sens_mul, rho_band;
   const float* vx;
   const float* vy;
+  const float* vmap;                          // custom display geometry: view direction per pixel [2][h][w] (deg), else nullptr
+  const float* rqmap;                         // custom display geometry: log2(clamp(rho_band * res_mag)) per pixel [h][w]
   float res_k0, res_delta_rad;
   float gaze[FVVDP_B200_MAX_BLOCK_FRAMES][2];
   // ---- optional outputs (EXTRA) ----
@@ -93,6 +95,7 @@ struct BandParams {
   float* tapS;   // [F][TC][h][w]
   float* tapD;   // [F][TC][h][w]
   float* dmap;   // [F][h][w]
+  float* ctxmap; // level 0: [F][h][w] sustained test frame = context image of the heat-map visualisation (fvvdp.py:475)
 };
 
 // ------------------------------------------------------------------------------------------------ packed fp32x2
@@ -637,12 +640,18 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
             int jj, ii, kk;
             float fy, fr, fe;
             locate_direct(yq, p.ax.x[1], p.ax.inv[1], p.ax.x0[1], p.ax.inv_dx[1], jj, fy);
-            const float vx = __ldg(p.vx + min(x, w - 1)), vy = __ldg(p.vy + min(y, h - 1));
+            float vx, vy, rq;
+            if (p.vmap != nullptr) {  // maps computed by a fvvdp_display_geometry subclass
+              const long long po = (long long)min(y, h - 1) * w + min(x, w - 1);
+              vx = __ldg(p.vmap + po); vy = __ldg(p.vmap + (long long)h * w + po); rq = __ldg(p.rqmap + po);
+            } else {
+              vx = __ldg(p.vx + min(x, w - 1)); vy = __ldg(p.vy + min(y, h - 1));
+              const float va = fminf(sqrtf(vx * vx + vy * vy), 89.9f) * 0.017453292519943295f;
+              const float res_mag = p.res_k0 / (__cosf(va) * __cosf(va + p.res_delta_rad));
+              rq = fast_log2(fminf(fmaxf(p.rho_band * res_mag, p.ax.lo[0]), p.ax.hi[0]));
+            }
             const float ex = vx - p.gaze[fi][0], ey = vy - p.gaze[fi][1];
             const float ecc = sqrtf(ex * ex + ey * ey);
-            const float va = fminf(sqrtf(vx * vx + vy * vy), 89.9f) * 0.017453292519943295f;
-            const float res_mag = p.res_k0 / (__cosf(va) * __cosf(va + p.res_delta_rad));
-            const float rq = fast_log2(fminf(fmaxf(p.rho_band * res_mag, p.ax.lo[0]), p.ax.hi[0]));
             const float eq = sqrtf(fminf(fmaxf(ecc, p.ax.lo[2]), p.ax.hi[2]));
             locate_direct(rq, p.ax.x[0], p.ax.inv[0], p.ax.x0[0], p.ax.inv_dx[0], ii, fr);
             locate_direct(eq, p.ax.x[2], p.ax.inv[2], p.ax.x0[2], p.ax.inv_dx[2], kk, fe);
@@ -694,6 +703,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
             p.tapR[((long long)fi * NCH + cc * 2 + 1) * plane + pofs] = hi_of(R[cc][e]);
           }
           if (cc == TC - 1 && p.dmap) p.dmap[(long long)fi * plane + pofs] = Dsum[e] / p.band_mul;
+          if (LEVEL0 && cc == 0 && p.ctxmap) p.ctxmap[(long long)fi * plane + pofs] = lo_of(R[0][e]);
         }
       }
     }

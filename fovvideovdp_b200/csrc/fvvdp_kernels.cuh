@@ -183,6 +183,8 @@ struct LevelParams {
   // foveation
   const float* vx;     // [w] horizontal view direction of the band's pixel columns (deg)
   const float* vy;     // [h]
+  const float* vmap;   // custom display geometry: view direction per pixel [2][h][w] (deg), else nullptr
+  const float* rqmap;  // custom display geometry: log2(clamp(rho_band * res_mag)) per pixel [h][w]
   float res_k0, res_delta_rad;  // res_mag = res_k0 / (cos(a) cos(a+delta))
   float gaze[FVVDP_B200_MAX_BLOCK_FRAMES][2];
   // optional outputs
@@ -333,12 +335,17 @@ __global__ void __launch_bounds__(LEVEL_THREADS) level_kernel(const __grid_const
         int i0 = 0, i1 = 0, k0 = 0, k1 = 0;
         float fi = 0.0f, fk = 0.0f;
         if (FOV) {
-          const float vx = __ldg(p.vx + x), vy = __ldg(p.vy + y);
+          float vx, vy, rq;
+          if (p.vmap != nullptr) {  // maps computed by a fvvdp_display_geometry subclass
+            vx = __ldg(p.vmap + pofs); vy = __ldg(p.vmap + plane + pofs); rq = __ldg(p.rqmap + pofs);
+          } else {
+            vx = __ldg(p.vx + x); vy = __ldg(p.vy + y);
+            const float va = fminf(sqrtf(vx * vx + vy * vy), 89.9f) * 0.017453292519943295f;
+            const float res_mag = p.res_k0 / (__cosf(va) * __cosf(va + p.res_delta_rad));
+            rq = fast_log2(fminf(fmaxf(p.rho_band * res_mag, p.ax.lo[0]), p.ax.hi[0]));
+          }
           const float ex = vx - p.gaze[f][0], ey = vy - p.gaze[f][1];
           const float ecc = sqrtf(ex * ex + ey * ey);
-          const float va = fminf(sqrtf(vx * vx + vy * vy), 89.9f) * 0.017453292519943295f;
-          const float res_mag = p.res_k0 / (__cosf(va) * __cosf(va + p.res_delta_rad));
-          const float rq = fast_log2(fminf(fmaxf(p.rho_band * res_mag, p.ax.lo[0]), p.ax.hi[0]));
           const float eq = sqrtf(fminf(fmaxf(ecc, p.ax.lo[2]), p.ax.hi[2]));
           locate(rq, p.ax.x[0], p.ax.inv[0], p.ax.x0[0], p.ax.inv_dx[0], i0, i1, fi);
           locate(eq, p.ax.x[2], p.ax.inv[2], p.ax.x0[2], p.ax.inv_dx[2], k0, k1, fk);
@@ -504,6 +511,132 @@ __global__ void __launch_bounds__(256) recon_kernel(const float* __restrict__ co
   const float v = e + band[(long long)y * w + x];
   if (out16 != nullptr) out16[(long long)y * w + x] = __float2half(powf(v, beta_jod) * jod_a_abs);
   else out[(long long)y * w + x] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Heat-map visualisation (visualize_diff_map.py:9-107): colour map of the difference map over the tone-mapped
+// context frame (the sustained test frame, fvvdp.py:475).  Four small kernels per frame:
+//   vis_range   min over the positive values and max of the context luminance
+//   vis_hist    1024-bin histogram of its log (torch.histc semantics)
+//   vis_curve   tone curve: cumulative sum of the cube root of the normalised histogram (vis_tonemap :26-50)
+//   vis_apply   dmap = |jod_a| recon^beta_jod, colour-map look-up, times the tone-mapped context, clip, fp16
+// ------------------------------------------------------------------------------------------------
+struct VisWork {            // device scratch, one per context
+  unsigned int range[2];    // bit patterns of (min positive y, max y)
+  unsigned int hist[1024];
+  float curve[1024];        // v of vis_tonemap
+  float b_min, b_max, clampval;
+  int linear;               // b_max - b_min < dr: no tone mapping
+};
+constexpr float VIS_DR = 0.6f;
+
+__global__ void vis_reset_kernel(VisWork* ws) {
+  const int i = threadIdx.x;
+  ws->hist[i] = 0u;
+  if (i == 0) { ws->range[0] = 0x7f800000u; ws->range[1] = 0u; }
+}
+
+__global__ void __launch_bounds__(256) vis_range_kernel(const float* __restrict__ y, long long n, VisWork* ws) {
+  unsigned int lo = 0x7f800000u, hi = 0u;  // positive floats order like their bit patterns
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += 256ll * gridDim.x) {
+    const float v = __ldg(y + i);
+    if (v > 0.0f) { lo = min(lo, __float_as_uint(v)); hi = max(hi, __float_as_uint(v)); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(&ws->range[0], lo); atomicMax(&ws->range[1], hi); }
+}
+
+// log-luminance of the context frame (log_luminance, visualize_diff_map.py:20-23)
+__device__ __forceinline__ float vis_log_lum(float y, float clampval) { return logf(fmaxf(y, clampval)); }
+
+__global__ void __launch_bounds__(256) vis_hist_kernel(const float* __restrict__ y, long long n, VisWork* ws) {
+  __shared__ unsigned int sh[1024];
+  for (int i = threadIdx.x; i < 1024; i += 256) sh[i] = 0u;
+  __syncthreads();
+  const float clampval = __uint_as_float(ws->range[0]);
+  const float b_min = logf(clampval), b_max = logf(fmaxf(__uint_as_float(ws->range[1]), clampval));
+  const float range = b_max - b_min;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += 256ll * gridDim.x) {
+    const float b = vis_log_lum(__ldg(y + i), clampval);
+    int pos = (int)((b - b_min) / range * 1024.0f);  // torch.histc; the maximum falls into the last bin
+    pos = min(max(pos, 0), 1023);
+    atomicAdd(&sh[pos], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 1024; i += 256)
+    if (sh[i]) atomicAdd(&ws->hist[i], sh[i]);
+}
+
+__global__ void __launch_bounds__(1024) vis_curve_kernel(VisWork* ws, float n_pix) {
+  __shared__ float sc[1024];
+  __shared__ float total;
+  const int i = threadIdx.x;
+  const float clampval = __uint_as_float(ws->range[0]);
+  const float b_min = logf(clampval), b_max = logf(fmaxf(__uint_as_float(ws->range[1]), clampval));
+  const float pw = cbrtf((float)ws->hist[i] / n_pix);  // b_p^(1/t), t = 3
+  sc[i] = pw;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {  // inclusive scan
+    const float add = i >= o ? sc[i - o] : 0.0f;
+    __syncthreads();
+    sc[i] += add;
+    __syncthreads();
+  }
+  if (i == 1023) total = sc[1023];
+  __syncthreads();
+  ws->curve[i] = sc[i] / total * VIS_DR + (1.0f - VIS_DR) / 2.0f;
+  if (i == 0) {
+    ws->b_min = b_min; ws->b_max = b_max; ws->clampval = clampval;
+    ws->linear = (b_max - b_min < VIS_DR) ? 1 : 0;
+  }
+}
+
+struct VisColorMap {  // colour-map nodes already divided by (their luminance + 1e-4), visualize_diff_map.py:96-98
+  int n;
+  float in[5];
+  float ch[5][3];
+};
+
+// torch.linspace(b_min, b_max, 1024)[i] in float32
+__device__ __forceinline__ float vis_scale(int i, float b_min, float b_max, float step) {
+  return i < 512 ? b_min + step * (float)i : b_max - step * (float)(1023 - i);
+}
+
+__global__ void __launch_bounds__(256) vis_apply_kernel(const float* __restrict__ recon, const float* __restrict__ y, long long n,
+                                                        const VisWork* __restrict__ ws, VisColorMap cm, float beta_jod, float jod_a_abs,
+                                                        __half* __restrict__ out) {
+  const long long i = blockIdx.x * 256ll + threadIdx.x;
+  if (i >= n) return;
+  const float b_min = ws->b_min, b_max = ws->b_max;
+  const float d = fminf(fmaxf(powf(recon[i], beta_jod) * jod_a_abs, 0.0f), 1.0f);
+  const float b = vis_log_lum(__ldg(y + i), ws->clampval);
+  float tmo;
+  if (ws->linear) {
+    tmo = (b - b_min) / (b_max - b_min + 1e-3f) * VIS_DR + (1.0f - VIS_DR) / 2.0f;
+  } else {
+    // interp1(b_scale, v, b) with get_interpolants_v1 (interp.py:11-20): imax = first index with b_scale[imax] >= b
+    const float step = (b_max - b_min) / 1023.0f;
+    int j = min(max((int)ceilf((b - b_min) / step), 0), 1023);
+    while (j > 0 && vis_scale(j - 1, b_min, b_max, step) >= b) --j;
+    while (j < 1023 && vis_scale(j, b_min, b_max, step) < b) ++j;
+    const int j0 = max(j - 1, 0);
+    const float x0 = vis_scale(j0, b_min, b_max, step), x1 = vis_scale(j, b_min, b_max, step);
+    const float f = (j == j0) ? 0.0f : fmaxf((b - x0) / (x1 - x0 + 0.000001f), 0.0f);
+    tmo = ws->curve[j0] * (1.0f - f) + ws->curve[j] * f;
+  }
+  int k = 0;
+  while (k < cm.n - 1 && cm.in[k] < d) ++k;  // bucketize
+  const int k0 = max(k - 1, 0);
+  const float fk = (k == k0) ? 0.0f : fmaxf((d - cm.in[k0]) / (cm.in[k] - cm.in[k0] + 0.000001f), 0.0f);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = cm.ch[k0][c] * (1.0f - fk) + cm.ch[k][c] * fk;
+    out[c * n + i] = __float2half(fminf(fmaxf(v * tmo, 0.0f), 1.0f));
+  }
 }
 
 }  // namespace fvvdp

@@ -306,13 +306,16 @@ class fvvdp:
         cfg.sens_mul = 10.0 ** (self.sensitivity_correction / 20.0)
         cfg.beta = self.beta
         cfg.w_transient = self.w_transient
-        cfg.foveated = 1 if self.foveated else 0
         geo = self.display_geometry
+        cfg.foveated = 0
         if self.foveated:
-            cfg.display_size_m[0], cfg.display_size_m[1] = float(geo.display_size_m[0]), float(geo.display_size_m[1])
-            cfg.distance_m = float(geo.distance_m)
+            # a fvvdp_display_geometry subclass supplies its own per-band maps (fvvdp_b200_set_foveation_maps)
+            cfg.foveated = 1 if geometry_is_stock(geo) else 2
+            if cfg.foveated == 1:
+                cfg.display_size_m[0], cfg.display_size_m[1] = float(geo.display_size_m[0]), float(geo.display_size_m[1])
+                cfg.distance_m = float(geo.distance_m)
         cfg.ppd_centre = float(self.pix_per_deg)
-        cfg.want_dmap = 1 if self.do_heatmap else 0
+        cfg.want_dmap = 0 if not self.do_heatmap else (1 if self.heatmap == "raw" else 2)
         cfg.want_taps = 1 if self.debug_taps else 0
         cfg.max_block_frames = T
         return cfg, keep
@@ -346,11 +349,6 @@ class fvvdp:
             F = temporal_filters(fps, fl, self.sustained_sigma, self.sustained_beta)
             self.F = torch.from_numpy(F)
 
-        if self.foveated and not geometry_is_stock(self.display_geometry):
-            raise NotImplementedError("foveated scoring with a custom fvvdp_display_geometry subclass is not implemented yet")
-        if self.do_heatmap and self.heatmap != "raw":
-            raise NotImplementedError(f"heatmap='{self.heatmap}' is not implemented yet (use 'raw')")
-
         # how the frames reach the kernels
         spec = None
         if is_array_source(vid_source):
@@ -381,8 +379,8 @@ class fvvdp:
 
         geo = self.display_geometry
         key = (width, height, n_levels, tuple(float(f) for f in freqs), temp_ch, fl, F.tobytes(), tuple(sorted(spec.items())), dtype, C, T,
-               self.foveated, self.do_heatmap, self.debug_taps, self.color_space,
-               (tuple(geo.display_size_m), geo.distance_m) if self.foveated else None)
+               self.foveated, self.heatmap if self.do_heatmap else None, self.debug_taps, self.color_space,
+               (tuple(geo.display_size_m), geo.distance_m, geometry_is_stock(geo)) if self.foveated else None)
         ctx = self._context(key, lambda: self._make_config(width, height, n_levels, freqs, temp_ch, fl, F, spec, dtype, C, T))
 
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -390,8 +388,12 @@ class fvvdp:
         flags = torch.zeros(1, dtype=torch.int32, device=dev)
         heatmap = None
         if self.do_heatmap:
-            heatmap = torch.zeros([1, 1, N_frames, height, width], dtype=torch.float16, device="cpu")
-            hm_dev = torch.empty((height, width), dtype=torch.float16, device=dev)
+            hm_ch = 1 if self.heatmap == "raw" else 3  # fvvdp.py:236
+            heatmap = torch.zeros([1, hm_ch, N_frames, height, width], dtype=torch.float16, device="cpu")
+            hm_dev = torch.empty((hm_ch, height, width), dtype=torch.float16, device=dev)
+        custom_geo = self.foveated and not geometry_is_stock(geo)
+        if custom_geo:
+            fov_maps = self._custom_foveation_maps(ctx, n_bands, freqs)  # kept alive until the end of this call
         first = initial_window(N_frames, fl, self.temp_padding) if not is_image else [0]
 
         def frame_at(t):  # frame shown at time t (t <= 0 falls into the temporal padding)
@@ -425,13 +427,18 @@ class fvvdp:
                 fix = None
                 if self.foveated:
                     fix = [fixation_point[f0 + i] if fixation_point.ndim == 2 else fixation_point for i in range(n)]
+                    if custom_geo:  # gaze direction [deg] through the plugin (fvvdp.py:429-431)
+                        fix = [self._gaze_direction(xy, width, height) for xy in fix]
                 ctx.score_block([p[0] for p in ptrs], [p[1] for p in ptrs], frames.strides, n, fix, Q_per_ch.data_ptr(), N_frames, f0,
                                 flags.data_ptr(), stream)
                 if self.do_heatmap:
                     beta_jod = 10.0 ** self.log_jod_exp
                     for i in range(n):
-                        ctx.heatmap(i, beta_jod, abs(self.jod_a), hm_dev.data_ptr(), stream)
-                        heatmap[0, 0, f0 + i].copy_(hm_dev)
+                        if self.heatmap == "raw":
+                            ctx.heatmap(i, beta_jod, abs(self.jod_a), hm_dev.data_ptr(), stream)
+                        else:
+                            ctx.heatmap_visualize(i, beta_jod, abs(self.jod_a), self.heatmap, hm_dev.data_ptr(), stream)
+                        heatmap[0, :, f0 + i].copy_(hm_dev)
                 scored = None
                 if frames.up_stream is not None:
                     scored = torch.cuda.Event()
@@ -461,6 +468,31 @@ class fvvdp:
         if self.do_heatmap:
             stats["heatmap"] = heatmap
         return out[0], stats
+
+    # ------------------------------------------------------------------ custom display geometry (foveated)
+    def _custom_foveation_maps(self, ctx, n_bands, freqs):
+        """Per-band view-direction and log2(rho) maps from the plugin's own pix2view_direction() and
+        get_resolution_magnification(), as the reference calls them for every band (fvvdp.py:422-438)."""
+        geo, dev, lut = self.display_geometry, self.device, self.lut
+        keep = []
+        for bb in range(n_bands):
+            h, w = ctx.level_size(bb)
+            xv = torch.linspace(0.5, w - 0.5, w, device=dev)
+            yv = torch.linspace(0.5, h - 0.5, h, device=dev)
+            xx, yy = torch.meshgrid(xv, yv, indexing="xy")
+            view = geo.pix2view_direction(torch.tensor((w, h)), xx, yy).to(device=dev, dtype=torch.float32)
+            res_mag = torch.as_tensor(geo.get_resolution_magnification(view), dtype=torch.float32, device=dev)
+            rho = (float(freqs[bb]) * res_mag).expand(h, w)
+            rq = torch.log2(torch.clamp(rho, float(lut["rho"][0]), float(lut["rho"][-1]))).contiguous()
+            view = view.reshape(2, h, w).contiguous()
+            ctx.set_foveation_maps(bb, view.data_ptr(), rq.data_ptr())
+            keep.append((view, rq))
+        return keep
+
+    def _gaze_direction(self, xy, width, height):
+        d = self.display_geometry.pix2view_direction(torch.tensor((width, height)), torch.as_tensor(float(xy[0]) + 0.5),
+                                                     torch.as_tensor(float(xy[1]) + 0.5))
+        return [float(d[0]), float(d[1])]
 
     # ------------------------------------------------------------------ debugging taps (tests)
     def read_tap(self, tap, level, frame_in_block):

@@ -95,11 +95,14 @@ typedef struct fvvdp_b200_config {
   float sens_mul;             /* 10^(sensitivity_correction/20) */
   float beta;                 /* spatial pooling exponent */
   float w_transient;          /* used only for the heat-map bands */
-  /* foveation */
+  /* foveation: 0 = off; 1 = stock fvvdp_display_geometry (maps computed from display_size_m / distance_m / ppd_centre);
+   * 2 = custom geometry plugin: per-band maps are supplied with fvvdp_b200_set_foveation_maps and fixation_xy of
+   * score_block holds the gaze DIRECTION in degrees (the plugin's pix2view_direction of the fixation point) */
   int32_t foveated;
   float display_size_m[2], distance_m, ppd_centre;
   /* options */
-  int32_t want_dmap;          /* keep per-band difference maps for the heat-map path */
+  int32_t want_dmap;          /* 1: keep per-band difference maps for the heat-map path; 2: also keep the sustained test
+                               * frames (context image of fvvdp_b200_heatmap_visualize) */
   int32_t want_taps;          /* keep intermediate tensors readable through fvvdp_b200_read_tap (tests) */
   int32_t max_block_frames;   /* frames scored per call, 1..FVVDP_B200_MAX_BLOCK_FRAMES */
 } fvvdp_b200_config;
@@ -132,6 +135,25 @@ int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* test_slots, c
  */
 int fvvdp_b200_heatmap(fvvdp_b200_ctx* ctx, int frame_in_block, float beta_jod, float jod_a_abs, void* dmap_out_f16,
                        void* cuda_stream);
+
+/*
+ * Heat-map visualisation (fvvdp.py:474-476 -> visualize_diff_map, visualize_diff_map.py:58-107; heatmap="threshold" /
+ * "supra-threshold"): the difference map of frame `frame_in_block`, clamped to [0,1], goes through the colour map
+ * and is multiplied by the tone-mapped context image (log luminance of the sustained test frame, 1024-bin histogram
+ * tone curve, vis_tonemap :26-50).  Writes fp16 sRGB planes (3,H,W) to `rgb_out_f16` (DEVICE).  Requires want_dmap = 2.
+ */
+typedef enum { FVVDP_B200_CMAP_THRESHOLD = 0, FVVDP_B200_CMAP_SUPRA_THRESHOLD = 1 } fvvdp_b200_colormap;
+int fvvdp_b200_heatmap_visualize(fvvdp_b200_ctx* ctx, int frame_in_block, float beta_jod, float jod_a_abs, int colormap,
+                                 void* rgb_out_f16, void* cuda_stream);
+
+/*
+ * Foveation maps of a custom fvvdp_display_geometry subclass (the reference calls the plugin's pix2view_direction and
+ * get_resolution_magnification per band, fvvdp.py:422-438; example: pytorch_examples/ex_custom_ppd.py:38-57).
+ *   view_xy:  DEVICE (2, h_l, w_l) view direction of every band pixel in degrees
+ *   log2_rho: DEVICE (h_l, w_l) log2 of rho_band[l] * res_mag clamped to the CSF table's rho range
+ * The caller keeps both alive while the ctx scores.  Requires cfg.foveated = 2; every scored band needs its maps.
+ */
+int fvvdp_b200_set_foveation_maps(fvvdp_b200_ctx* ctx, int level, const float* view_xy, const float* log2_rho);
 
 typedef struct fvvdp_b200_pool_params {
   float beta_sch, beta_tch, beta_t; /* Lp exponents over spatial bands, temporal channels, frames */

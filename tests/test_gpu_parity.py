@@ -140,6 +140,65 @@ def test_heatmap_raw(fv_mod, golden):
     assert abs(hm.mean() - float(g["hm_mean"])) < 2e-4
 
 
+@pytest.mark.parametrize("mode", ["threshold", "supra-threshold"])
+def test_heatmap_colour_maps(fv_mod, golden, mode):
+    """heatmap="threshold" / "supra-threshold": colour map over the tone-mapped sustained test frame
+    (visualize_diff_map.py:58-107) -> (1,3,N,H,W) fp16 on the CPU.  fp16 storage + histogram-bin jitter of log values."""
+    g = golden(f"video_fhd_heatmap_{mode}")
+    t, r = synth_pair_numpy(4, 270, 480)
+    jod, st = fv_mod.fvvdp(display_name="standard_fhd", heatmap=mode).predict(t, r, frames_per_second=30)
+    check_jod(jod, g["jod"])
+    hm = st["heatmap"]
+    assert hm.dtype == torch.float16 and tuple(hm.shape) == (1, 3, 4, 270, 480) and hm.device.type == "cpu"
+    hm = hm.float().numpy()
+    np.testing.assert_allclose(hm[0, :, :, ::SY, ::SX], g["heatmap_sub"], rtol=3e-3, atol=3e-3)
+    np.testing.assert_allclose(hm.mean(axis=(0, 2, 3, 4)), g["hm_mean"], atol=3e-4)
+
+
+def test_heatmap_colour_map_low_dynamic_range(fv_mod, golden):
+    g = golden("image_fhd_heatmap_threshold_lowdr")
+    t, r = synth_pair_numpy(1, 270, 480)
+    ti, ri = 0.5 + 0.1 * t[0, :, 0:1], 0.5 + 0.1 * r[0, :, 0:1]
+    jod, st = fv_mod.fvvdp(display_name="standard_fhd", heatmap="threshold").predict(ti, ri, dim_order="CFHW")
+    check_jod(jod, g["jod"])
+    hm = st["heatmap"].float().numpy()
+    assert hm.shape == (1, 3, 1, 270, 480)
+    np.testing.assert_allclose(hm[0, :, :, ::SY, ::SX], g["heatmap_sub"], rtol=3e-3, atol=3e-3)
+    np.testing.assert_allclose(hm.mean(axis=(0, 2, 3, 4)), g["hm_mean"], atol=3e-4)
+
+
+def test_heatmap_colour_map_60fps_general_path(fv_mod, oracle):
+    """15-tap window (general kernels): the context frame comes from the materialised temporal channels."""
+    t, r = synth_pair_numpy(3, 135, 240)
+    jod, st = fv_mod.fvvdp(display_name="standard_fhd", heatmap="supra-threshold").predict(t, r, frames_per_second=60)
+    want, wst = oracle.predict(t, r, frames_per_second=60, display_name="standard_fhd", heatmap="supra-threshold")
+    check_jod(jod, want)
+    np.testing.assert_allclose(st["heatmap"].float().numpy(), wst["heatmap"].astype(np.float32), rtol=3e-3, atol=3e-3)
+
+
+def test_custom_geometry_foveated(fv_mod, golden):
+    """Foveated scoring with a fvvdp_display_geometry SUBCLASS (pytorch_examples/ex_custom_ppd.py:38-57): the per-band
+    view-direction / resolution-magnification maps come from the plugin's own methods."""
+    class custom_display_geometry(fv_mod.fvvdp_display_geometry):
+        def get_ppd(self, view_dir=None):
+            if view_dir is None:
+                return self.ppd_centre
+            view_angle = torch.sqrt(torch.sum((view_dir) ** 2, dim=0, keepdim=False))
+            return self.ppd_centre / (view_angle / 20. + 1.)
+
+    g = golden("video_custom_geometry_foveated")
+    t, r = synth_pair_numpy(12, 270, 480)
+    geo = custom_display_geometry([480, 270], distance_m=0.6, diagonal_size_inches=24)
+    fv = fv_mod.fvvdp(display_name="standard_fhd", display_geometry=geo, foveated=True)
+    jod, st = fv.predict(t[:, :, :6], r[:, :, :6], frames_per_second=30, fixation_point=g["gaze"])
+    check_jod(jod, g["jod"])
+    np.testing.assert_allclose(st["rho_band"], g["rho_band"], rtol=1e-6)
+    check_q(st["Q_per_ch"], g["Q_per_ch"], tol=1e-3)
+    # 60 fps: the same plugin maps through the general kernels
+    jod60, _ = fv.predict(t[:, :, :6], r[:, :, :6], frames_per_second=60, fixation_point=g["gaze"])
+    assert 0 < float(jod60) < 10
+
+
 @pytest.mark.parametrize("hw", [(135, 240), (136, 241), (67, 97), (64, 64)])
 def test_odd_sizes_with_taps(fv_mod, golden, hw):
     """Odd rows / columns at several pyramid levels, incl. the row-parity quirk of gausspyr_reduce
