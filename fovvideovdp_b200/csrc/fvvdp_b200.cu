@@ -42,6 +42,7 @@ struct fvvdp_b200_ctx {
   float* axes = nullptr;                       // x[3][32], inv[3][32]
   float* csf1d = nullptr;                      // [n_bands][2][32]
   float* lut3d = nullptr;                      // [2][32][32][32]
+  float4* lut4 = nullptr;                      // fused, foveated: [rho 32][ecc 32][Y 32] (t0, dt0/dY-cell, t1, dt1/dY-cell), t = log2(S * sens_mul)
   float* vx[FVVDP_B200_MAX_LEVELS] = {};
   float* vy[FVVDP_B200_MAX_LEVELS] = {};
   CsfAxes ax;
@@ -96,7 +97,7 @@ static void free_ctx(fvvdp_b200_ctx* c) {
   cudaFree(c->cell);
   cudaFree(c->recon[0]); cudaFree(c->recon[1]);
   cudaFree(c->ctxmap); cudaFree(c->vis);
-  cudaFree(c->axes); cudaFree(c->csf1d); cudaFree(c->lut3d);
+  cudaFree(c->axes); cudaFree(c->csf1d); cudaFree(c->lut3d); cudaFree(c->lut4);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   delete c;
 }
@@ -248,6 +249,23 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
   c->log2_sens_mul = log2f(cfg->sens_mul);
   CUC(cudaMalloc(&c->lut3d, sizeof(float) * 2 * 32768));
   CUC(cudaMemcpy(c->lut3d, cfg->csf_S_log, sizeof(float) * 2 * 32768, cudaMemcpyHostToDevice));
+  if (cfg->foveated) {
+    // both temporal channels and the step to the next Y entry in one 16-byte record, Y innermost: the 8 corners of a
+    // trilinear look-up for both channels are four 16-byte loads
+    std::vector<float4> l4(32768);
+    for (int i = 0; i < 32; ++i)
+      for (int k = 0; k < 32; ++k)
+        for (int j = 0; j < 32; ++j) {
+          const int j1 = j < 31 ? j + 1 : 31;
+          const float* v0 = cfg->csf_S_log;
+          const float* v1 = cfg->csf_S_log + 32768;
+          const float a0 = v0[(j * 32 + i) * 32 + k], b0 = v0[(j1 * 32 + i) * 32 + k];
+          const float a1 = v1[(j * 32 + i) * 32 + k], b1 = v1[(j1 * 32 + i) * 32 + k];
+          l4[(i * 32 + k) * 32 + j] = make_float4(a0 + c->log2_sens_mul, b0 - a0, a1 + c->log2_sens_mul, b1 - a1);
+        }
+    CUC(cudaMalloc(&c->lut4, sizeof(float4) * l4.size()));
+    CUC(cudaMemcpy(c->lut4, l4.data(), sizeof(float4) * l4.size(), cudaMemcpyHostToDevice));
+  }
   {
     // non-foveated: rho and ecc (=0) are constant per band -> 32-entry table over log2 Y per (band, cc)
     // (cached_sensitivity fvvdp.py:520-537 with rho = rho_band[bb], ecc = 0, fvvdp.py:438-442)
@@ -481,7 +499,7 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
     bp.y0 = ctx->ax.x0[1]; bp.inv_dy = ctx->ax.inv_dx[1]; bp.lg_y_hi = log2f(cfg.csf_Y_range[1]);
     bp.mask_p = cfg.mask_p; bp.mask_q[0] = cfg.mask_q[0]; bp.mask_q[1] = cfg.mask_q[1];
     bp.log2_mask_c = log2f(cfg.mask_c_mul); bp.beta = cfg.beta; bp.w_transient = cfg.w_transient;
-    bp.ax = ctx->ax; bp.lut3d = ctx->lut3d; bp.log2_sens_mul = ctx->log2_sens_mul;
+    bp.ax = ctx->ax; bp.lut4 = ctx->lut4; bp.log2_sens_mul = ctx->log2_sens_mul;
     if (cfg.foveated) {
       const double delta = (1.0 / cfg.ppd_centre) / 2.0 * M_PI / 180.0;
       bp.res_k0 = (float)cos(delta);

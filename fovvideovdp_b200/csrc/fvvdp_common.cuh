@@ -21,6 +21,11 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float fast_pow(float x, float p) { return fast_exp2(p * fast_log2(x)); }
 __device__ __forceinline__ float fast_rcp(float x) { return __frcp_rn(x); }
 

@@ -79,7 +79,7 @@ struct BandParams {
   float mask_p, mask_q[2], log2_mask_c, beta, w_transient;
   // foveated
   CsfAxes ax;
-  const float* lut3d;
+  const float4* lut4;                         // [rho][ecc][Y] (t0, dt0, t1, dt1): log2(S * sens_mul) of both temporal channels + step to Y+1
   float log2_sens_mul, rho_band;
   const float* vx;
   const float* vy;
@@ -254,6 +254,25 @@ __device__ __forceinline__ void eotf8(float (&x)[8], const BandParams& p) {
       if (KIND == FVVDP_B200_EOTF_SRGB) lin = (x[j] > 0.04045f) ? lin : __saturatef(x[j] * (1.0f / 12.92f));
       x[j] = fmaf(p.Yscale, lin, p.Y_black);
     }
+  } else if (KIND == FVVDP_B200_EOTF_PQ) {
+    // pq2lin (fvvdp_display_model.py:100-112) stage-wise: L = 1e4 (max(t - c1, 0) / (c2 - c3 t))^(1/n), t = V^(1/m); the
+    // quotient is taken in the log2 domain (5 MUFU operations per sample, no division)
+    const float n_inv = 1.0f / 0.15930175781250000f, m_inv = 1.0f / 78.843750000000000f;
+    const float c1 = 0.83593750000000000f, c2 = 18.851562500000000f, c3 = 18.687500000000000f;
+    float t[8], u[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) asm volatile("lg2.approx.ftz.f32 %0, %1;" : "=f"(t[j]) : "f"(__saturatef(x[j])));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(t[j]) : "f"(t[j] * m_inv));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      asm volatile("lg2.approx.ftz.f32 %0, %1;" : "=f"(u[j]) : "f"(fmaxf(t[j] - c1, 0.0f)));
+      asm volatile("lg2.approx.ftz.f32 %0, %1;" : "=f"(t[j]) : "f"(fmaf(-c3, t[j], c2)));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(t[j]) : "f"(fmaf(u[j] - t[j], n_inv, 13.287712379549449f)));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = fminf(fmaxf(t[j], 0.005f), p.Y_peak) + p.Y_black;
   } else {
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = eotf_k<KIND>(x[j], p);
@@ -353,6 +372,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
   float* sNc = (FL == 1) ? sNr : sNr + FL * 2 * NE;  // [TC][NE][2]   temporally filtered reduced tiles
   float* sTab = sNr + FL * 2 * NE + (FL == 1 ? 0 : NCH * NE);  // [32][8]
   float* sRed = sTab + 256;                          // [MAXCHUNK][2][NT/32]
+  float4* sFov = reinterpret_cast<float4*>(sRed + MAXCHUNK * 2 * (NT / 32));  // FOV: [4 quad pixels][NT] (view x, view y, rho fraction, rho cell)
   __shared__ __align__(8) u64 bars[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -422,6 +442,29 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
   bool valid[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) valid[e] = (qy + (e >> 1) < h) && (qx + (e & 1) < w);
+
+  if (FOV) {
+    // per-pixel constants of the time walk: view direction and the rho cell / fraction of the CSF look-up
+    // (rho = rho_band * resolution magnification, fvvdp.py:436-438)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int x = min(qx + (e & 1), w - 1), y = min(qy + (e >> 1), h - 1);
+      float vx, vy, rq;
+      if (p.vmap != nullptr) {  // maps computed by a fvvdp_display_geometry subclass
+        const long long po = (long long)y * w + x;
+        vx = __ldg(p.vmap + po); vy = __ldg(p.vmap + (long long)h * w + po); rq = __ldg(p.rqmap + po);
+      } else {
+        vx = __ldg(p.vx + x); vy = __ldg(p.vy + y);
+        const float va = fminf(sqrtf(vx * vx + vy * vy), 89.9f) * 0.017453292519943295f;
+        const float res_mag = p.res_k0 / (__cosf(va) * __cosf(va + p.res_delta_rad));
+        rq = fast_log2(fminf(fmaxf(p.rho_band * res_mag, p.ax.lo[0]), p.ax.hi[0]));
+      }
+      int ii;
+      float fr;
+      locate_direct(rq, p.ax.x[0], p.ax.inv[0], p.ax.x0[0], p.ax.inv_dx[0], ii, fr);
+      sFov[e * NT + tid] = make_float4(vx, vy, fr, __int_as_float(ii * 1024));
+    }
+  }
 
   Ring<FL> ring;
 #pragma unroll
@@ -636,33 +679,24 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
             const float2 xi = *reinterpret_cast<const float2*>(sTab + cj[e]);
             fj[e] = (yq - xi.x) * xi.y;
           } else {
-            const int x = qx + (e & 1), y = qy + (e >> 1);
-            int jj, ii, kk;
-            float fy, fr, fe;
+            const float4 fc = sFov[e * NT + tid];
+            int jj, kk;
+            float fy, fe;
             locate_direct(yq, p.ax.x[1], p.ax.inv[1], p.ax.x0[1], p.ax.inv_dx[1], jj, fy);
-            float vx, vy, rq;
-            if (p.vmap != nullptr) {  // maps computed by a fvvdp_display_geometry subclass
-              const long long po = (long long)min(y, h - 1) * w + min(x, w - 1);
-              vx = __ldg(p.vmap + po); vy = __ldg(p.vmap + (long long)h * w + po); rq = __ldg(p.rqmap + po);
-            } else {
-              vx = __ldg(p.vx + min(x, w - 1)); vy = __ldg(p.vy + min(y, h - 1));
-              const float va = fminf(sqrtf(vx * vx + vy * vy), 89.9f) * 0.017453292519943295f;
-              const float res_mag = p.res_k0 / (__cosf(va) * __cosf(va + p.res_delta_rad));
-              rq = fast_log2(fminf(fmaxf(p.rho_band * res_mag, p.ax.lo[0]), p.ax.hi[0]));
-            }
-            const float ex = vx - p.gaze[fi][0], ey = vy - p.gaze[fi][1];
-            const float ecc = sqrtf(ex * ex + ey * ey);
-            const float eq = sqrtf(fminf(fmaxf(ecc, p.ax.lo[2]), p.ax.hi[2]));
-            locate_direct(rq, p.ax.x[0], p.ax.inv[0], p.ax.x0[0], p.ax.inv_dx[0], ii, fr);
+            const float ex = fc.x - p.gaze[fi][0], ey = fc.y - p.gaze[fi][1];
+            const float ecc = fast_sqrt(fmaf(ex, ex, ey * ey));  // eccentricity [deg] (fvvdp.py:432)
+            const float eq = fast_sqrt(fminf(fmaxf(ecc, p.ax.lo[2]), p.ax.hi[2]));
             locate_direct(eq, p.ax.x[2], p.ax.inv[2], p.ax.x0[2], p.ax.inv_dx[2], kk, fe);
+            // trilinear look-up of both temporal channels: 4 (rho, ecc) corners, each record holds the Y entry and its step
+            const float4* v = p.lut4 + __float_as_int(fc.w) + kk * 32 + jj;
+            const float4 c00 = __ldg(v), c01 = __ldg(v + 32), c10 = __ldg(v + 1024), c11 = __ldg(v + 1056);
+            const float fr = fc.z;
 #pragma unroll
             for (int c2 = 0; c2 < TC; ++c2) {
-              const float* v = p.lut3d + c2 * 32768 + (jj * 32 + ii) * 32 + kk;
-              const float a00 = __ldg(v), a01 = __ldg(v + 32), a10 = __ldg(v + 1024), a11 = __ldg(v + 1056);
-              const float b00 = __ldg(v + 1), b01 = __ldg(v + 33), b10 = __ldg(v + 1025), b11 = __ldg(v + 1057);
-              const float lo = (a00 * (1.0f - fr) + a01 * fr) * (1.0f - fy) + (a10 * (1.0f - fr) + a11 * fr) * fy;
-              const float hi = (b00 * (1.0f - fr) + b01 * fr) * (1.0f - fy) + (b10 * (1.0f - fr) + b11 * fr) * fy;
-              lsf[c2][e] = lo * (1.0f - fe) + hi * fe + p.log2_sens_mul;
+              const float t00 = c2 ? fmaf(fy, c00.w, c00.z) : fmaf(fy, c00.y, c00.x), t01 = c2 ? fmaf(fy, c01.w, c01.z) : fmaf(fy, c01.y, c01.x);
+              const float t10 = c2 ? fmaf(fy, c10.w, c10.z) : fmaf(fy, c10.y, c10.x), t11 = c2 ? fmaf(fy, c11.w, c11.z) : fmaf(fy, c11.y, c11.x);
+              const float lo = fmaf(fr, t10 - t00, t00), hi = fmaf(fr, t11 - t01, t01);  // along rho at ecc cell kk, kk + 1
+              lsf[c2][e] = fmaf(fe, hi - lo, lo);
             }
           }
         }
@@ -736,9 +770,9 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
   if (LEVEL0 && eotf_checks_range(p.eotf) && (vmin < 0.0f || vmax > 1.0f) && p.flags) atomicOr(p.flags, 1u);
 }
 
-template <int KIND, int FL, int TC>
+template <int KIND, int FL, int TC, bool FOV>
 constexpr size_t band_smem_bytes() {
-  return sizeof(float) * (size_t)((KIND == IN_PYRAMID_TMA ? 2 : 1) * TILE_FLOATS + ((KIND == IN_LEVEL0_TMA || KIND == IN_LEVEL0_CPASYNC) ? 2 * TILE_FLOATS : 0) +
+  return (FOV ? sizeof(float4) * 4 * NT : 0) + sizeof(float) * (size_t)((KIND == IN_PYRAMID_TMA ? 2 : 1) * TILE_FLOATS + ((KIND == IN_LEVEL0_TMA || KIND == IN_LEVEL0_CPASYNC) ? 2 * TILE_FLOATS : 0) +
                                   2 * NH * LW + FL * 2 * NE + (FL == 1 ? 0 : 2 * TC * NE) + 256 + MAXCHUNK * 2 * (NT / 32));
 }
 

@@ -18,11 +18,12 @@ constexpr int kTC = FUSED_VIDEO ? 2 : 1;
 #define FUSED_FN(name) FUSED_CAT(name, FUSED_KIND, FUSED_VIDEO)
 
 cudaError_t FUSED_FN(launch_band_)(bool foveated, bool extra, const BandParams& p, dim3 grid, cudaStream_t st) {
-  const size_t smem = band_smem_bytes<FUSED_KIND, kFL, kTC>();
   if (foveated) {
+    const size_t smem = band_smem_bytes<FUSED_KIND, kFL, kTC, true>();
     if (extra) band_kernel<FUSED_KIND, kFL, kTC, true, true><<<grid, NT, smem, st>>>(p);
     else band_kernel<FUSED_KIND, kFL, kTC, true, false><<<grid, NT, smem, st>>>(p);
   } else {
+    const size_t smem = band_smem_bytes<FUSED_KIND, kFL, kTC, false>();
     if (extra) band_kernel<FUSED_KIND, kFL, kTC, false, true><<<grid, NT, smem, st>>>(p);
     else band_kernel<FUSED_KIND, kFL, kTC, false, false><<<grid, NT, smem, st>>>(p);
   }
@@ -30,11 +31,11 @@ cudaError_t FUSED_FN(launch_band_)(bool foveated, bool extra, const BandParams& 
 }
 
 cudaError_t FUSED_FN(configure_band_)() {
-  const int smem = (int)band_smem_bytes<FUSED_KIND, kFL, kTC>();
+  const int smem_fov = (int)band_smem_bytes<FUSED_KIND, kFL, kTC, true>(), smem = (int)band_smem_bytes<FUSED_KIND, kFL, kTC, false>();
   cudaError_t e;
-  e = cudaFuncSetAttribute(band_kernel<FUSED_KIND, kFL, kTC, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  e = cudaFuncSetAttribute(band_kernel<FUSED_KIND, kFL, kTC, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fov);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(band_kernel<FUSED_KIND, kFL, kTC, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  e = cudaFuncSetAttribute(band_kernel<FUSED_KIND, kFL, kTC, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fov);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(band_kernel<FUSED_KIND, kFL, kTC, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
