@@ -311,10 +311,20 @@ def run_ours(args, W, H):
 def main():
     args = parse()
     W, H = [int(v) for v in args.size.lower().split("x")]
-    if args.impl == "reference":
-        run_reference(args, W, H)
-    else:
-        run_ours(args, W, H)
+    # stdout carries exactly one JSON line: anything libraries print on file descriptor 1 while the benchmark runs
+    # (e.g. NCCL's version banner) is sent to stderr instead
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout, sys.stdout = sys.stdout, os.fdopen(out_fd, "w")
+    try:
+        if args.impl == "reference":
+            run_reference(args, W, H)
+        else:
+            run_ours(args, W, H)
+    finally:
+        sys.stdout.flush()
+        sys.stdout = real_stdout
 
 
 if __name__ == "__main__":

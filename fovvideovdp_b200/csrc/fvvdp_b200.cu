@@ -22,7 +22,7 @@ struct fvvdp_b200_ctx {
   int nch = 4, n_bands = 0, T = 1;
   int lh[FVVDP_B200_MAX_LEVELS], lw[FVVDP_B200_MAX_LEVELS];
   int tiles_x[FVVDP_B200_MAX_LEVELS], tiles_y[FVVDP_B200_MAX_LEVELS];
-  bool fused = false;                          // fused band kernels (filter_len <= 8) or the general v1 path
+  bool fused = false;                          // fused band kernels (filter_len <= 16) or the general v1 path
   float* P[FVVDP_B200_MAX_LEVELS] = {};        // fused: luminance pyramid, level >= 1: [slots][h_l][pitch_l], (test, ref) interleaved
   int pitch[FVVDP_B200_MAX_LEVELS] = {};
   float* cell = nullptr;                       // fused: [n_bands][32][8] CSF cells over log2 Y
@@ -176,7 +176,7 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
   int hh = cfg->height, ww = cfg->width;
   {
     const char* force = getenv("FVVDP_B200_PATH");
-    c->fused = cfg->filter_len <= fused::RING && !(force && strcmp(force, "v1") == 0);
+    c->fused = cfg->filter_len <= fused::MAXRING && !(force && strcmp(force, "v1") == 0);
   }
   const int tile_w = c->fused ? fused::TW : TW, tile_h = c->fused ? fused::TH : TH;
   for (int l = 0; l < cfg->n_levels; ++l) {
@@ -454,10 +454,11 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
     }
     const bool contig = cfg.in_dtype == FVVDP_B200_F32 && cfg.in_channels == 1 && strides[2] == 1 && aligned && W % 4 == 0 &&
                         strides[1] % 4 == 0 && strides[1] >= W && strides[1] * (int64_t)H < (1ll << 31);
-    const bool video = cfg.temp_ch == 2;
+    const int mode = cfg.temp_ch == 2 ? (fl > fused::RING ? 2 : 1) : 0;
+    const int ring_len = mode == 2 ? fused::MAXRING : fused::RING;
     for (int cc = 0; cc < cfg.temp_ch; ++cc)
-      for (int k = 0; k < fused::RING; ++k) {
-        const int kk = k - (fused::RING - fl);  // window position within the real filter, 0 = oldest
+      for (int k = 0; k < ring_len; ++k) {
+        const int kk = k - (ring_len - fl);  // window position within the real filter, 0 = oldest
         const float wv = kk >= 0 ? cfg.filt[cc][fl - 1 - kk] : 0.0f;  // corr_filter = F.flip(0), fvvdp.py:298
         uint32_t bits;
         memcpy(&bits, &wv, 4);
@@ -538,7 +539,7 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
       if (l >= 1) bp.tmap[0] = ctx->pmap[l];
       dim3 grid(ctx->tiles_x[l], ctx->tiles_y[l], nchunks);
       ProfScope prof(ctx, 1 + l, st);
-      cudaError_t le2 = fused::launch_band(kind, video, cfg.foveated != 0, extra, bp, grid, st);
+      cudaError_t le2 = fused::launch_band(kind, mode, cfg.foveated != 0, extra, bp, grid, st);
       if (le2 != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "band_kernel[%d] launch: %s", l, cudaGetErrorString(le2));
       ctx->launches++;
     }

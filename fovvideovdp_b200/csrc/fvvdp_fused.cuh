@@ -34,13 +34,17 @@ constexpr int TH = 16, TW = 64;                 // output tile of one CTA
 constexpr int LH = TH + 8, LW = TW + 8;         // staged luminance tile: origin (ty0-4, tx0-4)
 constexpr int NH = TH / 2 + 2, NW = TW / 2 + 2; // reduced tile with 1-px halo: origin (jy0-1, jx0-1)
 constexpr int NE = NH * NW;                     // 340
-constexpr int NT = 256;                         // threads: one 2x2 quad each
-constexpr int RING = 8;                         // temporal window kept on chip
+constexpr int RING = 8;                         // temporal window kept on chip by the 256-thread kernels (one 2x2 quad per thread)
+constexpr int MAXRING = 16;                     // ... and by the 512-thread kernels (two pixels per thread; 60 fps clips)
 constexpr int MAXCHUNK = 64;                    // output frames walked by one CTA
 constexpr int LV4 = LW / 4;                     // 4-pixel chunks per staged row
 constexpr int NPC = LH * LV4;                   // 4-pixel position chunks of a staged tile (432)
-constexpr int NLD = (NPC + NT - 1) / NT;        // position chunks per thread and frame (2; the second round is ragged)
-constexpr int NCOL = (NE + NT - 1) / NT;        // column-pass outputs ((test, ref) pairs) per thread (2)
+// threads per CTA / pixels per thread: up to 8 taps the thread owns a 2x2 quad (8 x 4 ring registers pairs), beyond that
+// one row of the quad (16 x 2), so that the register ring stays at 64 registers
+__host__ __device__ constexpr int threads_of(int FL) { return FL > RING ? 512 : 256; }
+__host__ __device__ constexpr int pixels_of(int FL) { return FL > RING ? 2 : 4; }
+__host__ __device__ constexpr int nld_of(int FL) { return (NPC + threads_of(FL) - 1) / threads_of(FL); }   // position chunks per thread and frame
+__host__ __device__ constexpr int ncol_of(int FL) { return (NE + threads_of(FL) - 1) / threads_of(FL); }   // column-pass outputs per thread
 constexpr int PLANE = LH * LW;                  // one stream of a landing buffer
 constexpr int TILE_FLOATS = 2 * PLANE;          // one staged tile, both streams
 constexpr int ROW_SEGS = 3;                     // row pass: the NH coarse rows are split 4 + 3 + 3 over three threads per column
@@ -63,8 +67,8 @@ struct BandParams {
   float* partial;                             // [n_frames][2][ntiles]
   // ---- geometry / schedule ----
   int h, w, h2, w2, h_odd, ntiles;
-  int n_frames, fl, chunk;                    // output frames; filter taps (<= RING); output frames per CTA
-  u64 wgt2[2][RING];                          // [temporal channel][ring window position, 0 = oldest]: (w, w) packed
+  int n_frames, fl, chunk;                    // output frames; filter taps (<= ring length of the kernel); output frames per CTA
+  u64 wgt2[2][MAXRING];                        // [temporal channel][ring window position, 0 = oldest]: (w, w) packed
   // ---- level-0 input format ----
   long long sC, sH, sW;
   int C, dtype, eotf;
@@ -307,23 +311,26 @@ __device__ __forceinline__ void locate_direct(float q, const float* __restrict__
 // ------------------------------------------------------------------------------------------------ temporal rings
 template <int FL>
 struct Ring {
-  u64 v[FL][4];  // [ring slot][pixel of the 2x2 quad] = (test, reference)
+  u64 v[FL][pixels_of(FL)];  // [ring slot][pixel of the 2x2 quad, or of its row] = (test, reference)
 };
 
 template <int FL, int J>
 __device__ __forceinline__ void ring_store(Ring<FL>& ring, const float* __restrict__ sLb, int coff) {
   const ulonglong2 r0 = *reinterpret_cast<const ulonglong2*>(sLb + coff);
-  const ulonglong2 r1 = *reinterpret_cast<const ulonglong2*>(sLb + coff + 2 * LW);
-  ring.v[J][0] = r0.x; ring.v[J][1] = r0.y; ring.v[J][2] = r1.x; ring.v[J][3] = r1.y;
+  ring.v[J][0] = r0.x; ring.v[J][1] = r0.y;
+  if (pixels_of(FL) == 4) {
+    const ulonglong2 r1 = *reinterpret_cast<const ulonglong2*>(sLb + coff + 2 * LW);
+    ring.v[J][2] = r1.x; ring.v[J][3] = r1.y;
+  }
 }
 
 // R[cc][e] = sum_k wgt[cc][k] * ring[(J+1+k) % FL][e]   (window position k = 0 is the oldest frame)
 template <int FL, int TC, int J>
-__device__ __forceinline__ void fir_quad(const Ring<FL>& ring, const BandParams& p, u64 (&R)[TC][4]) {
+__device__ __forceinline__ void fir_quad(const Ring<FL>& ring, const BandParams& p, u64 (&R)[TC][pixels_of(FL)]) {
 #pragma unroll
   for (int cc = 0; cc < TC; ++cc)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < pixels_of(FL); ++e) {
       if (FL == 1) {
         R[cc][e] = ring.v[0][e];
       } else {
@@ -339,6 +346,7 @@ __device__ __forceinline__ void fir_quad(const Ring<FL>& ring, const BandParams&
 // needed between the column pass and this): sNc[cc][o] = sum_k wgt[cc][k] sNr[(J+1+k) % FL][o]
 template <int FL, int TC, int J>
 __device__ __forceinline__ void fir_coarse(const float* __restrict__ sNr, float* __restrict__ sNc, const BandParams& p, int tid) {
+  constexpr int NT = threads_of(FL), NCOL = ncol_of(FL);
 #pragma unroll
   for (int i = 0; i < NCOL; ++i) {
     const int o = tid + i * NT;
@@ -358,7 +366,8 @@ __device__ __forceinline__ void fir_coarse(const float* __restrict__ sNr, float*
 
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int KIND, int FL, int TC, bool FOV, bool EXTRA>
-__global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ BandParams p) {
+__global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel(const __grid_constant__ BandParams p) {
+  constexpr int NT = threads_of(FL), PXT = pixels_of(FL), NLD = nld_of(FL), NCOL = ncol_of(FL);
   constexpr bool LEVEL0 = KIND != IN_PYRAMID_TMA;
   constexpr bool TMA = KIND == IN_PYRAMID_TMA || KIND == IN_LEVEL0_TMA;
   constexpr bool LANDING = KIND == IN_LEVEL0_TMA || KIND == IN_LEVEL0_CPASYNC;  // raw planes land first, the EOTF pass interleaves them
@@ -372,7 +381,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
   float* sNc = (FL == 1) ? sNr : sNr + FL * 2 * NE;  // [TC][NE][2]   temporally filtered reduced tiles
   float* sTab = sNr + FL * 2 * NE + (FL == 1 ? 0 : NCH * NE);  // [32][8]
   float* sRed = sTab + 256;                          // [MAXCHUNK][2][NT/32]
-  float4* sFov = reinterpret_cast<float4*>(sRed + MAXCHUNK * 2 * (NT / 32));  // FOV: [4 quad pixels][NT] (view x, view y, rho fraction, rho cell)
+  float4* sFov = reinterpret_cast<float4*>(sRed + MAXCHUNK * 2 * (NT / 32));  // FOV: [PXT pixels][NT] (view x, view y, rho fraction, rho cell)
   __shared__ __align__(8) u64 bars[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -434,21 +443,23 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
   // row pass: column and first coarse row of this thread (tid < ROW_THREADS)
   const int rw_c = tid % LW, rw_seg = tid / LW;
   const int rw_a0 = rw_seg == 0 ? 0 : (rw_seg == 1 ? 4 : 7), rw_n = rw_seg == 0 ? 4 : 3;
-  // the quad of this thread
-  const int qa = tid >> 5, qb = lane;
-  const int qy = ty0 + 2 * qa, qx = tx0 + 2 * qb;
-  const int coff = 2 * ((4 + 2 * qa) * LW + 4 + 2 * qb);   // quad's top-left pixel in the luminance tile (floats)
+  // the quad of this thread (PXT == 4), or the row `half` of the quad (PXT == 2; warp-uniform)
+  const int qa = (tid >> 5) & 7, qb = lane, half = PXT == 2 ? (tid >> 8) : 0;
+  const int qy = ty0 + 2 * qa + half, qx = tx0 + 2 * qb;  // first pixel of the thread
+#define FVVDP_EY(e) (PXT == 4 ? ((e) >> 1) : 0)
+#define FVVDP_EX(e) ((e) & 1)
+  const int coff = 2 * ((4 + 2 * qa + half) * LW + 4 + 2 * qb);   // first pixel in the luminance tile (floats)
   const int noff = 2 * (qa * NW + qb);                     // top-left of its 3x3 coarse neighbourhood
-  bool valid[4];
+  bool valid[PXT];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) valid[e] = (qy + (e >> 1) < h) && (qx + (e & 1) < w);
+  for (int e = 0; e < PXT; ++e) valid[e] = (qy + FVVDP_EY(e) < h) && (qx + FVVDP_EX(e) < w);
 
   if (FOV) {
     // per-pixel constants of the time walk: view direction and the rho cell / fraction of the CSF look-up
     // (rho = rho_band * resolution magnification, fvvdp.py:436-438)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int x = min(qx + (e & 1), w - 1), y = min(qy + (e >> 1), h - 1);
+    for (int e = 0; e < PXT; ++e) {
+      const int x = min(qx + FVVDP_EX(e), w - 1), y = min(qy + FVVDP_EY(e), h - 1);
       float vx, vy, rq;
       if (p.vmap != nullptr) {  // maps computed by a fvvdp_display_geometry subclass
         const long long po = (long long)y * w + x;
@@ -470,7 +481,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
 #pragma unroll
   for (int k = 0; k < FL; ++k)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) ring.v[k][e] = 0ull;
+    for (int e = 0; e < PXT; ++e) ring.v[k][e] = 0ull;
 
   const float K0 = 0.05f, K1 = 0.25f, K3 = 0.25f, K4 = 0.05f;
   const bool rows_interior = (jy0 - 1 >= 1) && (jy0 + TH / 2 <= h2 - 2);
@@ -508,11 +519,9 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
   // level 0: landing buffer -> display EOTF -> luminance tile
   auto convert = [&](int buf) {
     const unsigned raw = sRaw_u32 + buf * (TILE_FLOATS * 4) + 16 * tid, lum = sL_u32 + 32 * tid;
-#define FVVDP_EOTF_PASS(K)                                                                                          \
-  {                                                                                                                 \
-    eotf_chunk<K>(raw, lum, halo_inside || ld_goff[0] >= 0, p, vmin, vmax);                                         \
-    if (tid < NPC - NT) eotf_chunk<K>(raw + NT * 16, lum + NT * 32, halo_inside || ld_goff[1] >= 0, p, vmin, vmax); \
-  }
+#define FVVDP_EOTF_PASS(K)                                                                                                      \
+  _Pragma("unroll") for (int i = 0; i < NLD; ++i)                                                                               \
+    if (tid + i * NT < NPC) eotf_chunk<K>(raw + i * (NT * 16), lum + i * (NT * 32), halo_inside || ld_goff[i] >= 0, p, vmin, vmax);
     switch (p.eotf) {  // uniform; one specialised conversion loop per EOTF
       case FVVDP_B200_EOTF_NONE: FVVDP_EOTF_PASS(FVVDP_B200_EOTF_NONE) break;
       case FVVDP_B200_EOTF_SRGB: FVVDP_EOTF_PASS(FVVDP_B200_EOTF_SRGB) break;
@@ -524,7 +533,6 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
 #undef FVVDP_EOTF_PASS
   };
 
-  static_assert(NLD == 2, "EOTF pass: chunk tid and, for tid < NPC - NT, chunk tid + NT");
   if (TMA) __syncthreads();  // barrier initialisation visible before the first wait
   issue_load(s_lo, 0);
   if (LANDING && s_lo + 1 < s_hi) issue_load(s_lo + 1, 1);
@@ -623,7 +631,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
     const int fi = s - (p.fl - 1);  // output frame
     // ---- temporal filter of the thread's own coarse elements; its pixels into the register ring and their filter.
     //      The ring position is a compile-time constant inside each case: no address arithmetic, no register moves.
-    u64 R[TC][4];
+    u64 R[TC][PXT];
     switch (s % FL) {
 #define FVVDP_CASE(J)                                             \
   case J:                                                         \
@@ -632,6 +640,9 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
     if (emit) fir_quad<FL, TC, (J) % FL>(ring, p, R);             \
     break;
       FVVDP_CASE(0) FVVDP_CASE(1) FVVDP_CASE(2) FVVDP_CASE(3) FVVDP_CASE(4) FVVDP_CASE(5) FVVDP_CASE(6) FVVDP_CASE(7)
+#if FUSED_MAXRING_CASES
+      FVVDP_CASE(8) FVVDP_CASE(9) FVVDP_CASE(10) FVVDP_CASE(11) FVVDP_CASE(12) FVVDP_CASE(13) FVVDP_CASE(14) FVVDP_CASE(15)
+#endif
 #undef FVVDP_CASE
     }
     if (NLUM == 1 || emit) __syncthreads();  // (3) filtered coarse tiles visible; the single luminance tile may be rewritten
@@ -639,10 +650,12 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
 
     // ---- expand the filtered coarse tile, contrast, CSF, masking, pooling: one 2x2 quad per thread ----
     float acc[2] = {0.0f, 0.0f};
-    float Lb[4], lgL[4], fj[4];
-    int cj[4];
-    float lsf[TC][4];  // FOV: log2 S per temporal channel
-    float Dsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    float Lb[PXT], lgL[PXT], fj[PXT];
+    int cj[PXT];
+    float lsf[TC][PXT];  // FOV: log2 S per temporal channel
+    float Dsum[PXT];
+#pragma unroll
+    for (int e = 0; e < PXT; ++e) Dsum[e] = 0.0f;
     const u64 c01 = pk(0.1f, 0.1f), c08 = pk(0.8f, 0.8f), c05 = pk(0.5f, 0.5f), cm1 = pk(-1.0f, -1.0f);
 #pragma unroll
     for (int cc = 0; cc < TC; ++cc) {
@@ -653,24 +666,30 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
       for (int c = 0; c < 3; ++c) {
         const u64 n0 = *reinterpret_cast<const u64*>(n + 2 * c), n1 = *reinterpret_cast<const u64*>(n + 2 * (NW + c)),
                   n2 = *reinterpret_cast<const u64*>(n + 2 * (2 * NW + c));
-        ve[c] = ffma2(c08, n1, fmul2(c01, fadd2(n0, n2)));  // even row: taps 2K[0], 2K[2], 2K[4]
-        vo[c] = fmul2(c05, fadd2(n1, n2));                  // odd row:  taps 2K[1], 2K[3]
+        if (PXT == 4 || half == 0) ve[c] = ffma2(c08, n1, fmul2(c01, fadd2(n0, n2)));  // even row: taps 2K[0], 2K[2], 2K[4]
+        if (PXT == 4 || half == 1) vo[c] = fmul2(c05, fadd2(n1, n2));                  // odd row:  taps 2K[1], 2K[3]
       }
-      u64 E[4];
-      E[0] = ffma2(c08, ve[1], fmul2(c01, fadd2(ve[0], ve[2])));
-      E[1] = fmul2(c05, fadd2(ve[1], ve[2]));
-      E[2] = ffma2(c08, vo[1], fmul2(c01, fadd2(vo[0], vo[2])));
-      E[3] = fmul2(c05, fadd2(vo[1], vo[2]));
-      float B[2][4];  // band (G_l - E) of the test / reference channel
+      u64 E[PXT];
+      if (PXT == 4) {
+        E[0] = ffma2(c08, ve[1], fmul2(c01, fadd2(ve[0], ve[2])));
+        E[1] = fmul2(c05, fadd2(ve[1], ve[2]));
+        E[PXT - 2] = ffma2(c08, vo[1], fmul2(c01, fadd2(vo[0], vo[2])));
+        E[PXT - 1] = fmul2(c05, fadd2(vo[1], vo[2]));
+      } else {
+        if (half) { ve[0] = vo[0]; ve[1] = vo[1]; ve[2] = vo[2]; }
+        E[0] = ffma2(c08, ve[1], fmul2(c01, fadd2(ve[0], ve[2])));
+        E[1] = fmul2(c05, fadd2(ve[1], ve[2]));
+      }
+      float B[2][PXT];  // band (G_l - E) of the test / reference channel
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < PXT; ++e) {
         const u64 b = ffma2(E[e], cm1, R[cc][e]);  // R - E, rounded once like the scalar subtraction
         B[0][e] = lo_of(b);
         B[1][e] = hi_of(b);
       }
       if (cc == 0) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < PXT; ++e) {
           Lb[e] = fmaxf(hi_of(E[e]), 0.1f);  // L_bkg = expanded sustained reference (:264-266)
           lgL[e] = fast_log2(Lb[e]);
           const float yq = fminf(lgL[e], p.lg_y_hi);
@@ -702,7 +721,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
         }
       }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < PXT; ++e) {
         float lS;  // log2 of (sensitivity x sensitivity_correction)
         if (!FOV) {
           const float2 td = *reinterpret_cast<const float2*>(sTab + cj[e] + 2 + 2 * cc);
@@ -721,7 +740,7 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
         acc[cc] += fast_exp2(p.beta * lD);
         if (EXTRA && valid[e]) {
           const long long plane = (long long)h * w;
-          const long long pofs = (long long)(qy + (e >> 1)) * w + qx + (e & 1);
+          const long long pofs = (long long)(qy + FVVDP_EY(e)) * w + qx + FVVDP_EX(e);
           const float invL = 1.0f / Lb[e];
           if (p.tapC) {
             p.tapC[((long long)fi * NCH + cc * 2 + 0) * plane + pofs] = bT * invL * p.band_mul;
@@ -768,11 +787,14 @@ __global__ void __launch_bounds__(NT, 2) band_kernel(const __grid_constant__ Ban
     p.partial[((long long)fi * 2 + cc) * p.ntiles + tile] = v;
   }
   if (LEVEL0 && eotf_checks_range(p.eotf) && (vmin < 0.0f || vmax > 1.0f) && p.flags) atomicOr(p.flags, 1u);
+#undef FVVDP_EY
+#undef FVVDP_EX
 }
 
 template <int KIND, int FL, int TC, bool FOV>
 constexpr size_t band_smem_bytes() {
-  return (FOV ? sizeof(float4) * 4 * NT : 0) + sizeof(float) * (size_t)((KIND == IN_PYRAMID_TMA ? 2 : 1) * TILE_FLOATS + ((KIND == IN_LEVEL0_TMA || KIND == IN_LEVEL0_CPASYNC) ? 2 * TILE_FLOATS : 0) +
+  constexpr int NT = threads_of(FL);
+  return (FOV ? sizeof(float4) * pixels_of(FL) * NT : 0) + sizeof(float) * (size_t)((KIND == IN_PYRAMID_TMA ? 2 : 1) * TILE_FLOATS + ((KIND == IN_LEVEL0_TMA || KIND == IN_LEVEL0_CPASYNC) ? 2 * TILE_FLOATS : 0) +
                                   2 * NH * LW + FL * 2 * NE + (FL == 1 ? 0 : 2 * TC * NE) + 256 + MAXCHUNK * 2 * (NT / 32));
 }
 

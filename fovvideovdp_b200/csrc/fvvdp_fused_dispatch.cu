@@ -1,4 +1,4 @@
-// Dispatch over the eight fused-kernel translation units.
+// Dispatch over the twelve fused-kernel translation units.
 #include "fvvdp_fused_launch.h"
 
 namespace fvvdp {
@@ -7,33 +7,26 @@ namespace fused {
 #define DECL(k, v)                                                                                          \
   cudaError_t launch_band_##k##_##v(bool foveated, bool extra, const BandParams& p, dim3 grid, cudaStream_t st); \
   cudaError_t configure_band_##k##_##v();
-DECL(0, 0) DECL(0, 1) DECL(1, 0) DECL(1, 1) DECL(2, 0) DECL(2, 1) DECL(3, 0) DECL(3, 1)
+#define DECL3(k) DECL(k, 0) DECL(k, 1) DECL(k, 2)
+DECL3(0) DECL3(1) DECL3(2) DECL3(3)
+#undef DECL3
 #undef DECL
 
-cudaError_t launch_band(int kind, bool video, bool foveated, bool extra, const BandParams& p, dim3 grid, cudaStream_t st) {
-  switch (kind * 2 + (video ? 1 : 0)) {
-    case 0: return launch_band_0_0(foveated, extra, p, grid, st);
-    case 1: return launch_band_0_1(foveated, extra, p, grid, st);
-    case 2: return launch_band_1_0(foveated, extra, p, grid, st);
-    case 3: return launch_band_1_1(foveated, extra, p, grid, st);
-    case 4: return launch_band_2_0(foveated, extra, p, grid, st);
-    case 5: return launch_band_2_1(foveated, extra, p, grid, st);
-    case 6: return launch_band_3_0(foveated, extra, p, grid, st);
-    case 7: return launch_band_3_1(foveated, extra, p, grid, st);
+cudaError_t launch_band(int kind, int mode, bool foveated, bool extra, const BandParams& p, dim3 grid, cudaStream_t st) {
+  switch (kind * 3 + mode) {
+#define CASE(k, v) case (k) * 3 + (v): return launch_band_##k##_##v(foveated, extra, p, grid, st);
+    CASE(0, 0) CASE(0, 1) CASE(0, 2) CASE(1, 0) CASE(1, 1) CASE(1, 2) CASE(2, 0) CASE(2, 1) CASE(2, 2) CASE(3, 0) CASE(3, 1) CASE(3, 2)
+#undef CASE
   }
   return cudaErrorInvalidValue;
 }
 
 cudaError_t configure_band_kernels() {
   cudaError_t e;
-  if ((e = configure_band_0_0()) != cudaSuccess) return e;
-  if ((e = configure_band_0_1()) != cudaSuccess) return e;
-  if ((e = configure_band_1_0()) != cudaSuccess) return e;
-  if ((e = configure_band_1_1()) != cudaSuccess) return e;
-  if ((e = configure_band_2_0()) != cudaSuccess) return e;
-  if ((e = configure_band_2_1()) != cudaSuccess) return e;
-  if ((e = configure_band_3_0()) != cudaSuccess) return e;
-  return configure_band_3_1();
+#define CONF(k, v) if ((e = configure_band_##k##_##v()) != cudaSuccess) return e;
+  CONF(0, 0) CONF(0, 1) CONF(0, 2) CONF(1, 0) CONF(1, 1) CONF(1, 2) CONF(2, 0) CONF(2, 1) CONF(2, 2) CONF(3, 0) CONF(3, 1) CONF(3, 2)
+#undef CONF
+  return cudaSuccess;
 }
 
 }  // namespace fused

@@ -1,16 +1,17 @@
 // Instantiations of the fused band kernel.  Compiled once per (input kind, temporal mode) with
-// -DFUSED_KIND={0,1,2,3} (fused::InputKind) -DFUSED_VIDEO={0,1} so that the eight translation units build in parallel.
+// -DFUSED_KIND={0,1,2,3} (fused::InputKind) -DFUSED_VIDEO={0: image, 1: video with up to 8 taps, 2: video with up to 16 taps}
+// so that the twelve translation units build in parallel.
+#ifndef FUSED_KIND
+#error "compile with -DFUSED_KIND and -DFUSED_VIDEO"
+#endif
+#define FUSED_MAXRING_CASES (FUSED_VIDEO == 2)
 #include "fvvdp_fused.cuh"
 #include "fvvdp_fused_launch.h"
 
 namespace fvvdp {
 namespace fused {
 
-#ifndef FUSED_KIND
-#error "compile with -DFUSED_KIND and -DFUSED_VIDEO"
-#endif
-
-constexpr int kFL = FUSED_VIDEO ? RING : 1;
+constexpr int kFL = FUSED_VIDEO == 2 ? MAXRING : (FUSED_VIDEO ? RING : 1);
 constexpr int kTC = FUSED_VIDEO ? 2 : 1;
 
 #define FUSED_CAT2(a, b, c) a##b##_##c
@@ -20,12 +21,12 @@ constexpr int kTC = FUSED_VIDEO ? 2 : 1;
 cudaError_t FUSED_FN(launch_band_)(bool foveated, bool extra, const BandParams& p, dim3 grid, cudaStream_t st) {
   if (foveated) {
     const size_t smem = band_smem_bytes<FUSED_KIND, kFL, kTC, true>();
-    if (extra) band_kernel<FUSED_KIND, kFL, kTC, true, true><<<grid, NT, smem, st>>>(p);
-    else band_kernel<FUSED_KIND, kFL, kTC, true, false><<<grid, NT, smem, st>>>(p);
+    if (extra) band_kernel<FUSED_KIND, kFL, kTC, true, true><<<grid, threads_of(kFL), smem, st>>>(p);
+    else band_kernel<FUSED_KIND, kFL, kTC, true, false><<<grid, threads_of(kFL), smem, st>>>(p);
   } else {
     const size_t smem = band_smem_bytes<FUSED_KIND, kFL, kTC, false>();
-    if (extra) band_kernel<FUSED_KIND, kFL, kTC, false, true><<<grid, NT, smem, st>>>(p);
-    else band_kernel<FUSED_KIND, kFL, kTC, false, false><<<grid, NT, smem, st>>>(p);
+    if (extra) band_kernel<FUSED_KIND, kFL, kTC, false, true><<<grid, threads_of(kFL), smem, st>>>(p);
+    else band_kernel<FUSED_KIND, kFL, kTC, false, false><<<grid, threads_of(kFL), smem, st>>>(p);
   }
   return cudaGetLastError();
 }

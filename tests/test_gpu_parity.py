@@ -99,6 +99,16 @@ def test_short_clip_padding(fv_mod, golden, fps, pad):
     check_q(st["Q_per_ch"], g["Q_per_ch"])
 
 
+@pytest.mark.parametrize("fps", [50, 120])
+def test_high_frame_rates_vs_oracle(fv_mod, oracle, fps):
+    """50 fps: 13 taps -> the 16-frame on-chip ring (512-thread kernels); 120 fps: 30 taps -> the general kernels."""
+    t, r = synth_pair_numpy(9, 135, 240)
+    jod, st = fv_mod.fvvdp(display_name="standard_fhd").predict(t, r, frames_per_second=fps)
+    want, wst = oracle.predict(t, r, frames_per_second=fps, display_name="standard_fhd")
+    check_jod(jod, want)
+    check_q(st["Q_per_ch"], wst["Q_per_ch"])
+
+
 def test_image_with_taps(fv_mod, golden):
     g = golden("image_fhd")
     t, r = synth_pair_numpy(1, 270, 480)
