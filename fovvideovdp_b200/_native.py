@@ -19,7 +19,8 @@ TAP_R, TAP_GAUSS, TAP_CONTRAST, TAP_LBKG, TAP_S, TAP_D, TAP_DMAP_BAND = range(7)
 EXPORTS = ["fvvdp_b200_create", "fvvdp_b200_score_block", "fvvdp_b200_heatmap", "fvvdp_b200_read_tap",
            "fvvdp_b200_level_size", "fvvdp_b200_launch_count", "fvvdp_b200_traffic_model", "fvvdp_b200_destroy",
            "fvvdp_b200_last_error", "fvvdp_b200_abi_version", "fvvdp_b200_pool_jod",
-           "fvvdp_b200_profile", "fvvdp_b200_profile_read", "fvvdp_b200_heatmap_visualize", "fvvdp_b200_set_foveation_maps"]
+           "fvvdp_b200_profile", "fvvdp_b200_profile_read", "fvvdp_b200_heatmap_visualize", "fvvdp_b200_set_foveation_maps",
+           "fvvdp_b200_yuv_to_luminance"]
 COLORMAPS = {"threshold": 0, "supra-threshold": 1}
 PROFILE_CLASSES = MAX_LEVELS + 2
 
@@ -50,6 +51,13 @@ class Config(C.Structure):
         ("want_taps", C.c_int32),
         ("max_block_frames", C.c_int32),
     ]
+
+
+class YuvDesc(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bit_depth", C.c_int32), ("chroma_420", C.c_int32),
+                ("ycbcr2rgb", C.c_float * 9), ("eotf", C.c_int32),
+                ("Y_peak", C.c_float), ("Y_black", C.c_float), ("gamma", C.c_float), ("L_min", C.c_float), ("L_max", C.c_float),
+                ("rgb2y", C.c_float * 3)]
 
 
 class PoolParams(C.Structure):
@@ -86,6 +94,8 @@ def load_library():
     lib.fvvdp_b200_heatmap_visualize.restype = C.c_int
     lib.fvvdp_b200_set_foveation_maps.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.fvvdp_b200_set_foveation_maps.restype = C.c_int
+    lib.fvvdp_b200_yuv_to_luminance.argtypes = [C.POINTER(YuvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.fvvdp_b200_yuv_to_luminance.restype = C.c_int
     lib.fvvdp_b200_read_tap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
     lib.fvvdp_b200_read_tap.restype = C.c_int64
     lib.fvvdp_b200_level_size.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
@@ -194,6 +204,16 @@ class Context:
         out = (C.c_double * 2)()
         self._check(self._lib.fvvdp_b200_traffic_model(self.handle, out), "fvvdp_b200_traffic_model")
         return float(out[0]), float(out[1])
+
+
+def yuv_to_luminance(desc: YuvDesc, y_ptr, u_ptr, v_ptr, lum_ptr, rgb_ptr, device_index, stream):
+    """One planar Y'CbCr frame (device planes) -> luminance (H,W) and / or display-encoded RGB (H,W,3)."""
+    lib = load_library()
+    rc = lib.fvvdp_b200_yuv_to_luminance(C.byref(desc), C.c_void_p(y_ptr), C.c_void_p(u_ptr), C.c_void_p(v_ptr),
+                                         C.c_void_p(lum_ptr) if lum_ptr else None, C.c_void_p(rgb_ptr) if rgb_ptr else None,
+                                         int(device_index), C.c_void_p(stream))
+    if rc != 0:
+        raise RuntimeError(f"fvvdp_b200_yuv_to_luminance failed ({rc}): {last_error(None)}")
 
 
 def pool_jod(q_ptr, n_bands, n_frames, q_stride, params: PoolParams, device_index, out_ptr, stream):

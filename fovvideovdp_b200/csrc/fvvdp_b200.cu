@@ -763,6 +763,37 @@ extern "C" int fvvdp_b200_heatmap_visualize(fvvdp_b200_ctx* ctx, int frame, floa
   return FVVDP_B200_OK;
 }
 
+extern "C" int fvvdp_b200_yuv_to_luminance(const fvvdp_b200_yuv_desc* d, const void* y_plane, const void* u_plane, const void* v_plane,
+                                           float* lum_out, float* rgb_out, int cuda_device, void* cuda_stream) {
+  fvvdp_b200_ctx* ctx = nullptr;  // ctx-free: errors are reported through fvvdp_b200_last_error(NULL)
+  if (!d || !y_plane || !u_plane || !v_plane || (!lum_out && !rgb_out)) return fail(ctx, FVVDP_B200_ERR_INVALID, "null argument");
+  if (d->width < 1 || d->height < 1) return fail(ctx, FVVDP_B200_ERR_INVALID, "bad frame size %dx%d", d->width, d->height);
+  if (d->bit_depth < 8 || d->bit_depth > 16) return fail(ctx, FVVDP_B200_ERR_INVALID, "bit depth %d not in 8..16", d->bit_depth);
+  if (d->chroma_420 && ((d->width | d->height) & 1)) return fail(ctx, FVVDP_B200_ERR_INVALID, "4:2:0 frames need an even width and height");
+  if (d->eotf < 0 || d->eotf > 5) return fail(ctx, FVVDP_B200_ERR_INVALID, "Unknown EOTF %d", d->eotf);
+  CU(cudaSetDevice(cuda_device));
+  YuvParams p;
+  memset(&p, 0, sizeof(p));
+  p.y = y_plane; p.u = u_plane; p.v = v_plane;
+  p.W = d->width; p.H = d->height;
+  p.is420 = d->chroma_420 ? 1 : 0;
+  p.cw = p.is420 ? d->width / 2 : d->width; p.ch = p.is420 ? d->height / 2 : d->height;
+  p.is16 = d->bit_depth > 8;
+  const float scale = (float)(1 << (d->bit_depth - 8));
+  p.wy = 1.0f / (scale * 219.0f); p.oy = 16.0f / 219.0f;    // fixed2float, video_source_yuv.py:198-212
+  p.wc = 1.0f / (scale * 224.0f); p.oc = 128.0f / 224.0f;
+  for (int i = 0; i < 9; ++i) p.m[i] = d->ycbcr2rgb[i];
+  p.eotf = d->eotf;
+  p.Yscale = d->Y_peak - d->Y_black; p.Y_black = d->Y_black; p.Y_peak = d->Y_peak; p.gamma = d->gamma; p.L_min = d->L_min; p.L_max = d->L_max;
+  for (int i = 0; i < 3; ++i) p.rgb2y[i] = d->rgb2y[i];
+  p.lum = lum_out; p.rgb = rgb_out;
+  dim3 grid((d->width + 31) / 32, (d->height + 7) / 8);
+  yuv_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(p);
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "yuv_kernel launch: %s", cudaGetErrorString(le));
+  return FVVDP_B200_OK;
+}
+
 extern "C" int fvvdp_b200_pool_jod(const float* q, int n_bands, int64_t n_frames, int64_t q_stride, const fvvdp_b200_pool_params* params,
                                    int cuda_device, float* jod_out, void* cuda_stream) {
   fvvdp_b200_ctx* ctx = nullptr;  // ctx-free: errors are reported through fvvdp_b200_last_error(NULL)

@@ -639,4 +639,74 @@ __global__ void __launch_bounds__(256) vis_apply_kernel(const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K_yuv: planar Y'CbCr frame (8 / 10..16 bit, 4:2:0 or 4:4:4, limited range) -> display-encoded RGB -> luminance
+// (video_source_yuv.py:157-228, video_source_file.py:219-276: fixed2float, bilinear chroma upsampling = torch
+// interpolate(scale_factor=2, mode='bilinear'), ycbcr2rgb matrix, clip; then the display model and RGB2Y of
+// fvvdp_video_source_dm, video_source_yuv.py:299-302)
+// ------------------------------------------------------------------------------------------------
+struct YuvParams {
+  const void* y;
+  const void* u;
+  const void* v;
+  int W, H, cw, ch, is16, is420;
+  float wy, oy, wc, oc;   // fixed2float: Y' = clip(wy * Y - oy, 0, 1), C = clip(wc * c - oc, -0.5, 0.5)
+  float m[9];             // ycbcr2rgb, row-major
+  int eotf;
+  float Yscale, Y_black, Y_peak, gamma, L_min, L_max;
+  float rgb2y[3];
+  float* lum;             // [H][W] or nullptr
+  float* rgb;             // [H][W][3] display-encoded, clipped to [0,1], or nullptr
+};
+
+__device__ __forceinline__ float yuv_sample(const void* p, long long i, int is16) {
+  return is16 ? (float)__ldg(reinterpret_cast<const unsigned short*>(p) + i) : (float)__ldg(reinterpret_cast<const unsigned char*>(p) + i);
+}
+__device__ __forceinline__ float yuv_chroma(const YuvParams& p, const void* plane, int cy, int cx) {
+  return fminf(fmaxf(p.wc * yuv_sample(plane, (long long)cy * p.cw + cx, p.is16) - p.oc, -0.5f), 0.5f);
+}
+__device__ __forceinline__ float eotf_dyn(float v, int kind, const YuvParams& p) {
+  switch (kind) {
+    case FVVDP_B200_EOTF_NONE: return v;
+    case FVVDP_B200_EOTF_ABSOLUTE: return fminf(fmaxf(v, p.L_min), p.L_max);
+    case FVVDP_B200_EOTF_LINEAR: return fminf(fmaxf(v, 0.005f), p.Y_peak) + p.Y_black;
+    case FVVDP_B200_EOTF_SRGB: {
+      const float lin = (v > 0.04045f) ? fast_pow((v + 0.055f) / 1.055f, 2.4f) : v / 12.92f;
+      return fmaf(p.Yscale, lin, p.Y_black);
+    }
+    case FVVDP_B200_EOTF_GAMMA: return fmaf(p.Yscale, fast_pow(v, p.gamma), p.Y_black);
+    default: {  // PQ, fvvdp_display_model.py:100-112
+      const float t = fast_pow(v, 1.0f / 78.843750000000000f);
+      const float L = 10000.0f * fast_pow(fmaxf(t - 0.83593750000000000f, 0.0f) / (18.851562500000000f - 18.687500000000000f * t), 1.0f / 0.15930175781250000f);
+      return fminf(fmaxf(L, 0.005f), p.Y_peak) + p.Y_black;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) yuv_kernel(const YuvParams p) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= p.W || y >= p.H) return;
+  const long long i = (long long)y * p.W + x;
+  const float Y = fminf(fmaxf(p.wy * yuv_sample(p.y, i, p.is16) - p.oy, 0.0f), 1.0f);
+  float cb, cr;
+  if (p.is420) {
+    // bilinear, align_corners = False: source coordinate max((dst + 0.5) / 2 - 0.5, 0); neighbour clamped to the last sample
+    const float sy = fmaxf(0.5f * (float)y - 0.25f, 0.0f), sx = fmaxf(0.5f * (float)x - 0.25f, 0.0f);
+    const int y0 = (int)sy, x0 = (int)sx, y1 = min(y0 + 1, p.ch - 1), x1 = min(x0 + 1, p.cw - 1);
+    const float ly = sy - (float)y0, lx = sx - (float)x0;
+    cb = (1.0f - ly) * ((1.0f - lx) * yuv_chroma(p, p.u, y0, x0) + lx * yuv_chroma(p, p.u, y0, x1)) +
+         ly * ((1.0f - lx) * yuv_chroma(p, p.u, y1, x0) + lx * yuv_chroma(p, p.u, y1, x1));
+    cr = (1.0f - ly) * ((1.0f - lx) * yuv_chroma(p, p.v, y0, x0) + lx * yuv_chroma(p, p.v, y0, x1)) +
+         ly * ((1.0f - lx) * yuv_chroma(p, p.v, y1, x0) + lx * yuv_chroma(p, p.v, y1, x1));
+  } else {
+    cb = yuv_chroma(p, p.u, y, x);
+    cr = yuv_chroma(p, p.v, y, x);
+  }
+  float rgb[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) rgb[c] = fminf(fmaxf(p.m[3 * c] * Y + p.m[3 * c + 1] * cb + p.m[3 * c + 2] * cr, 0.0f), 1.0f);
+  if (p.rgb) { p.rgb[3 * i] = rgb[0]; p.rgb[3 * i + 1] = rgb[1]; p.rgb[3 * i + 2] = rgb[2]; }
+  if (p.lum) p.lum[i] = eotf_dyn(rgb[0], p.eotf, p) * p.rgb2y[0] + eotf_dyn(rgb[1], p.eotf, p) * p.rgb2y[1] + eotf_dyn(rgb[2], p.eotf, p) * p.rgb2y[2];
+}
+
 }  // namespace fvvdp

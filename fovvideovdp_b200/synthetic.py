@@ -40,3 +40,25 @@ def synth_pair_torch(n_frames, height, width, device, first_frame=0, chunk=8):
         ref[0, 0, f0:f1] = r.clamp(0.0, 1.0).float()
         test[0, 0, f0:f1] = t.clamp(0.0, 1.0).float()
     return test, ref
+
+
+def synth_yuv_pair(n_frames, height, width, bit_depth=10, chroma_ss="420"):
+    """The same clips as limited-range planar Y'CbCr code values (test, ref), each (n_frames, frame_pixels) uint8 / uint16
+    in file order (Y plane, Cb plane, Cr plane per frame): luma from the pattern above, smooth analytic chroma."""
+    test, ref = synth_pair_numpy(n_frames, height, width)
+    sc = float(2 ** (bit_depth - 8))
+    ch, cw = (height // 2, width // 2) if chroma_ss == "420" else (height, width)
+    f = np.arange(n_frames, dtype=np.float64)[:, None, None]
+    y = np.arange(ch, dtype=np.float64)[None, :, None]
+    x = np.arange(cw, dtype=np.float64)[None, None, :]
+    tp = 2.0 * math.pi
+    cb = 0.30 * np.sin(tp * (x / 23.0 + y / 31.0) + 0.2 * f)
+    cr = 0.25 * np.cos(tp * (x / 17.0 - y / 41.0) + 0.1 * f)
+    dtype = np.uint16 if bit_depth > 8 else np.uint8
+    out = []
+    for luma, dc in ((test[0, 0], 0.02), (ref[0, 0], 0.0)):
+        Y = np.round((16.0 + 219.0 * luma.astype(np.float64)) * sc)
+        U = np.round((128.0 + 224.0 * (cb + dc * np.sin(tp * x / 5.0))) * sc)
+        V = np.round((128.0 + 224.0 * cr) * sc)
+        out.append(np.concatenate([Y.reshape(n_frames, -1), U.reshape(n_frames, -1), V.reshape(n_frames, -1)], 1).astype(dtype))
+    return out[0], out[1]

@@ -155,6 +155,26 @@ int fvvdp_b200_heatmap_visualize(fvvdp_b200_ctx* ctx, int frame_in_block, float 
  */
 int fvvdp_b200_set_foveation_maps(fvvdp_b200_ctx* ctx, int level, const float* view_xy, const float* log2_rho);
 
+/*
+ * Video front end (ctx-free): one planar Y'CbCr frame -> luminance, replacing YUVReader.get_frame_rgb_tensor /
+ * video_reader_yuv_pytorch.unpack + the display model of fvvdp_video_source_dm (video_source_yuv.py:157-228,299-302,
+ * video_source_file.py:219-276): limited-range fixed2float, bilinear 4:2:0 chroma upsampling, ycbcr2rgb, clip to [0,1],
+ * display EOTF, RGB2Y.  Planes are DEVICE pointers (uint8, or uint16 when bit_depth > 8); 4:2:0 needs even width/height.
+ * lum_out: DEVICE float (H,W) in cd/m^2, or NULL; rgb_out: DEVICE float (H,W,3) display-encoded RGB (for callers that
+ * resize or apply their own photometry), or NULL.
+ */
+typedef struct fvvdp_b200_yuv_desc {
+  int32_t width, height;
+  int32_t bit_depth;          /* 8..16 */
+  int32_t chroma_420;         /* 1: 4:2:0, 0: 4:4:4 */
+  float ycbcr2rgb[9];         /* row-major 3x3 */
+  int32_t eotf;               /* fvvdp_b200_eotf */
+  float Y_peak, Y_black, gamma, L_min, L_max;
+  float rgb2y[3];
+} fvvdp_b200_yuv_desc;
+int fvvdp_b200_yuv_to_luminance(const fvvdp_b200_yuv_desc* desc, const void* y_plane, const void* u_plane, const void* v_plane,
+                                float* lum_out, float* rgb_out, int cuda_device, void* cuda_stream);
+
 typedef struct fvvdp_b200_pool_params {
   float beta_sch, beta_tch, beta_t; /* Lp exponents over spatial bands, temporal channels, frames */
   float w_transient;                /* weight of the transient channel */

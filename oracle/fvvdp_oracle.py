@@ -447,6 +447,45 @@ def visualize_diff_map(diff_map, context, colormap_type):
 
 
 # ----------------------------------------------------------------------------------------------
+# planar Y'CbCr frames (video_source_yuv.py:157-228, video_source_file.py:219-276)
+# ----------------------------------------------------------------------------------------------
+_YCBCR2RGB = {"2020": [[1, 0, 1.47460], [1, -0.16455, -0.57135], [1, 1.88140, 0]],
+              "709": [[1, 0, 1.402], [1, -0.344136, -0.714136], [1, 1.772, 0]]}
+
+
+def _upsample2_bilinear(c):
+    """torch.nn.functional.interpolate(scale_factor=2, mode='bilinear') (align_corners=False) of a (h,w) plane:
+    source coordinate max((dst + 0.5) / 2 - 0.5, 0), second tap clamped to the last sample."""
+    h, w = c.shape
+
+    def taps(n):
+        src = np.maximum((np.arange(2 * n, dtype=_F) + _F(0.5)) * _F(0.5) - _F(0.5), _F(0))
+        i0 = src.astype(np.int64)
+        return i0, np.minimum(i0 + 1, n - 1), (src - i0.astype(_F)).astype(_F)
+
+    y0, y1, ly = taps(h)
+    x0, x1, lx = taps(w)
+    ly, lx = ly[:, None], lx[None, :]
+    top = (_F(1) - lx) * c[y0][:, x0] + lx * c[y0][:, x1]
+    bot = (_F(1) - lx) * c[y1][:, x0] + lx * c[y1][:, x1]
+    return ((_F(1) - ly) * top + ly * bot).astype(_F)
+
+
+def yuv_frame_rgb(Y, u, v, bit_depth, chroma_ss, color_space):
+    """One planar frame (integer planes) -> display-encoded RGB (H,W,3) float32 in [0,1]:
+    _fixed2float_upscale :198-228 and get_frame_rgb_tensor :157-182."""
+    sc = _F(2 ** (bit_depth - 8))
+    Yf = np.clip(_F(1) / (sc * _F(219)) * Y.astype(_F) - _F(16 / 219), _F(0), _F(1))
+    planes = []
+    for c in (u, v):
+        cf = np.clip(_F(1) / (sc * _F(224)) * c.astype(_F) - _F(128 / 224), _F(-0.5), _F(0.5)).astype(_F)
+        planes.append(_upsample2_bilinear(cf) if chroma_ss == "420" else cf)
+    yuv = np.stack([Yf, planes[0], planes[1]], -1).astype(_F)
+    M = np.array(_YCBCR2RGB["2020" if color_space == "2020" else "709"], _F)
+    return np.clip(yuv @ M.T, _F(0), _F(1)).astype(_F)
+
+
+# ----------------------------------------------------------------------------------------------
 # the metric (fvvdp.py:190-334, 359-478)
 # ----------------------------------------------------------------------------------------------
 def to_bcfhw(a, dim_order):

@@ -186,6 +186,39 @@ def test_heatmap_colour_map_60fps_general_path(fv_mod, oracle):
     np.testing.assert_allclose(st["heatmap"].float().numpy(), wst["heatmap"].astype(np.float32), rtol=3e-3, atol=3e-3)
 
 
+@pytest.mark.parametrize("case", [("yuv_10b_420_2020", "420", "2020", "standard_hdr_pq"), ("yuv_8b_444_709", "444", "709", "standard_4k")])
+def test_yuv_video_source(fv_mod, golden, tmp_path, case):
+    """fvvdp_video_source_yuv_file on raw .yuv files: planes uploaded as stored, one conversion kernel per frame
+    (fvvdp_b200_yuv_to_luminance), metric through predict_video_source()."""
+    from fovvideovdp_b200 import video_source_yuv as vy
+    from fovvideovdp_b200.synthetic import synth_yuv_pair
+    name, css, cs, disp = case
+    g = golden(name)
+    H, W, bits = int(g["H"]), int(g["W"]), int(g["bits"])
+    t, r = synth_yuv_pair(6, H, W, bits, css)
+    props = dict(width=W, height=H, bit_depth=bits, color_space=cs, chroma_ss=css, fps=float(g["fps"]))
+    ft, fr = str(tmp_path / vy.create_yuv_fname("test", props)), str(tmp_path / vy.create_yuv_fname("ref", props))
+    t.tofile(ft)
+    r.tofile(fr)
+    assert vy.decode_video_props(ft) == dict(props, fps=float(g["fps"]))
+    vs = vy.fvvdp_video_source_yuv_file(ft, fr, display_photometry=disp)
+    assert list(vs.get_video_size()) == [H, W, 6] and vs.get_frames_per_second() == float(g["fps"])
+    dev = torch.device("cuda:0")
+    rgb = vs.test_vidr.get_frame_rgb_tensor(2, dev).cpu().numpy()
+    np.testing.assert_allclose(rgb[::3, ::3], g["rgb_test_f2"], atol=2e-6)
+    lum = vs.get_test_frame(2, dev)
+    assert tuple(lum.shape) == (1, 1, 1, H, W)
+    np.testing.assert_allclose(lum.cpu().numpy()[0, 0, 0], g["lum_test_f2"], rtol=5e-4, atol=2e-4)  # PQ amplifies the 1e-6 differences of the RGB stage
+    fv = fv_mod.fvvdp(display_name=disp)
+    jod, st = fv.predict_video_source(vs)
+    check_jod(jod, g["jod"])
+    check_q(st["Q_per_ch"], g["Q_per_ch"])
+    # resized clip: RGB from the kernel, torch interpolate, display model through forward()
+    vs2 = vy.fvvdp_video_source_yuv_file(ft, fr, display_photometry=disp, full_screen_resize="bilinear", resize_resolution=(W * 2, H * 2))
+    jod2, st2 = fv.predict_video_source(vs2)
+    assert st2["width"] == 2 * W and st2["height"] == 2 * H and 0 < float(jod2) <= 10
+
+
 def test_custom_geometry_foveated(fv_mod, golden):
     """Foveated scoring with a fvvdp_display_geometry SUBCLASS (pytorch_examples/ex_custom_ppd.py:38-57): the per-band
     view-direction / resolution-magnification maps come from the plugin's own methods."""

@@ -244,6 +244,36 @@ def test_custom_geometry_foveated(golden):
     _check_q(st["Q_per_ch"], g["Q_per_ch"], tol=1e-3)
 
 
+YUV_CASES = [("yuv_10b_420_2020", "420", "2020", "standard_hdr_pq"), ("yuv_8b_444_709", "444", "709", "standard_4k")]
+
+
+@pytest.mark.parametrize("case", YUV_CASES)
+def test_yuv_video_source(golden, case):
+    """Raw planar .yuv clips (video_source_yuv.py:157-302): fixed2float, bilinear chroma upsampling, ycbcr2rgb, display
+    model, metric."""
+    from fovvideovdp_b200.synthetic import synth_yuv_pair
+    name, css, cs, disp = case
+    g = golden(name)
+    H, W, bits = int(g["H"]), int(g["W"]), int(g["bits"])
+    ny, nc = H * W, (H * W // 4 if css == "420" else H * W)
+    ch, cw = (H // 2, W // 2) if css == "420" else (H, W)
+
+    def rgb_clip(frames):
+        return np.stack([O.yuv_frame_rgb(f[:ny].reshape(H, W), f[ny:ny + nc].reshape(ch, cw), f[ny + nc:].reshape(ch, cw), bits, css, cs)
+                         for f in frames], 0)
+
+    t, r = synth_yuv_pair(6, H, W, bits, css)
+    rt, rr = rgb_clip(t), rgb_clip(r)
+    np.testing.assert_allclose(rt[2][::3, ::3], g["rgb_test_f2"], atol=2e-6)
+    photo = O.photometry_from_preset(disp)
+    cspace = "BT.2020" if cs == "2020" else "sRGB"
+    lum = O.frame_luminance(np.transpose(rt[2], (2, 0, 1)), photo, O.metric_data()["rgb2y"][cspace])
+    np.testing.assert_allclose(lum, g["lum_test_f2"], rtol=3e-4, atol=1e-4)  # PQ amplifies the 1e-6 differences of the RGB stage
+    jod, st = O.predict(rt, rr, dim_order="FHWC", frames_per_second=float(g["fps"]), display_name=disp, color_space=cspace)
+    assert abs(jod - float(g["jod"])) / float(g["jod"]) < JOD_RTOL
+    _check_q(st["Q_per_ch"], g["Q_per_ch"])
+
+
 @pytest.mark.parametrize("hw", [(135, 240), (136, 241), (67, 97), (64, 64)])
 def test_odd_sizes(golden, hw):
     H, W = hw

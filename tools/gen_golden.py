@@ -5,6 +5,7 @@ CUDA path).  Inputs are analytic / seeded so only outputs (and small inputs) are
 
     python tools/gen_golden.py            # rewrites every fixture
     python tools/gen_golden.py widen      # only the fixtures of the widened surface (heat-map colour maps, custom geometry)
+    python tools/gen_golden.py yuv        # only the raw .yuv video-source fixtures
 
 Large tap tensors are stored as strided sub-samples ([::SY, ::SX]) to keep the fixtures small.
 """
@@ -309,13 +310,44 @@ def gen_widened_cases():
     save("video_custom_geometry_foveated", jod=float(q), Q_per_ch=st["Q_per_ch"], gaze=gaze, rho_band=st["rho_band"])
 
 
+def gen_yuv_cases():
+    """Raw .yuv clips through the reference's fvvdp_video_source_yuv_file (video_source_yuv.py).  That module imports its
+    siblings as top-level modules, so the package directory itself goes on sys.path."""
+    import tempfile
+    sys.path.insert(0, "/root/reference/pyfvvdp")
+    import video_source_yuv as vy
+    from fovvideovdp_b200.synthetic import synth_yuv_pair
+    # the reference's constructor formats a debug message from two attributes YUVReader never sets
+    # (video_source_yuv.py:266, AttributeError); give the class placeholders -- no arithmetic is touched
+    vy.YUVReader.color_transfer = "n/a"
+    vy.YUVReader.in_pix_fmt = "n/a"
+    for (H, W, bits, css, cs, fps, disp) in ((96, 160, 10, "420", "2020", 30, "standard_hdr_pq"), (72, 100, 8, "444", "709", 25, "standard_4k")):
+        t, r = synth_yuv_pair(6, H, W, bits, css)
+        with tempfile.TemporaryDirectory() as d:
+            props = dict(width=W, height=H, bit_depth=bits, color_space=cs, chroma_ss=css, fps=fps)
+            ft, fr = os.path.join(d, vy.create_yuv_fname("test", props)), os.path.join(d, vy.create_yuv_fname("ref", props))
+            t.tofile(ft)
+            r.tofile(fr)
+            vs = vy.fvvdp_video_source_yuv_file(ft, fr, display_photometry=disp)
+            fv = pyfvvdp.fvvdp(display_name=disp, device=CPU)
+            q, st = fv.predict_video_source(vs)
+            lum0 = vs.get_test_frame(2, CPU).numpy()[0, 0, 0]
+            rgb0 = vs.test_vidr.get_frame_rgb_tensor(2, CPU).numpy()
+            save(f"yuv_{bits}b_{css}_{cs}", jod=float(q), Q_per_ch=st["Q_per_ch"], lum_test_f2=lum0, rgb_test_f2=rgb0[::3, ::3],
+                 H=H, W=W, bits=bits, fps=fps, frames_per_second=st["frames_per_second"])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_grad_enabled(False)
     if len(sys.argv) > 1 and sys.argv[1] == "widen":
         gen_widened_cases()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "yuv":
+        gen_yuv_cases()
+        sys.exit(0)
     gen_unit_cases()
     gen_metric_cases()
     gen_known_answer()
     gen_widened_cases()
+    gen_yuv_cases()
