@@ -385,15 +385,22 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
   __shared__ __align__(8) u64 bars[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+  // the CTA coordinates are read ONCE through volatile asm: left to itself the compiler re-reads %ctaid (S2UR, long
+  // latency) inside the time loop instead of keeping the derived values
+  int bx, by, bz;
+  asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bx));
+  asm volatile("mov.u32 %0, %%ctaid.y;" : "=r"(by));
+  asm volatile("mov.u32 %0, %%ctaid.z;" : "=r"(bz));
+  const int tx0 = bx * TW, ty0 = by * TH;
   const int jx0 = tx0 >> 1, jy0 = ty0 >> 1;
   const int h = p.h, w = p.w, h2 = p.h2, w2 = p.w2;
-  const int f_lo = blockIdx.z * p.chunk, f_hi = min(f_lo + p.chunk, p.n_frames);
+  const int f_lo = bz * p.chunk, f_hi = min(f_lo + p.chunk, p.n_frames);
   const int s_lo = f_lo, s_hi = f_hi + p.fl - 1;  // slots walked by this CTA
-  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+  const int tile = by * gridDim.x + bx;
   float vmin = 0.0f, vmax = 1.0f;  // range of the raw level-0 samples this thread converted
-  const unsigned bar0 = smem_u32(&bars[0]);
-  const unsigned sL_u32 = smem_u32(sL), sRaw_u32 = smem_u32(sRaw);
+  // shared-window addresses, made opaque so that they are computed once (the conversion reads %cluster_ctaid: S2UR)
+  unsigned bar0 = smem_u32(&bars[0]), sL_u32 = smem_u32(sL), sRaw_u32 = smem_u32(sRaw);
+  asm volatile("" : "+r"(bar0), "+r"(sL_u32), "+r"(sRaw_u32));
 
   // ---------------- one-time set-up (all index arithmetic lives here, outside the time loop) ----------------
   if (TMA && tid == 0) {
@@ -602,7 +609,7 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
     // ---- reduce, columns -> ring slot s % FL (+ next level out) ----
     {
       float* ring_s = sNr + (s % FL) * (2 * NE);
-      float* gout = (p.Pn != nullptr && s >= s_lo + ((blockIdx.z > 0) ? p.fl - 1 : 0)) ? p.Pn + (long long)s * p.Pn_slot_stride : nullptr;
+      float* gout = (p.Pn != nullptr && s >= s_lo + ((bz > 0) ? p.fl - 1 : 0)) ? p.Pn + (long long)s * p.Pn_slot_stride : nullptr;
 #pragma unroll
       for (int i = 0; i < NCOL; ++i) {
         if (i < NCOL - 1 || cl_src[i] >= 0) {  // only the last round is partial
