@@ -20,7 +20,7 @@ EXPORTS = ["fvvdp_b200_create", "fvvdp_b200_score_block", "fvvdp_b200_heatmap", 
            "fvvdp_b200_level_size", "fvvdp_b200_launch_count", "fvvdp_b200_traffic_model", "fvvdp_b200_destroy",
            "fvvdp_b200_last_error", "fvvdp_b200_abi_version", "fvvdp_b200_pool_jod",
            "fvvdp_b200_profile", "fvvdp_b200_profile_read", "fvvdp_b200_heatmap_visualize", "fvvdp_b200_set_foveation_maps",
-           "fvvdp_b200_yuv_to_luminance"]
+           "fvvdp_b200_yuv_to_luminance", "fvvdp_b200_pu_sq_err"]
 COLORMAPS = {"threshold": 0, "supra-threshold": 1}
 PROFILE_CLASSES = MAX_LEVELS + 2
 
@@ -60,6 +60,10 @@ class YuvDesc(C.Structure):
                 ("rgb2y", C.c_float * 3)]
 
 
+class PuParams(C.Structure):
+    _fields_ = [("p", C.c_float * 7), ("L_min", C.c_float), ("L_max", C.c_float)]
+
+
 class PoolParams(C.Structure):
     _fields_ = [("beta_sch", C.c_float), ("beta_tch", C.c_float), ("beta_t", C.c_float), ("w_transient", C.c_float),
                 ("jod_a", C.c_float), ("log_jod_exp", C.c_float)]
@@ -96,6 +100,8 @@ def load_library():
     lib.fvvdp_b200_set_foveation_maps.restype = C.c_int
     lib.fvvdp_b200_yuv_to_luminance.argtypes = [C.POINTER(YuvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.fvvdp_b200_yuv_to_luminance.restype = C.c_int
+    lib.fvvdp_b200_pu_sq_err.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(PuParams), C.c_void_p, C.c_int, C.c_void_p]
+    lib.fvvdp_b200_pu_sq_err.restype = C.c_int
     lib.fvvdp_b200_read_tap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
     lib.fvvdp_b200_read_tap.restype = C.c_int64
     lib.fvvdp_b200_level_size.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
@@ -214,6 +220,15 @@ def yuv_to_luminance(desc: YuvDesc, y_ptr, u_ptr, v_ptr, lum_ptr, rgb_ptr, devic
                                          int(device_index), C.c_void_p(stream))
     if rc != 0:
         raise RuntimeError(f"fvvdp_b200_yuv_to_luminance failed ({rc}): {last_error(None)}")
+
+
+def pu_sq_err(test_ptr, ref_ptr, n, params: PuParams, acc_ptr, device_index, stream):
+    """acc (device double) += sum((PU(test) - PU(ref))^2) over n luminance samples."""
+    lib = load_library()
+    rc = lib.fvvdp_b200_pu_sq_err(C.c_void_p(test_ptr), C.c_void_p(ref_ptr), int(n), C.byref(params), C.c_void_p(acc_ptr), int(device_index),
+                                  C.c_void_p(stream))
+    if rc != 0:
+        raise RuntimeError(f"fvvdp_b200_pu_sq_err failed ({rc}): {last_error(None)}")
 
 
 def pool_jod(q_ptr, n_bands, n_frames, q_stride, params: PoolParams, device_index, out_ptr, stream):

@@ -794,6 +794,22 @@ extern "C" int fvvdp_b200_yuv_to_luminance(const fvvdp_b200_yuv_desc* d, const v
   return FVVDP_B200_OK;
 }
 
+extern "C" int fvvdp_b200_pu_sq_err(const float* lum_test, const float* lum_ref, int64_t n, const fvvdp_b200_pu_params* params,
+                                    double* sq_err_acc, int cuda_device, void* cuda_stream) {
+  fvvdp_b200_ctx* ctx = nullptr;  // ctx-free: errors are reported through fvvdp_b200_last_error(NULL)
+  if (!lum_test || !lum_ref || !params || !sq_err_acc) return fail(ctx, FVVDP_B200_ERR_INVALID, "null argument");
+  if (n < 1) return fail(ctx, FVVDP_B200_ERR_INVALID, "empty frame");
+  CU(cudaSetDevice(cuda_device));
+  PuParams q;
+  for (int i = 0; i < 7; ++i) q.p[i] = params->p[i];
+  q.L_min = params->L_min; q.L_max = params->L_max;
+  const long long blocks = (n + 255) / 256;
+  pu_sqerr_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, (cudaStream_t)cuda_stream>>>(lum_test, lum_ref, (long long)n, q, sq_err_acc);
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "pu_sqerr_kernel launch: %s", cudaGetErrorString(le));
+  return FVVDP_B200_OK;
+}
+
 extern "C" int fvvdp_b200_pool_jod(const float* q, int n_bands, int64_t n_frames, int64_t q_stride, const fvvdp_b200_pool_params* params,
                                    int cuda_device, float* jod_out, void* cuda_stream) {
   fvvdp_b200_ctx* ctx = nullptr;  // ctx-free: errors are reported through fvvdp_b200_last_error(NULL)

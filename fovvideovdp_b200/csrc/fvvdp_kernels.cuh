@@ -709,4 +709,39 @@ __global__ void __launch_bounds__(256) yuv_kernel(const YuvParams p) {
   if (p.lum) p.lum[i] = eotf_dyn(rgb[0], p.eotf, p) * p.rgb2y[0] + eotf_dyn(rgb[1], p.eotf, p) * p.rgb2y[1] + eotf_dyn(rgb[2], p.eotf, p) * p.rgb2y[2];
 }
 
+// ------------------------------------------------------------------------------------------------
+// K_pu: PU21-PSNR frame term (pupsnr.py:52-79, utils.py:157-202): sum over the frame of (PU(T) - PU(R))^2 with
+// PU(Y) = p6 (((p0 + p1 Y^p3) / (1 + p2 Y^p3))^p4 - p5), Y clipped to [L_min, L_max]
+// ------------------------------------------------------------------------------------------------
+struct PuParams {
+  float p[7];
+  float L_min, L_max;
+};
+__device__ __forceinline__ float pu_encode(float Y, const PuParams& q) {
+  Y = fminf(fmaxf(Y, q.L_min), q.L_max);
+  const float yp = fast_exp2(q.p[3] * fast_log2(Y));
+  const float r = (q.p[0] + q.p[1] * yp) / (1.0f + q.p[2] * yp);
+  return q.p[6] * (fast_exp2(q.p[4] * fast_log2(r)) - q.p[5]);
+}
+__global__ void __launch_bounds__(256) pu_sqerr_kernel(const float* __restrict__ t, const float* __restrict__ r, long long n, PuParams q,
+                                                       double* __restrict__ acc) {
+  float s = 0.0f;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += 256ll * gridDim.x) {
+    const float d = pu_encode(__ldg(t + i), q) - pu_encode(__ldg(r + i), q);
+    s = fmaf(d, d, s);
+  }
+  double v = (double)s;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __shared__ double sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += sh[k];
+    atomicAdd(acc, tot);
+  }
+}
+
 }  // namespace fvvdp

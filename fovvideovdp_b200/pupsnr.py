@@ -1,0 +1,71 @@
+"""PU21-PSNR, the second metric of the reference's command line (pyfvvdp/pupsnr.py, utils.PU: utils.py:157-202):
+both luminance frames are encoded with the perceptually uniform PU21 transfer function and compared by PSNR, frame by
+frame.  The per-frame sum of squared differences is one CUDA kernel (fvvdp_b200_pu_sq_err, include/fvvdp_b200.h); there is
+no CPU fallback.  Interface = the reference's `pu_psnr` class; `predict()` takes the display model explicitly because
+the reference's relies on attributes its constructor never sets (pupsnr.py:43)."""
+import math
+
+import torch
+
+from . import _native
+from .display_model import fvvdp_display_photometry
+from .video_source import fvvdp_video_source_array
+
+PU21_BANDING_GLARE = [234.0235618, 216.9339286, 0.0001091864237, 0.893206924, 0.06733984121, 1.444718567, 567.6315065]  # utils.py:175
+
+
+class pu_psnr:
+    def __init__(self, device=None, display_name="standard_4k", display_photometry=None, color_space="sRGB"):
+        if device is None:
+            if not (torch.cuda.is_available() and torch.cuda.device_count() > 0):
+                raise RuntimeError("fovvideovdp_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+            device = torch.device("cuda:0")
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError(f"fovvideovdp_b200 runs on CUDA devices only (got '{device}'); there is no CPU fallback")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = device
+        _native.load_library()
+        self.display_photometry = fvvdp_display_photometry.load(display_name) if display_photometry is None else display_photometry
+        self.color_space = color_space
+        self.L_min, self.L_max = 0.005, 10000.0
+        p = PU21_BANDING_GLARE
+        self.peak = p[6] * (((p[0] + p[1] * self.L_max ** p[3]) / (1 + p[2] * self.L_max ** p[3])) ** p[4] - p[5])  # utils.py:185
+        self._params = _native.PuParams()
+        for i, v in enumerate(p):
+            self._params.p[i] = v
+        self._params.L_min, self._params.L_max = self.L_min, self.L_max
+
+    def predict(self, test_cont, reference_cont, dim_order="BCFHW", frames_per_second=0, fixation_point=None, frame_padding="replicate"):
+        vs = fvvdp_video_source_array(test_cont, reference_cont, frames_per_second, dim_order=dim_order,
+                                      display_photometry=self.display_photometry, color_space_name=self.color_space)
+        return self.predict_video_source(vs, fixation_point=fixation_point, frame_padding=frame_padding)
+
+    def predict_video_source(self, vid_source, fixation_point=None, frame_padding="replicate"):
+        _, _, N_frames = vid_source.get_video_size()
+        N_frames = int(N_frames)
+        dev = self.device
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            acc = torch.zeros(N_frames, dtype=torch.float64, device=dev)
+            n = 0
+            for ff in range(N_frames):
+                T = vid_source.get_test_frame(ff, device=dev).to(device=dev, dtype=torch.float32).contiguous()
+                R = vid_source.get_reference_frame(ff, device=dev).to(device=dev, dtype=torch.float32).contiguous()
+                n = T.numel()
+                _native.pu_sq_err(T.data_ptr(), R.data_ptr(), n, self._params, acc.data_ptr() + 8 * ff, dev.index, stream)
+                T.record_stream(torch.cuda.current_stream(dev))
+                R.record_stream(torch.cuda.current_stream(dev))
+            sq = acc.cpu().numpy()  # one device->host read
+        psnr = sum(20.0 * math.log10(self.peak / math.sqrt(float(s) / n)) for s in sq) / N_frames  # pupsnr.py:66-79
+        return torch.tensor(psnr, dtype=torch.float32, device=dev), None
+
+    def short_name(self):
+        return "PU21-PSNR"
+
+    def quality_unit(self):
+        return "dB"
+
+    def get_info_string(self):
+        return None

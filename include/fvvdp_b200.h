@@ -175,6 +175,18 @@ typedef struct fvvdp_b200_yuv_desc {
 int fvvdp_b200_yuv_to_luminance(const fvvdp_b200_yuv_desc* desc, const void* y_plane, const void* u_plane, const void* v_plane,
                                 float* lum_out, float* rgb_out, int cuda_device, void* cuda_stream);
 
+/*
+ * PU21-PSNR (the reference CLI's second metric, pupsnr.py:52-79 with utils.PU, utils.py:157-202), ctx-free: adds
+ * sum((PU(test) - PU(ref))^2) over `n` luminance samples (DEVICE floats, cd/m^2) to *sq_err_acc (DEVICE double, zeroed by
+ * the caller).  The caller finishes a frame as 20 log10(peak / sqrt(acc / n)) and averages the frames.
+ */
+typedef struct fvvdp_b200_pu_params {
+  float p[7];                 /* PU21 parameters (utils.py:172-179) */
+  float L_min, L_max;         /* luminance clip range, 0.005 .. 10000 cd/m^2 */
+} fvvdp_b200_pu_params;
+int fvvdp_b200_pu_sq_err(const float* lum_test, const float* lum_ref, int64_t n, const fvvdp_b200_pu_params* params,
+                         double* sq_err_acc, int cuda_device, void* cuda_stream);
+
 typedef struct fvvdp_b200_pool_params {
   float beta_sch, beta_tch, beta_t; /* Lp exponents over spatial bands, temporal channels, frames */
   float w_transient;                /* weight of the transient channel */

@@ -486,6 +486,36 @@ def yuv_frame_rgb(Y, u, v, bit_depth, chroma_ss, color_space):
 
 
 # ----------------------------------------------------------------------------------------------
+# PU21-PSNR (pupsnr.py:52-79, utils.py:157-202)
+# ----------------------------------------------------------------------------------------------
+_PU21 = [234.0235618, 216.9339286, 0.0001091864237, 0.893206924, 0.06733984121, 1.444718567, 567.6315065]  # 'banding_glare'
+
+
+def pu_encode(Y, L_min=0.005, L_max=10000.0):
+    p = _PU21
+    Y = np.clip(Y.astype(_F), _F(L_min), _F(L_max))
+    Yp = Y ** _F(p[3])
+    return (_F(p[6]) * (((_F(p[0]) + _F(p[1]) * Yp) / (_F(1) + _F(p[2]) * Yp)) ** _F(p[4]) - _F(p[5]))).astype(_F)
+
+
+def pu_psnr(test, ref, dim_order="BCFHW", display_name="standard_4k", photometry=None, color_space="sRGB"):
+    """pu_psnr.predict_video_source: mean over the frames of 20 log10(peak / sqrt(mean((PU(T) - PU(R))^2)))."""
+    p = _PU21
+    L_max = 10000.0
+    peak = p[6] * (((p[0] + p[1] * L_max ** p[3]) / (1 + p[2] * L_max ** p[3])) ** p[4] - p[5])
+    photo = photometry if photometry is not None else photometry_from_preset(display_name)
+    rgb2y = metric_data()["rgb2y"][color_space]
+    tv, rv = to_bcfhw(np.asarray(test), dim_order), to_bcfhw(np.asarray(ref), dim_order)
+    N = tv.shape[2]
+    total = 0.0
+    for ff in range(N):
+        d = pu_encode(frame_luminance(tv[0, :, ff], photo, rgb2y)) - pu_encode(frame_luminance(rv[0, :, ff], photo, rgb2y))
+        mse = np.mean(d.astype(np.float64) ** 2)
+        total += 20.0 * math.log10(peak / math.sqrt(mse)) / N
+    return total
+
+
+# ----------------------------------------------------------------------------------------------
 # the metric (fvvdp.py:190-334, 359-478)
 # ----------------------------------------------------------------------------------------------
 def to_bcfhw(a, dim_order):

@@ -219,6 +219,20 @@ def test_yuv_video_source(fv_mod, golden, tmp_path, case):
     assert st2["width"] == 2 * W and st2["height"] == 2 * H and 0 < float(jod2) <= 10
 
 
+def test_pu_psnr(fv_mod, golden):
+    """PU21-PSNR (the reference CLI's --metrics pu-psnr): one squared-error kernel per frame pair."""
+    g = golden("pu_psnr")
+    t, r = synth_pair_numpy(5, 135, 240)
+    m = fv_mod.pu_psnr(display_name="standard_4k")
+    q, stats = m.predict(t, r, frames_per_second=30)
+    assert stats is None and m.short_name() == "PU21-PSNR" and m.quality_unit() == "dB" and m.get_info_string() is None
+    assert abs(float(q) - float(g["standard_4k"])) < 2e-3  # dB
+    q, _ = fv_mod.pu_psnr(display_name="standard_hdr_pq").predict(0.1 + 0.65 * t, 0.1 + 0.65 * r, frames_per_second=30)
+    assert abs(float(q) - float(g["standard_hdr_pq"])) < 2e-3
+    q, _ = fv_mod.pu_psnr(display_name="standard_fhd").predict(g["test_u8"], g["ref_u8"], dim_order="FHWC", frames_per_second=30)
+    assert abs(float(q) - float(g["u8_rgb_fhd"])) < 2e-3
+
+
 def test_custom_geometry_foveated(fv_mod, golden):
     """Foveated scoring with a fvvdp_display_geometry SUBCLASS (pytorch_examples/ex_custom_ppd.py:38-57): the per-band
     view-direction / resolution-magnification maps come from the plugin's own methods."""

@@ -244,6 +244,15 @@ def test_custom_geometry_foveated(golden):
     _check_q(st["Q_per_ch"], g["Q_per_ch"], tol=1e-3)
 
 
+def test_pu_psnr(golden):
+    """PU21-PSNR (pupsnr.py:52-79, utils.py:157-202) against the reference on sRGB, PQ and uint8 RGB content."""
+    g = golden("pu_psnr")
+    t, r = synth_pair_numpy(5, 135, 240)
+    assert abs(O.pu_psnr(t, r, display_name="standard_4k") - float(g["standard_4k"])) < 2e-3
+    assert abs(O.pu_psnr(0.1 + 0.65 * t, 0.1 + 0.65 * r, display_name="standard_hdr_pq") - float(g["standard_hdr_pq"])) < 2e-3
+    assert abs(O.pu_psnr(g["test_u8"], g["ref_u8"], dim_order="FHWC", display_name="standard_fhd") - float(g["u8_rgb_fhd"])) < 2e-3
+
+
 YUV_CASES = [("yuv_10b_420_2020", "420", "2020", "standard_hdr_pq"), ("yuv_8b_444_709", "444", "709", "standard_4k")]
 
 

@@ -310,6 +310,25 @@ def gen_widened_cases():
     save("video_custom_geometry_foveated", jod=float(q), Q_per_ch=st["Q_per_ch"], gaze=gaze, rho_band=st["rho_band"])
 
 
+def gen_pu_psnr_cases():
+    """PU21-PSNR through the reference's pu_psnr.predict_video_source (pupsnr.py:52-79) with its array video source."""
+    from pyfvvdp.video_source import fvvdp_video_source_array
+    test, ref = synth_pair_numpy(5, 135, 240)
+    out = {}
+    m = pyfvvdp.pu_psnr(device=CPU)
+    for disp in ("standard_4k", "standard_hdr_pq"):
+        t, r = (test, ref) if disp == "standard_4k" else (0.1 + 0.65 * test, 0.1 + 0.65 * ref)
+        vs = fvvdp_video_source_array(torch.tensor(t), torch.tensor(r), 30, dim_order="BCFHW", display_photometry=disp)
+        q, _ = m.predict_video_source(vs)
+        out[disp] = float(q)
+    rng = np.random.default_rng(7)
+    t8 = rng.integers(0, 256, (3, 40, 56, 3), dtype=np.uint8)
+    r8 = np.clip(t8.astype(np.int16) + rng.integers(-6, 7, t8.shape), 0, 255).astype(np.uint8)
+    vs = fvvdp_video_source_array(t8, r8, 30, dim_order="FHWC", display_photometry="standard_fhd")
+    out["u8_rgb_fhd"] = float(m.predict_video_source(vs)[0])
+    save("pu_psnr", test_u8=t8, ref_u8=r8, **out)
+
+
 def gen_yuv_cases():
     """Raw .yuv clips through the reference's fvvdp_video_source_yuv_file (video_source_yuv.py).  That module imports its
     siblings as top-level modules, so the package directory itself goes on sys.path."""
@@ -343,6 +362,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "widen":
         gen_widened_cases()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "pupsnr":
+        gen_pu_psnr_cases()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "yuv":
         gen_yuv_cases()
         sys.exit(0)
@@ -351,3 +373,4 @@ if __name__ == "__main__":
     gen_known_answer()
     gen_widened_cases()
     gen_yuv_cases()
+    gen_pu_psnr_cases()
