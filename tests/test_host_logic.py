@@ -202,3 +202,61 @@ def test_config_search_order(tmp_path, monkeypatch):
     assert config.parameters()["version"] == "1.2.3"
     with pytest.raises(RuntimeError):
         config.rgb2y("no such space")
+
+
+def test_yuv_file_name_properties(tmp_path):
+    """decode_video_props / create_yuv_fname / YUVReader geometry (video_source_yuv.py:6-110) -- host logic only."""
+    from fovvideovdp_b200 import video_source_yuv as vy
+    from fovvideovdp_b200.synthetic import synth_yuv_pair
+    props = dict(width=64, height=48, bit_depth=10, color_space="2020", chroma_ss="420", fps=29.97)
+    name = vy.create_yuv_fname("clip", props)
+    assert name == "clip_64x48_10b_420_2020_29.97fps.yuv"
+    assert vy.decode_video_props("/some/dir/" + name) == props
+    assert vy.decode_video_props("x_1280x720p_8b_444_bt709_25fps.yuv") == dict(width=1280, height=720, bit_depth=8, color_space="709",
+                                                                                  chroma_ss="444", fps=25.0)
+    d = vy.decode_video_props("noprops.yuv")  # the reference's defaults (:8-14)
+    assert (d["width"], d["height"], d["fps"], d["bit_depth"], d["color_space"], d["chroma_ss"]) == (1920, 1080, 24, 8, "2020", "420")
+    t, r = synth_yuv_pair(3, 48, 64, 10, "420")
+    assert t.dtype == np.uint16 and t.shape == (3, 48 * 64 * 3 // 2) and t.min() >= 64 and t.max() <= 940
+    path = tmp_path / name
+    t.tofile(path)
+    rd = vy.YUVReader(str(path))
+    assert (rd.width, rd.height, rd.frame_count, rd.bit_depth, rd.uv_shape) == (64, 48, 3, 10, (24, 32))
+    Y, u, v = rd.get_frame_yuv(2)
+    assert Y.shape == (48, 64) and u.shape == (24, 32) and np.array_equal(Y.ravel(), t[2, :48 * 64])
+    with pytest.raises(RuntimeError):
+        rd.get_frame_yuv(3)
+    with pytest.raises(FileNotFoundError):
+        vy.YUVReader(str(tmp_path / "missing_64x48.yuv"))
+    with pytest.raises(RuntimeError):  # conversion needs the CUDA kernel: no CPU fallback
+        rd.get_frame_rgb_tensor(0, torch.device("cpu"))
+
+
+def test_oracle_chroma_upsampling_is_torch_bilinear():
+    """The oracle's 4:2:0 chroma upsampling restates torch.nn.functional.interpolate(scale_factor=2, mode='bilinear')
+    (video_source_yuv.py:219-221)."""
+    from oracle import fvvdp_oracle as O
+    rng = np.random.default_rng(3)
+    for shape in ((5, 7), (24, 32), (1, 9)):
+        c = rng.random(shape, dtype=np.float32) - 0.5
+        want = torch.nn.functional.interpolate(torch.tensor(c)[None, None], scale_factor=2, mode="bilinear")[0, 0].numpy()
+        np.testing.assert_allclose(O._upsample2_bilinear(c), want, atol=1e-6)
+
+
+def test_heatmap_and_geometry_arguments_are_validated():
+    import fovvideovdp_b200 as m
+    with pytest.raises(AssertionError):
+        m.fvvdp.__init__(m.fvvdp.__new__(m.fvvdp), heatmap="rainbow")
+    with pytest.raises(AssertionError):
+        m.fvvdp.__init__(m.fvvdp.__new__(m.fvvdp), temp_padding="mirror")
+    from fovvideovdp_b200.display_model import fvvdp_display_geometry, geometry_is_stock
+
+    class custom(fvvdp_display_geometry):
+        def get_ppd(self, view_dir=None):
+            return self.ppd_centre if view_dir is None else self.ppd_centre / (torch.sqrt(torch.sum(view_dir ** 2, dim=0)) / 20.0 + 1.0)
+
+    stock = fvvdp_display_geometry([480, 270], distance_m=0.6, diagonal_size_inches=24)
+    mine = custom([480, 270], distance_m=0.6, diagonal_size_inches=24)
+    assert geometry_is_stock(stock) and not geometry_is_stock(mine)
+    view = mine.pix2view_direction(torch.tensor((4, 2)), torch.tensor([[0.5, 3.5]]), torch.tensor([[0.5, 1.5]]))
+    assert view.shape == (2, 1, 2) and float(mine.get_resolution_magnification(view).max()) < 1.0
