@@ -27,6 +27,24 @@ _WORKSPACE_BUDGET_BYTES = 16e9  # device memory a scoring context may take for i
 _HOST_BLOCK_FRAMES = 8          # clips in host memory: frames per block, so that uploads and kernels overlap block by block
 
 
+_LAYOUT_CACHE, _FILTER_CACHE = {}, {}
+
+
+def cached_pyramid_layout(width, height, ppd):
+    key = (width, height, float(ppd))
+    if key not in _LAYOUT_CACHE:
+        _LAYOUT_CACHE[key] = pyramid_layout(width, height, ppd)
+    return _LAYOUT_CACHE[key]
+
+
+def cached_temporal_filters(frames_per_second, filter_len, sigma, beta):
+    key = (float(frames_per_second), filter_len, float(sigma), float(beta))
+    if key not in _FILTER_CACHE:
+        F = temporal_filters(frames_per_second, filter_len, sigma, beta)
+        _FILTER_CACHE[key] = (F, F.tobytes(), torch.from_numpy(F))
+    return _FILTER_CACHE[key]
+
+
 def pyramid_layout(width, height, ppd):
     """Number of Gaussian levels and the band centre frequencies [cpd] for a W x H frame seen at `ppd`
     pixels per degree (fvvdp_lpyr_dec.__init__, fvvdp_lpyr_dec.py:15-49).  Returns (n_levels, freqs) with
@@ -151,6 +169,26 @@ class _FrameSet:
         ev = torch.cuda.Event()
         ev.record(self.up_stream)
         return ev
+
+    def fetch_all(self, indices):
+        """fetch() for every frame index of a block."""
+        if self.raw and self.resident:  # nothing to move: range check only
+            first = getattr(self.vs, "first_frame", 0)
+            lo, hi = min(indices) - first, max(indices) - first
+            if lo < 0 or hi >= self._n_local:
+                raise RuntimeError(f"frames {min(indices)}..{max(indices)} are not all held by this process")
+            return
+        for idx in indices:
+            self.fetch(idx)
+
+    def block_pointers(self, indices):
+        """([test pointers], [reference pointers]) of the frames of a block."""
+        if self.raw and self.resident:
+            first, fb, (bt, br) = getattr(self.vs, "first_frame", 0), self._frame_bytes, self._base
+            offs = [(i - first) * fb for i in indices]
+            return [bt + o for o in offs], [br + o for o in offs]
+        ptrs = [self.pointers(i) for i in indices]
+        return [q[0] for q in ptrs], [q[1] for q in ptrs]
 
     def fetch(self, idx):
         if idx in self.held:
@@ -333,21 +371,21 @@ class fvvdp:
             fixation_point = fixation_point.detach().cpu().numpy()
         fixation_point = np.asarray(fixation_point, dtype=np.float32)
 
-        n_levels, freqs = pyramid_layout(width, height, self.pix_per_deg)
+        n_levels, freqs = cached_pyramid_layout(width, height, self.pix_per_deg)
         n_bands = n_levels - 1
         if n_bands < 1:
             raise RuntimeError(f"Frames of {width}x{height} are too small to build a contrast pyramid")
         if is_image:
             temp_ch, fl = 1, 1
             F = np.ones((1, 1), np.float32)
+            F_bytes = F.tobytes()
         else:
             temp_ch = 2
             fl = int(math.ceil(250.0 / (1000.0 / fps)))
             self.filter_len = fl
             if fl > _native.MAX_FILTER_LEN:
                 raise RuntimeError(f"frame rate {fps} needs {fl} filter taps; at most {_native.MAX_FILTER_LEN} are supported")
-            F = temporal_filters(fps, fl, self.sustained_sigma, self.sustained_beta)
-            self.F = torch.from_numpy(F)
+            F, F_bytes, self.F = cached_temporal_filters(fps, fl, self.sustained_sigma, self.sustained_beta)
 
         # how the frames reach the kernels
         spec = None
@@ -378,7 +416,7 @@ class fvvdp:
         T = max(1, min(T, _native.MAX_BLOCK_FRAMES, f_end - f_begin))
 
         geo = self.display_geometry
-        key = (width, height, n_levels, tuple(float(f) for f in freqs), temp_ch, fl, F.tobytes(), tuple(sorted(spec.items())), dtype, C, T,
+        key = (width, height, n_levels, float(self.pix_per_deg), temp_ch, fl, F_bytes, tuple(sorted(spec.items())), dtype, C, T,
                self.foveated, self.heatmap if self.do_heatmap else None, self.debug_taps, self.color_space,
                (tuple(geo.display_size_m), geo.distance_m, geometry_is_stock(geo)) if self.foveated else None)
         ctx = self._context(key, lambda: self._make_config(width, height, n_levels, freqs, temp_ch, fl, F, spec, dtype, C, T))
@@ -404,8 +442,7 @@ class fvvdp:
             return n, [frame_at(f0 - (fl - 1) + s) for s in range(n + fl - 1)]
 
         def prefetch(f0):  # frames of the block starting at f0 -> device (host sources: on the upload stream)
-            for idx in block_slots(f0)[1]:
-                frames.fetch(idx)
+            frames.fetch_all(block_slots(f0)[1])
             return frames.uploaded()
 
         launches0 = ctx.launch_count()
@@ -423,13 +460,13 @@ class fvvdp:
                 ready_next = prefetch(nxt) if (ahead and nxt < f_end) else None
                 if ready is not None:
                     cur.wait_event(ready)
-                ptrs = [frames.pointers(idx) for idx in slots]
+                test_ptrs, ref_ptrs = frames.block_pointers(slots)
                 fix = None
                 if self.foveated:
                     fix = [fixation_point[f0 + i] if fixation_point.ndim == 2 else fixation_point for i in range(n)]
                     if custom_geo:  # gaze direction [deg] through the plugin (fvvdp.py:429-431)
                         fix = [self._gaze_direction(xy, width, height) for xy in fix]
-                ctx.score_block([p[0] for p in ptrs], [p[1] for p in ptrs], frames.strides, n, fix, Q_per_ch.data_ptr(), N_frames, f0,
+                ctx.score_block(test_ptrs, ref_ptrs, frames.strides, n, fix, Q_per_ch.data_ptr(), N_frames, f0,
                                 flags.data_ptr(), stream)
                 if self.do_heatmap:
                     beta_jod = 10.0 ** self.log_jod_exp
