@@ -491,6 +491,8 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
       (void)base; (void)step;
     }
     bp.n_frames = n_frames; bp.fl = fl;
+    while (bp.dup_prefix + 1 < n_slots && test_slots[bp.dup_prefix + 1] == test_slots[0] && ref_slots[bp.dup_prefix + 1] == ref_slots[0]) bp.dup_prefix++;
+    if (getenv("FVVDP_B200_NO_DUP_SKIP")) bp.dup_prefix = 0;  // A/B switch
     bp.sC = strides[0]; bp.sH = strides[1]; bp.sW = strides[2];
     bp.C = cfg.in_channels; bp.dtype = cfg.in_dtype; bp.eotf = cfg.eotf;
     bp.Yscale = cfg.Y_peak - cfg.Y_black; bp.Y_black = cfg.Y_black; bp.Y_peak = cfg.Y_peak; bp.gamma = cfg.gamma;

@@ -68,6 +68,7 @@ struct BandParams {
   // ---- geometry / schedule ----
   int h, w, h2, w2, h_odd, ntiles;
   int n_frames, fl, chunk;                    // output frames; filter taps (<= ring length of the kernel); output frames per CTA
+  int dup_prefix;                             // slots 1 .. dup_prefix hold the same frame as slot 0 (replicate padding)
   u64 wgt2[2][MAXRING];                        // [temporal channel][ring window position, 0 = oldest]: (w, w) packed
   // ---- level-0 input format ----
   long long sC, sH, sW;
@@ -540,14 +541,9 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
 #undef FVVDP_EOTF_PASS
   };
 
-  if (TMA) __syncthreads();  // barrier initialisation visible before the first wait
-  issue_load(s_lo, 0);
-  if (LANDING && s_lo + 1 < s_hi) issue_load(s_lo + 1, 1);
-
-  for (int s = s_lo; s < s_hi; ++s) {
-    const int buf = (s - s_lo) & 1;
-    const float* sLb = sL + (NLUM == 2 ? buf * TILE_FLOATS : 0);
-    // ---- the staged tile of slot s ----
+  // ---- stages of one slot (used by the time loop and by the peeled first slot below) ----
+  // stage A: luminance tile of `slot` complete in its buffer (this thread's part of it; a barrier follows)
+  auto stage_tile = [&](int s, int buf, int phase, bool later_in_flight) {
     if (KIND == IN_LEVEL0_GENERIC) {
       for (int pos = tid; pos < PLANE; pos += NT) {
         const int r = pos / LW, c = pos % LW;
@@ -560,19 +556,17 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
         reinterpret_cast<float2*>(sL)[pos] = v;
       }
     } else {
-      if (TMA) mbar_wait(bar0 + 8 * buf, ((s - s_lo) >> 1) & 1);
-      else if (s + 1 < s_hi) cp_async_wait<1>();
+      if (TMA) mbar_wait(bar0 + 8 * buf, phase);
+      else if (later_in_flight) cp_async_wait<1>();
       else cp_async_wait<0>();
       if (LANDING) {
         if (!TMA) __syncthreads();  // cp.async: the chunks of other threads
         convert(buf);
       }
     }
-    __syncthreads();  // (1) luminance tile of slot s complete; every reader of the buffers refilled below is done
-    if (LANDING) { if (s + 2 < s_hi) issue_load(s + 2, buf); }
-    else if (KIND == IN_PYRAMID_TMA) { if (s + 1 < s_hi) issue_load(s + 1, buf ^ 1); }
-
-    // ---- reduce, rows: sV[a][c] = sum_k K[k] L[2j-2+k][c],  j = clamp(jy0-1+a)  (zero padding + edge terms) ----
+  };
+  // stage B: reduce, rows: sV[a][c] = sum_k K[k] L[2j-2+k][c],  j = clamp(jy0-1+a)  (zero padding + edge terms)
+  auto rows_pass = [&](const float* sLb) {
     if (tid < ROW_THREADS) {  // one thread walks down a third of one staged column, (test, ref) pairs
       const float* col = sLb + 2 * rw_c;
       float* out = sV + 2 * rw_c;
@@ -605,8 +599,10 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
         }
       }
     }
-    __syncthreads();  // (2)
-    // ---- reduce, columns -> ring slot s % FL (+ next level out) ----
+  };
+  // stage C: reduce, columns -> ring slot s % FL (+ next level out); `dup` further ring positions / pyramid slots get the
+  // same tile (repeats of the first frame)
+  auto cols_pass = [&](int s, int dup) {
     {
       float* ring_s = sNr + (s % FL) * (2 * NE);
       float* gout = (p.Pn != nullptr && s >= s_lo + ((bz > 0) ? p.fl - 1 : 0)) ? p.Pn + (long long)s * p.Pn_slot_stride : nullptr;
@@ -630,9 +626,65 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
           }
           *reinterpret_cast<u64*>(ring_s + 2 * (tid + i * NT)) = o;
           if (gout != nullptr && cl_g[i] >= 0) *reinterpret_cast<u64*>(gout + cl_g[i]) = o;
+          for (int d = 1; d <= dup; ++d) {
+            *reinterpret_cast<u64*>(sNr + ((s + d) % FL) * (2 * NE) + 2 * (tid + i * NT)) = o;
+            if (gout != nullptr && cl_g[i] >= 0) *reinterpret_cast<u64*>(gout + d * p.Pn_slot_stride + cl_g[i]) = o;
+          }
         }
       }
     }
+
+  };
+
+  if (TMA) __syncthreads();  // barrier initialisation visible before the first wait
+  // Replicate padding repeats the first frame through the warm-up slots (fvvdp.py:259-260): the CTAs that start at slot 0
+  // stage and reduce it ONCE, copy the result into the ring positions and pyramid slots of the repeats, and start the time
+  // loop at the first slot that differs.
+  int s_begin = s_lo;
+  {
+    const int dup = (s_lo == 0) ? min(p.dup_prefix, p.fl - 2) : 0;
+    if (dup > 0) {
+      issue_load(0, 0);
+      stage_tile(0, 0, 0, false);
+      __syncthreads();
+      rows_pass(sL);
+      __syncthreads();
+      cols_pass(0, dup);
+      ring_store<FL, 0>(ring, sL, coff);
+#pragma unroll
+      for (int k = 1; k < FL; ++k)
+        if (k <= dup) {
+#pragma unroll
+          for (int e = 0; e < PXT; ++e) ring.v[k][e] = ring.v[0][e];
+        }
+      __syncthreads();
+      if (TMA) {  // fresh barrier phases for the time loop
+        if (tid == 0) {
+          asm volatile("mbarrier.inval.shared.b64 [%0];" ::"r"(bar0) : "memory");
+          asm volatile("mbarrier.inval.shared.b64 [%0];" ::"r"(bar0 + 8) : "memory");
+          mbar_init(bar0, 1);
+          mbar_init(bar0 + 8, 1);
+          asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+      }
+      s_begin = dup + 1;
+    }
+  }
+  issue_load(s_begin, 0);
+  if (LANDING && s_begin + 1 < s_hi) issue_load(s_begin + 1, 1);
+
+  for (int s = s_begin; s < s_hi; ++s) {
+    const int buf = (s - s_begin) & 1;
+    const float* sLb = sL + (NLUM == 2 ? buf * TILE_FLOATS : 0);
+    stage_tile(s, buf, ((s - s_begin) >> 1) & 1, s + 1 < s_hi);
+    __syncthreads();  // (1) luminance tile of slot s complete; every reader of the buffers refilled below is done
+    if (LANDING) { if (s + 2 < s_hi) issue_load(s + 2, buf); }
+    else if (KIND == IN_PYRAMID_TMA) { if (s + 1 < s_hi) issue_load(s + 1, buf ^ 1); }
+
+    rows_pass(sLb);
+    __syncthreads();  // (2)
+    cols_pass(s, 0);
 
     const bool emit = s >= f_lo + p.fl - 1;
     const int fi = s - (p.fl - 1);  // output frame
