@@ -336,6 +336,30 @@ def test_against_oracle_4k_image(fv_mod, oracle):
     check_q(st["Q_per_ch"], wst["Q_per_ch"])
 
 
+def test_against_oracle_4k_foveated_pq_image(fv_mod, oracle):
+    """One full 3840x2160 PQ frame pair scored foveated on standard_hdr_pq with an off-centre gaze (the frame size and
+    display of BASELINE config 5): view-direction tables, per-pixel rho cells and the re-laid-out CSF table at full size."""
+    t, r = synth_pair_numpy(1, 2160, 3840)
+    tq, rq = 0.1 + 0.65 * t[0, 0, 0], 0.1 + 0.65 * r[0, 0, 0]
+    gaze = np.array([900.0, 1700.0], dtype=np.float32)
+    want, wst = oracle.predict(tq, rq, dim_order="HW", display_name="standard_hdr_pq", foveated=True, fixation_point=gaze)
+    jod, st = fv_mod.fvvdp(display_name="standard_hdr_pq", foveated=True).predict(tq, rq, dim_order="HW", fixation_point=gaze)
+    check_jod(jod, want)
+    check_q(st["Q_per_ch"], wst["Q_per_ch"], tol=1e-3)
+
+
+def test_replicated_first_frame_shortcut_is_exact(fv_mod, monkeypatch):
+    """Replicate padding: the kernels reduce the repeated first frame once and copy it into the ring; the result must be
+    bit-identical to walking every repeat (FVVDP_B200_NO_DUP_SKIP=1), on the 8- and the 16-frame rings."""
+    t, r = synth_pair_torch(20, 270, 480, torch.device("cuda:0"))
+    for fps in (30, 60):
+        monkeypatch.delenv("FVVDP_B200_NO_DUP_SKIP", raising=False)
+        a, sa = fv_mod.fvvdp(display_name="standard_fhd").predict(t, r, frames_per_second=fps)
+        monkeypatch.setenv("FVVDP_B200_NO_DUP_SKIP", "1")
+        b, sb = fv_mod.fvvdp(display_name="standard_fhd").predict(t, r, frames_per_second=fps)
+        assert float(a) == float(b) and np.array_equal(sa["Q_per_ch"], sb["Q_per_ch"])
+
+
 # ---------------------------------------------------------------------------------------------- plumbing variants
 def test_block_size_and_residency_do_not_change_results(fv_mod):
     t, r = synth_pair_numpy(13, 135, 240)
