@@ -9,10 +9,11 @@ from .display_model import (fvvdp_display_geometry, fvvdp_display_photo_absolute
 from .fvvdp import fvvdp
 from .pupsnr import pu_psnr
 from .video_source import fvvdp_video_source, fvvdp_video_source_array, fvvdp_video_source_dm, reshuffle_dims
+from .video_source_file import fvvdp_video_source_file, load_image_as_array
 from .video_source_yuv import fvvdp_video_source_yuv_file
 
 __all__ = ["fvvdp", "pu_psnr", "fvvdp_display_photometry", "fvvdp_display_photo_eotf", "fvvdp_display_photo_gog", "fvvdp_display_photo_absolute",
-           "fvvdp_display_geometry", "fvvdp_video_source", "fvvdp_video_source_dm", "fvvdp_video_source_array", "fvvdp_video_source_yuv_file", "reshuffle_dims", "install"]
+           "fvvdp_display_geometry", "fvvdp_video_source", "fvvdp_video_source_dm", "fvvdp_video_source_array", "fvvdp_video_source_yuv_file", "fvvdp_video_source_file", "load_image_as_array", "reshuffle_dims", "install"]
 
 
 def install():

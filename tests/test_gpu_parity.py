@@ -219,6 +219,40 @@ def test_yuv_video_source(fv_mod, golden, tmp_path, case):
     assert st2["width"] == 2 * W and st2["height"] == 2 * H and 0 < float(jod2) <= 10
 
 
+def test_batch_front_end(fv_mod, tmp_path, capsys):
+    """Pair-level scheduling (two workers on one GPU) returns, in input order, what scoring each pair alone returns; the
+    command line prints them and writes the feature files."""
+    import cv2
+    from fovvideovdp_b200 import run_fvvdp as rf
+    from fovvideovdp_b200 import video_source_yuv as vy
+    from fovvideovdp_b200.synthetic import synth_yuv_pair
+    files = []
+    for k, (H, W) in enumerate(((48, 64), (64, 96))):
+        t, r = synth_yuv_pair(4 + k, H, W, 10, "420")
+        props = dict(width=W, height=H, bit_depth=10, color_space="709", chroma_ss="420", fps=30)
+        ft, fr = str(tmp_path / vy.create_yuv_fname(f"t{k}", props)), str(tmp_path / vy.create_yuv_fname(f"r{k}", props))
+        t.tofile(ft)
+        r.tofile(fr)
+        files.append((ft, fr))
+    ti, ri = synth_pair_numpy(1, 72, 100)
+    cv2.imwrite(str(tmp_path / "t.png"), np.round(ti[0, 0, 0] * 65535).astype(np.uint16))
+    cv2.imwrite(str(tmp_path / "r.png"), np.round(ri[0, 0, 0] * 65535).astype(np.uint16))
+    files.append((str(tmp_path / "t.png"), str(tmp_path / "r.png")))
+    res = rf.score_pairs(files, display="standard_fhd", metrics=("fvvdp", "pu-psnr"), devices=[0, 0])
+    assert len(res) == 3
+    fv = fv_mod.fvvdp(display_name="standard_fhd")
+    for (ft, fr), out in zip(files, res):
+        alone, st = fv.predict_video_source(fv_mod.fvvdp_video_source_file(ft, fr, display_photometry="standard_fhd"))
+        assert abs(out["FovVideoVDP"][0] - float(alone)) < 1e-6 and np.array_equal(out["FovVideoVDP"][1]["Q_per_ch"], st["Q_per_ch"])
+        assert out["PU21-PSNR"][0] > 10
+    capsys.readouterr()
+    rc = rf.main(["--test"] + [f[0] for f in files] + ["--ref"] + [f[1] for f in files] + ["--display", "standard_fhd", "--quiet", "--features",
+                 "--output-dir", str(tmp_path / "out"), "--gpus", "0"])
+    printed = [float(v) for v in capsys.readouterr().out.split()]
+    assert rc == 0 and len(printed) == 3 and all(abs(a - b["FovVideoVDP"][0]) < 1e-4 for a, b in zip(printed, res))
+    assert (tmp_path / "out" / "t_fmap.json").is_file()
+
+
 def test_pu_psnr(fv_mod, golden):
     """PU21-PSNR (the reference CLI's --metrics pu-psnr): one squared-error kernel per frame pair."""
     g = golden("pu_psnr")

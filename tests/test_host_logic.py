@@ -260,3 +260,36 @@ def test_heatmap_and_geometry_arguments_are_validated():
     assert geometry_is_stock(stock) and not geometry_is_stock(mine)
     view = mine.pix2view_direction(torch.tensor((4, 2)), torch.tensor([[0.5, 3.5]]), torch.tensor([[0.5, 1.5]]))
     assert view.shape == (2, 1, 2) and float(mine.get_resolution_magnification(view).max()) < 1.0
+
+
+def test_batch_front_end_host_logic(tmp_path):
+    """Pair expansion / dealing of the batch front end and the file-type dispatch of fvvdp_video_source_file
+    (run_fvvdp.py:156-167,201-212; video_source_file.py:413-443)."""
+    import cv2
+    from fovvideovdp_b200 import run_fvvdp as rf
+    from fovvideovdp_b200.video_source_file import fvvdp_video_source_file, load_image_as_array
+    assert rf.deal_pairs(7, 3) == [[0, 3, 6], [1, 4], [2, 5]] and rf.deal_pairs(2, 4) == [[0], [1], [], []]
+    assert rf.expand_pairs(["a", "b", "c"], ["r"]) == [("a", "r"), ("b", "r"), ("c", "r")]
+    assert rf.expand_pairs(["a"], ["r", "s"]) == [("a", "r"), ("a", "s")]
+    with pytest.raises(RuntimeError):
+        rf.expand_pairs(["a", "b"], ["r", "s", "t"])
+    rng = np.random.default_rng(5)
+    rgb16 = rng.integers(0, 65536, (20, 32, 3), dtype=np.uint16)
+    grey8 = rng.integers(0, 256, (20, 32), dtype=np.uint8)
+    cv2.imwrite(str(tmp_path / "a.png"), rgb16[:, :, ::-1])
+    cv2.imwrite(str(tmp_path / "b.png"), np.dstack([rgb16[:, :, ::-1], np.full((20, 32), 65535, np.uint16)]))  # with alpha
+    cv2.imwrite(str(tmp_path / "g.png"), grey8)
+    assert np.array_equal(load_image_as_array(str(tmp_path / "a.png")), rgb16)
+    assert np.array_equal(load_image_as_array(str(tmp_path / "b.png")), rgb16)
+    assert load_image_as_array(str(tmp_path / "g.png")).shape == (20, 32, 1)
+    vs = fvvdp_video_source_file(str(tmp_path / "a.png"), str(tmp_path / "b.png"), display_photometry="standard_4k")
+    assert tuple(vs.get_video_size()) == (20, 32, 1) and vs.get_frames_per_second() == 0
+    (tmp_path / "clip_32x20_8b_420_709_25fps.yuv").write_bytes(bytes(32 * 20 * 3 // 2 * 2))
+    (tmp_path / "clip.mp4").write_bytes(b"not a video")
+    with pytest.raises(AssertionError):
+        fvvdp_video_source_file(str(tmp_path / "a.png"), str(tmp_path / "clip_32x20_8b_420_709_25fps.yuv"))
+    with pytest.raises(RuntimeError):
+        fvvdp_video_source_file(str(tmp_path / "clip.mp4"), str(tmp_path / "clip.mp4"))
+    y = fvvdp_video_source_file(str(tmp_path / "clip_32x20_8b_420_709_25fps.yuv"), str(tmp_path / "clip_32x20_8b_420_709_25fps.yuv"),
+                                display_photometry="standard_4k")
+    assert list(y.get_video_size()) == [20, 32, 2] and y.get_frames_per_second() == 25.0
