@@ -457,12 +457,12 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
     const int mode = cfg.temp_ch == 2 ? (fl > fused::RING ? 2 : 1) : 0;
     const int ring_len = mode == 2 ? fused::MAXRING : fused::RING;
     for (int cc = 0; cc < cfg.temp_ch; ++cc)
-      for (int k = 0; k < ring_len; ++k) {
-        const int kk = k - (ring_len - fl);  // window position within the real filter, 0 = oldest
-        const float wv = kk >= 0 ? cfg.filt[cc][fl - 1 - kk] : 0.0f;  // corr_filter = F.flip(0), fvvdp.py:298
+      for (int i = 0; i < 2 * ring_len; ++i) {
+        const int age = i % ring_len;  // 0 = newest frame; cfg.filt[cc][0] weighs the newest (corr_filter = F.flip(0), fvvdp.py:298)
+        const float wv = age < fl ? cfg.filt[cc][age] : 0.0f;
         uint32_t bits;
         memcpy(&bits, &wv, 4);
-        bp.wgt2[cc][k] = ((unsigned long long)bits << 32) | bits;
+        bp.wext[cc][i] = ((unsigned long long)bits << 32) | bits;
       }
     // contiguous float frames at a common stride from one base address: level 0 is staged by TMA as well
     bool l0_tma = false;
@@ -491,6 +491,7 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
       (void)base; (void)step;
     }
     bp.n_frames = n_frames; bp.fl = fl;
+    bp.ring_phase = (int)(((q_col0 - (fl - 1)) % ring_len + ring_len) % ring_len);  // slot 0 is the frame shown at time q_col0 - (fl-1)
     while (bp.dup_prefix + 1 < n_slots && test_slots[bp.dup_prefix + 1] == test_slots[0] && ref_slots[bp.dup_prefix + 1] == ref_slots[0]) bp.dup_prefix++;
     if (getenv("FVVDP_B200_NO_DUP_SKIP")) bp.dup_prefix = 0;  // A/B switch
     bp.sC = strides[0]; bp.sH = strides[1]; bp.sW = strides[2];

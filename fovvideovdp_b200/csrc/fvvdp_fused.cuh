@@ -69,7 +69,11 @@ struct BandParams {
   int h, w, h2, w2, h_odd, ntiles;
   int n_frames, fl, chunk;                    // output frames; filter taps (<= ring length of the kernel); output frames per CTA
   int dup_prefix;                             // slots 1 .. dup_prefix hold the same frame as slot 0 (replicate padding)
-  u64 wgt2[2][MAXRING];                        // [temporal channel][ring window position, 0 = oldest]: (w, w) packed
+  int ring_phase;                             // slot s sits at ring position (s + ring_phase) mod ring length: the position follows
+                                              //   the frame's index in the CLIP, so the summation order of the temporal filters (and
+                                              //   with it every rounding) does not depend on how the clip is cut into blocks / ranks
+  u64 wext[2][2 * MAXRING];                    // [temporal channel][i]: (w, w) packed weight of AGE (i mod ring length), 0 = newest frame;
+                                              //   ring position j has age (rp - j) mod ring length when the newest frame sits at position rp: weight wext[rp + RL - j]
   // ---- level-0 input format ----
   long long sC, sH, sW;
   int C, dtype, eotf;
@@ -325,9 +329,10 @@ __device__ __forceinline__ void ring_store(Ring<FL>& ring, const float* __restri
   }
 }
 
-// R[cc][e] = sum_k wgt[cc][k] * ring[(J+1+k) % FL][e]   (window position k = 0 is the oldest frame)
-template <int FL, int TC, int J>
-__device__ __forceinline__ void fir_quad(const Ring<FL>& ring, const BandParams& p, u64 (&R)[TC][pixels_of(FL)]) {
+// R[cc][e] = sum_j w(age of slot j) * ring[j][e]: the frames stay in their ring slots and the WEIGHTS rotate with the step
+// (wp[cc] points at wext[cc][(s mod FL) + FL]; slot j has weight wp[cc][-j]), so the filter needs no per-step code version
+template <int FL, int TC>
+__device__ __forceinline__ void fir_quad(const Ring<FL>& ring, const u64* const (&wp)[2], u64 (&R)[TC][pixels_of(FL)]) {
 #pragma unroll
   for (int cc = 0; cc < TC; ++cc)
 #pragma unroll
@@ -335,18 +340,18 @@ __device__ __forceinline__ void fir_quad(const Ring<FL>& ring, const BandParams&
       if (FL == 1) {
         R[cc][e] = ring.v[0][e];
       } else {
-        u64 a = fmul2(ring.v[(J + 1) % FL][e], p.wgt2[cc][0]);
+        u64 a = fmul2(ring.v[0][e], wp[cc][0]);
 #pragma unroll
-        for (int k = 1; k < FL; ++k) a = ffma2(ring.v[(J + 1 + k) % FL][e], p.wgt2[cc][k], a);
+        for (int j = 1; j < FL; ++j) a = ffma2(ring.v[j][e], wp[cc][-j], a);
         R[cc][e] = a;
       }
     }
 }
 
 // temporal filter of this thread's own elements of the reduced-tile ring (written by the same thread, so no barrier is
-// needed between the column pass and this): sNc[cc][o] = sum_k wgt[cc][k] sNr[(J+1+k) % FL][o]
-template <int FL, int TC, int J>
-__device__ __forceinline__ void fir_coarse(const float* __restrict__ sNr, float* __restrict__ sNc, const BandParams& p, int tid) {
+// needed between the column pass and this): sNc[cc][o] = sum_j w(age of slot j) sNr[j][o]
+template <int FL, int TC>
+__device__ __forceinline__ void fir_coarse(const float* __restrict__ sNr, float* __restrict__ sNc, const u64* const (&wp)[2], int tid) {
   constexpr int NT = threads_of(FL), NCOL = ncol_of(FL);
 #pragma unroll
   for (int i = 0; i < NCOL; ++i) {
@@ -354,10 +359,10 @@ __device__ __forceinline__ void fir_coarse(const float* __restrict__ sNr, float*
     if (i < NCOL - 1 || o < NE) {
       u64 a[TC];
 #pragma unroll
-      for (int k = 0; k < FL; ++k) {
-        const u64 v = *reinterpret_cast<const u64*>(sNr + ((J + 1 + k) % FL) * (2 * NE) + 2 * o);
+      for (int j = 0; j < FL; ++j) {
+        const u64 v = *reinterpret_cast<const u64*>(sNr + j * (2 * NE) + 2 * o);
 #pragma unroll
-        for (int cc = 0; cc < TC; ++cc) a[cc] = k == 0 ? fmul2(v, p.wgt2[cc][0]) : ffma2(v, p.wgt2[cc][k], a[cc]);
+        for (int cc = 0; cc < TC; ++cc) a[cc] = j == 0 ? fmul2(v, wp[cc][0]) : ffma2(v, wp[cc][-j], a[cc]);
       }
 #pragma unroll
       for (int cc = 0; cc < TC; ++cc) *reinterpret_cast<u64*>(sNc + cc * (2 * NE) + 2 * o) = a[cc];
@@ -600,11 +605,11 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
       }
     }
   };
-  // stage C: reduce, columns -> ring slot s % FL (+ next level out); `dup` further ring positions / pyramid slots get the
-  // same tile (repeats of the first frame)
-  auto cols_pass = [&](int s, int dup) {
+  // stage C: reduce, columns -> ring position rp (+ next level out); dup > 0: every ring position and `dup` further
+  // pyramid slots get the same tile (repeats of the first frame)
+  auto cols_pass = [&](int s, int rp, int dup) {
     {
-      float* ring_s = sNr + (s % FL) * (2 * NE);
+      float* ring_s = sNr + rp * (2 * NE);
       float* gout = (p.Pn != nullptr && s >= s_lo + ((bz > 0) ? p.fl - 1 : 0)) ? p.Pn + (long long)s * p.Pn_slot_stride : nullptr;
 #pragma unroll
       for (int i = 0; i < NCOL; ++i) {
@@ -626,9 +631,10 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
           }
           *reinterpret_cast<u64*>(ring_s + 2 * (tid + i * NT)) = o;
           if (gout != nullptr && cl_g[i] >= 0) *reinterpret_cast<u64*>(gout + cl_g[i]) = o;
-          for (int d = 1; d <= dup; ++d) {
-            *reinterpret_cast<u64*>(sNr + ((s + d) % FL) * (2 * NE) + 2 * (tid + i * NT)) = o;
-            if (gout != nullptr && cl_g[i] >= 0) *reinterpret_cast<u64*>(gout + d * p.Pn_slot_stride + cl_g[i]) = o;
+          if (dup > 0) {
+            for (int j = 0; j < FL; ++j) *reinterpret_cast<u64*>(sNr + j * (2 * NE) + 2 * (tid + i * NT)) = o;
+            for (int d = 1; d <= dup; ++d)
+              if (gout != nullptr && cl_g[i] >= 0) *reinterpret_cast<u64*>(gout + d * p.Pn_slot_stride + cl_g[i]) = o;
           }
         }
       }
@@ -649,14 +655,14 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
       __syncthreads();
       rows_pass(sL);
       __syncthreads();
-      cols_pass(0, dup);
+      cols_pass(0, 0, dup);
+      // every ring position starts as the first frame: the repeats sit where the time loop would have put them, the
+      // positions beyond the window carry zero weights
       ring_store<FL, 0>(ring, sL, coff);
 #pragma unroll
       for (int k = 1; k < FL; ++k)
-        if (k <= dup) {
 #pragma unroll
-          for (int e = 0; e < PXT; ++e) ring.v[k][e] = ring.v[0][e];
-        }
+        for (int e = 0; e < PXT; ++e) ring.v[k][e] = ring.v[0][e];
       __syncthreads();
       if (TMA) {  // fresh barrier phases for the time loop
         if (tid == 0) {
@@ -684,20 +690,17 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
 
     rows_pass(sLb);
     __syncthreads();  // (2)
-    cols_pass(s, 0);
+    const int rp = (s + p.ring_phase) % FL;  // ring position of slot s
+    cols_pass(s, rp, 0);
 
     const bool emit = s >= f_lo + p.fl - 1;
     const int fi = s - (p.fl - 1);  // output frame
-    // ---- temporal filter of the thread's own coarse elements; its pixels into the register ring and their filter.
-    //      The ring position is a compile-time constant inside each case: no address arithmetic, no register moves.
-    u64 R[TC][PXT];
-    switch (s % FL) {
-#define FVVDP_CASE(J)                                             \
-  case J:                                                         \
-    if (emit && FL > 1) fir_coarse<FL, TC, (J) % FL>(sNr, sNc, p, tid); \
-    ring_store<FL, (J) % FL>(ring, sLb, coff);                    \
-    if (emit) fir_quad<FL, TC, (J) % FL>(ring, p, R);             \
-    break;
+    // ---- temporal filter of the thread's own coarse elements; its pixels into the register ring (the only step-dependent
+    //      register index: one small switch); the filter of the pixels follows the barrier, next to the masking maths
+    const u64* const wp[2] = {p.wext[0] + rp + FL, p.wext[1] + rp + FL};
+    if (emit && FL > 1) fir_coarse<FL, TC>(sNr, sNc, wp, tid);
+    switch (rp) {
+#define FVVDP_CASE(J) case J: ring_store<FL, (J) % FL>(ring, sLb, coff); break;
       FVVDP_CASE(0) FVVDP_CASE(1) FVVDP_CASE(2) FVVDP_CASE(3) FVVDP_CASE(4) FVVDP_CASE(5) FVVDP_CASE(6) FVVDP_CASE(7)
 #if FUSED_MAXRING_CASES
       FVVDP_CASE(8) FVVDP_CASE(9) FVVDP_CASE(10) FVVDP_CASE(11) FVVDP_CASE(12) FVVDP_CASE(13) FVVDP_CASE(14) FVVDP_CASE(15)
@@ -707,7 +710,9 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
     if (NLUM == 1 || emit) __syncthreads();  // (3) filtered coarse tiles visible; the single luminance tile may be rewritten
     if (!emit) continue;
 
-    // ---- expand the filtered coarse tile, contrast, CSF, masking, pooling: one 2x2 quad per thread ----
+    // ---- temporal filter of the own pixels, expand of the filtered coarse tile, contrast, CSF, masking, pooling ----
+    u64 R[TC][PXT];
+    fir_quad<FL, TC>(ring, wp, R);
     float acc[2] = {0.0f, 0.0f};
     float Lb[PXT], lgL[PXT], fj[PXT];
     int cj[PXT];

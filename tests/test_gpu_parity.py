@@ -469,7 +469,9 @@ def test_errors_and_warnings(fv_mod, caplog):
 def test_full_size_properties_4k(fv_mod):
     """BASELINE config 3 frame size (3840x2160, standard_4k), 12 frames resident on the GPU:
     identical clips score exactly 10 JOD; a frame block scored on its own reproduces the same per-frame
-    pooled energies as the whole clip (what frame sharding relies on); a static clip has constant Q."""
+    pooled energies as the whole clip (what frame sharding relies on); a static clip has constant Q (the temporal
+    filters add the ring positions in a fixed order while the weights rotate, so the rounding of a frame depends on its
+    index modulo the ring length: exact across block cuts, ~1e-7 of the luminance from frame to frame)."""
     dev = torch.device("cuda:0")
     t, r = synth_pair_torch(12, 2160, 3840, dev)
     fv = fv_mod.fvvdp(display_name="standard_4k", block_frames=4)
@@ -479,8 +481,8 @@ def test_full_size_properties_4k(fv_mod):
     assert 5.0 < float(jod) < 10.0 and np.all(np.isfinite(st["Q_per_ch"]))
     fv12 = fv_mod.fvvdp(display_name="standard_4k", block_frames=12)
     jod12, st12 = fv12.predict(t, r, frames_per_second=30)
-    np.testing.assert_allclose(st12["Q_per_ch"], st["Q_per_ch"], rtol=1e-6)
+    assert np.array_equal(st12["Q_per_ch"], st["Q_per_ch"])  # bit-identical: the ring position follows the frame index in the clip
     stat_t, stat_r = t[:, :, 3:4].expand(1, 1, 9, 2160, 3840), r[:, :, 3:4].expand(1, 1, 9, 2160, 3840)
     jod_s, st_s = fv.predict(stat_t, stat_r, frames_per_second=30)
     q = st_s["Q_per_ch"]
-    np.testing.assert_allclose(q, np.repeat(q[:, :, :1], 9, axis=2), rtol=1e-6)
+    assert np.abs(q - q[:, :, :1]).max() <= 1e-6 * q.max()  # the transient response of a static clip is itself ~1e-5 of the sustained one
