@@ -6,7 +6,9 @@
 //   * reduces the tile to the next Gaussian level (separable 5-tap, stride 2; fvvdp_lpyr_dec.py:183-207) and writes that
 //     level out for the next launch,
 //   * keeps the last `fl` frames of both streams ON CHIP while it walks through time: the tile's own pixels in a
-//     register ring, the reduced tile in a shared-memory ring,
+//     register ring, the reduced tile in a shared-memory ring; a frame stays in the ring position given by its index in
+//     the clip and the filter WEIGHTS rotate from step to step (one code version of the filters, and rounding that does
+//     not depend on how the clip is cut into blocks),
 //   * applies the sustained / transient temporal filters (fvvdp.py:294-300) to both rings, expands the filtered
 //     reduced tile (fvvdp_lpyr_dec.py:219-235), forms the contrast bands (:259-269), looks up the CSF
 //     (fvvdp.py:520-537), applies the masking model (:574-596) and accumulates sum D^beta (:467,598-607).
