@@ -34,14 +34,16 @@ def test_config_struct_matches_header_size():
     """sizeof(fvvdp_b200_config) as laid out by ctypes == as laid out by the C compiler."""
     import subprocess
     import tempfile
-    src = '#include <stdio.h>\n#include "fvvdp_b200.h"\nint main(){printf("%zu %zu", sizeof(fvvdp_b200_config), sizeof(fvvdp_b200_pool_params));return 0;}\n'
+    src = '#include <stdio.h>\n#include "fvvdp_b200.h"\nint main(){printf("%zu %zu %zu %zu", sizeof(fvvdp_b200_config), sizeof(fvvdp_b200_pool_params), sizeof(fvvdp_b200_yuv_desc), sizeof(fvvdp_b200_pu_params));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
         open(c, "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", os.path.join(d, "s")])
-        a, b = subprocess.check_output([os.path.join(d, "s")]).decode().split()
+        a, b, c_, d_ = subprocess.check_output([os.path.join(d, "s")]).decode().split()
     assert int(a) == ctypes.sizeof(_native.Config)
     assert int(b) == ctypes.sizeof(_native.PoolParams)
+    assert int(c_) == ctypes.sizeof(_native.YuvDesc)
+    assert int(d_) == ctypes.sizeof(_native.PuParams)
 
 
 def test_create_fails_loudly_without_gpu():
