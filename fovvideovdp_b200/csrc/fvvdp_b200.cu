@@ -538,7 +538,28 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
       bp.tapG = cfg.want_taps ? ctx->G[l + 1] : nullptr;
       bp.tapC = ctx->tapC[l]; bp.tapL = ctx->tapL[l]; bp.tapS = ctx->tapS[l]; bp.tapD = ctx->tapD[l];
       bp.dmap = ctx->dmap[l];
-      const int kind = l == 0 ? (l0_tma ? fused::IN_LEVEL0_TMA : (contig ? fused::IN_LEVEL0_CPASYNC : fused::IN_LEVEL0_GENERIC)) : fused::IN_PYRAMID_TMA;
+      int kind = l == 0 ? (l0_tma ? fused::IN_LEVEL0_TMA : (contig ? fused::IN_LEVEL0_CPASYNC : fused::IN_LEVEL0_GENERIC)) : fused::IN_PYRAMID_TMA;
+      if (kind == fused::IN_LEVEL0_GENERIC && !getenv("FVVDP_B200_NO_FRONT")) {
+        // any other input format: one luminance pass into planes laid out like the pyramid, then level 0 is TMA-staged too
+        if (!ctx->P[0]) {
+          const size_t n = (size_t)(ctx->T + cfg.filter_len - 1) * H * ctx->pitch[0];
+          CU(cudaMalloc(&ctx->P[0], sizeof(float) * n));
+          CU(cudaMemsetAsync(ctx->P[0], 0, sizeof(float) * n, st));
+          const cuuint64_t dims[3] = {(cuuint64_t)(2 * W), (cuuint64_t)H, (cuuint64_t)(ctx->T + cfg.filter_len - 1)};
+          const cuuint64_t str[2] = {(cuuint64_t)ctx->pitch[0] * 4, (cuuint64_t)H * ctx->pitch[0] * 4};
+          if (!make_tile_map(&ctx->pmap[0], ctx->P[0], 3, dims, str, 2 * fused::LW)) return fail(ctx, FVVDP_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the luminance planes");
+        }
+        {
+          ProfScope prof(ctx, 0, st);
+          // 4 pixels per thread with vector loads when rows are contiguous and every row / plane / frame starts aligned
+          const bool vec_ok = strides[2] == 1 && aligned && strides[1] % 4 == 0 && (cfg.in_channels == 1 || strides[0] % 4 == 0);
+          cudaError_t le1 = fused::launch_luminance(bp, ctx->P[0], (long long)H * ctx->pitch[0], ctx->pitch[0], n_slots, vec_ok, st);
+          if (le1 != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "luminance_kernel launch: %s", cudaGetErrorString(le1));
+          ctx->launches++;
+        }
+        kind = fused::IN_PYRAMID_TMA;
+        bp.tmap[0] = ctx->pmap[0];
+      }
       if (l >= 1) bp.tmap[0] = ctx->pmap[l];
       dim3 grid(ctx->tiles_x[l], ctx->tiles_y[l], nchunks);
       ProfScope prof(ctx, 1 + l, st);

@@ -817,12 +817,12 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
           if (p.tapD) p.tapD[((long long)fi * TC + cc) * plane + pofs] = D;
           Dsum[e] += (cc == 0 ? 1.0f : p.w_transient) * D;
           if (cc == 0 && p.tapL) p.tapL[(long long)fi * plane + pofs] = Lb[e];
-          if (LEVEL0 && p.tapR) {
+          if (p.tapR) {
             p.tapR[((long long)fi * NCH + cc * 2 + 0) * plane + pofs] = lo_of(R[cc][e]);
             p.tapR[((long long)fi * NCH + cc * 2 + 1) * plane + pofs] = hi_of(R[cc][e]);
           }
           if (cc == TC - 1 && p.dmap) p.dmap[(long long)fi * plane + pofs] = Dsum[e] / p.band_mul;
-          if (LEVEL0 && cc == 0 && p.ctxmap) p.ctxmap[(long long)fi * plane + pofs] = lo_of(R[0][e]);
+          if (cc == 0 && p.ctxmap) p.ctxmap[(long long)fi * plane + pofs] = lo_of(R[0][e]);
         }
       }
     }

@@ -10,5 +10,8 @@ struct BandParams;
 // 2 = video, ring of 16 frames (512 threads, one row of a quad each)
 cudaError_t launch_band(int input_kind, int mode, bool foveated, bool extra, const BandParams& p, dim3 grid, cudaStream_t st);
 cudaError_t configure_band_kernels();
+// level-0 input of any dtype / channel count / strides -> luminance planes in the pyramid layout (slots x h x pitch floats)
+// rows_vectorisable: unit pixel stride, row / channel strides and frame addresses aligned for 4-pixel vector loads
+cudaError_t launch_luminance(const BandParams& p, float* out, long long slot_stride, int pitch, int n_slots, bool rows_vectorisable, cudaStream_t st);
 }  // namespace fused
 }  // namespace fvvdp
