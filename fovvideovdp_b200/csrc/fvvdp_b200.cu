@@ -538,8 +538,8 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
       bp.tapG = cfg.want_taps ? ctx->G[l + 1] : nullptr;
       bp.tapC = ctx->tapC[l]; bp.tapL = ctx->tapL[l]; bp.tapS = ctx->tapS[l]; bp.tapD = ctx->tapD[l];
       bp.dmap = ctx->dmap[l];
-      int kind = l == 0 ? (l0_tma ? fused::IN_LEVEL0_TMA : (contig ? fused::IN_LEVEL0_CPASYNC : fused::IN_LEVEL0_GENERIC)) : fused::IN_PYRAMID_TMA;
-      if (kind == fused::IN_LEVEL0_GENERIC && !getenv("FVVDP_B200_NO_FRONT")) {
+      int kind = l == 0 ? (l0_tma ? fused::IN_LEVEL0_TMA : fused::IN_LEVEL0_CPASYNC) : fused::IN_PYRAMID_TMA;
+      if (l == 0 && !contig) {
         // any other input format: one luminance pass into planes laid out like the pyramid, then level 0 is TMA-staged too
         if (!ctx->P[0]) {
           const size_t n = (size_t)(ctx->T + cfg.filter_len - 1) * H * ctx->pitch[0];

@@ -1,7 +1,8 @@
 // Fused band kernel of the B200-native FovVideoVDP core (sm_100a): ONE kernel per pyramid level that
 //   * stages the level's luminance tile (+4 px halo) of the NEXT frames into shared memory while the current one is
 //     processed: TMA (cp.async.bulk.tensor, zero fill outside the image, mbarrier completion) for the pyramid levels and
-//     for contiguous float input frames, cp.async / plain loads for everything else (uint8, RGB, strided);
+//     for contiguous float input frames, cp.async for float frames TMA cannot address; every other input format
+//     (uint8, uint16, RGB, strided) is converted to luminance planes in the pyramid layout by luminance_kernel first;
 //     level 0 applies the display EOTF on the way from the landing buffer to the luminance tile,
 //   * reduces the tile to the next Gaussian level (separable 5-tap, stride 2; fvvdp_lpyr_dec.py:183-207) and writes that
 //     level out for the next launch,
@@ -54,7 +55,7 @@ constexpr int ROW_THREADS = ROW_SEGS * LW;      // 216
 
 typedef unsigned long long u64;  // two packed floats (lo = test, hi = reference)
 
-enum InputKind { IN_LEVEL0_CPASYNC = 0, IN_LEVEL0_GENERIC = 1, IN_PYRAMID_TMA = 2, IN_LEVEL0_TMA = 3 };
+enum InputKind { IN_LEVEL0_CPASYNC = 0, IN_PYRAMID_TMA = 2, IN_LEVEL0_TMA = 3 };  // any other level-0 input: luminance_kernel first
 
 struct BandParams {
   // ---- TMA descriptors: [0] pyramid planes (3-D: 2x+stream, y, slot) or level-0 test frames (3-D: x, y, frame); [1] level-0 reference frames
@@ -214,30 +215,6 @@ __device__ __forceinline__ float eotf_k(float v, const BandParams& p) {
 // EOTFs that expect display-encoded values in [0,1] and report anything outside ("Pixel outside the valid range 0-1")
 __device__ __forceinline__ bool eotf_checks_range(int kind) {
   return kind == FVVDP_B200_EOTF_SRGB || kind == FVVDP_B200_EOTF_GAMMA || kind == FVVDP_B200_EOTF_PQ;
-}
-
-__device__ __forceinline__ float eotf_one(float v, const BandParams& p, float& vmin, float& vmax) {
-  vmin = fminf(vmin, v);
-  vmax = fmaxf(vmax, v);
-  switch (p.eotf) {
-    case FVVDP_B200_EOTF_NONE: return v;
-    case FVVDP_B200_EOTF_ABSOLUTE: return eotf_k<FVVDP_B200_EOTF_ABSOLUTE>(v, p);
-    case FVVDP_B200_EOTF_LINEAR: return eotf_k<FVVDP_B200_EOTF_LINEAR>(v, p);
-    case FVVDP_B200_EOTF_SRGB: return eotf_k<FVVDP_B200_EOTF_SRGB>(v, p);
-    case FVVDP_B200_EOTF_GAMMA: return eotf_k<FVVDP_B200_EOTF_GAMMA>(v, p);
-    default: return eotf_k<FVVDP_B200_EOTF_PQ>(v, p);
-  }
-}
-
-__device__ __forceinline__ float lum_generic(const BandParams& p, const void* base, int y, int x, float& vmin, float& vmax) {
-  const long long off = (long long)y * p.sH + (long long)x * p.sW;
-  if (p.C == 3) {
-    const float r = eotf_one(load_sample(base, off, p.dtype), p, vmin, vmax);
-    const float g = eotf_one(load_sample(base, off + p.sC, p.dtype), p, vmin, vmax);
-    const float b = eotf_one(load_sample(base, off + 2 * p.sC, p.dtype), p, vmin, vmax);
-    return r * p.rgb2y[0] + g * p.rgb2y[1] + b * p.rgb2y[2];
-  }
-  return eotf_one(load_sample(base, off, p.dtype), p, vmin, vmax);
 }
 
 // EOTF of 8 raw samples in place (4 pixels of the test stream, 4 of the reference stream)
@@ -550,26 +527,13 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
 
   // ---- stages of one slot (used by the time loop and by the peeled first slot below) ----
   // stage A: luminance tile of `slot` complete in its buffer (this thread's part of it; a barrier follows)
-  auto stage_tile = [&](int s, int buf, int phase, bool later_in_flight) {
-    if (KIND == IN_LEVEL0_GENERIC) {
-      for (int pos = tid; pos < PLANE; pos += NT) {
-        const int r = pos / LW, c = pos % LW;
-        const int y = ty0 - 4 + r, x = tx0 - 4 + c;
-        float2 v = make_float2(0.0f, 0.0f);
-        if (y >= 0 && y < h && x >= 0 && x < w) {
-          v.x = lum_generic(p, p.slot[0][s], y, x, vmin, vmax);
-          v.y = lum_generic(p, p.slot[1][s], y, x, vmin, vmax);
-        }
-        reinterpret_cast<float2*>(sL)[pos] = v;
-      }
-    } else {
-      if (TMA) mbar_wait(bar0 + 8 * buf, phase);
-      else if (later_in_flight) cp_async_wait<1>();
-      else cp_async_wait<0>();
-      if (LANDING) {
-        if (!TMA) __syncthreads();  // cp.async: the chunks of other threads
-        convert(buf);
-      }
+  auto stage_tile = [&](int buf, int phase, bool later_in_flight) {
+    if (TMA) mbar_wait(bar0 + 8 * buf, phase);
+    else if (later_in_flight) cp_async_wait<1>();
+    else cp_async_wait<0>();
+    if (LANDING) {
+      if (!TMA) __syncthreads();  // cp.async: the chunks of other threads
+      convert(buf);
     }
   };
   // stage B: reduce, rows: sV[a][c] = sum_k K[k] L[2j-2+k][c],  j = clamp(jy0-1+a)  (zero padding + edge terms)
@@ -653,7 +617,7 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
     const int dup = (s_lo == 0) ? min(p.dup_prefix, p.fl - 2) : 0;
     if (dup > 0) {
       issue_load(0, 0);
-      stage_tile(0, 0, 0, false);
+      stage_tile(0, 0, false);
       __syncthreads();
       rows_pass(sL);
       __syncthreads();
@@ -685,7 +649,7 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
   for (int s = s_begin; s < s_hi; ++s) {
     const int buf = (s - s_begin) & 1;
     const float* sLb = sL + (NLUM == 2 ? buf * TILE_FLOATS : 0);
-    stage_tile(s, buf, ((s - s_begin) >> 1) & 1, s + 1 < s_hi);
+    stage_tile(buf, ((s - s_begin) >> 1) & 1, s + 1 < s_hi);
     __syncthreads();  // (1) luminance tile of slot s complete; every reader of the buffers refilled below is done
     if (LANDING) { if (s + 2 < s_hi) issue_load(s + 2, buf); }
     else if (KIND == IN_PYRAMID_TMA) { if (s + 1 < s_hi) issue_load(s + 1, buf ^ 1); }

@@ -1,6 +1,6 @@
 // Instantiations of the fused band kernel.  Compiled once per (input kind, temporal mode) with
-// -DFUSED_KIND={0,1,2,3} (fused::InputKind) -DFUSED_VIDEO={0: image, 1: video with up to 8 taps, 2: video with up to 16 taps}
-// so that the twelve translation units build in parallel.
+// -DFUSED_KIND={0,2,3} (fused::InputKind) -DFUSED_VIDEO={0: image, 1: video with up to 8 taps, 2: video with up to 16 taps}
+// so that the nine translation units build in parallel.
 #ifndef FUSED_KIND
 #error "compile with -DFUSED_KIND and -DFUSED_VIDEO"
 #endif
