@@ -22,7 +22,7 @@ runs = [
     ("image", dict(display_name="standard_fhd"), (td[0, 0, 0], rd[0, 0, 0]), dict(dim_order="HW")),
     ("foveated PQ", dict(display_name="standard_hdr_pq", foveated=True), (0.1 + 0.65 * t, 0.1 + 0.65 * r), dict(frames_per_second=30, fixation_point=gaze)),
     ("heat map, colour map", dict(display_name="standard_fhd", heatmap="threshold"), (t, r), dict(frames_per_second=30)),
-    ("uint8 RGB (generic staging)", dict(display_name="standard_fhd"),
+    ("uint8 RGB (luminance front end)", dict(display_name="standard_fhd"),
      ((t[0, 0, :, :, :, None] * 255).astype(np.uint8).repeat(3, -1), (r[0, 0, :, :, :, None] * 255).astype(np.uint8).repeat(3, -1)),
      dict(dim_order="FHWC", frames_per_second=30)),
 ]
