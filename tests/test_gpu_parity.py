@@ -465,6 +465,28 @@ def test_errors_and_warnings(fv_mod, caplog):
     assert fv.get_info_string() == '"FovVideoVDP v1.2.3, 37.84 [pix/deg], Lpeak=200, Lblack=0.5979 [cd/m^2], non-foveated, (standard_fhd)"'
 
 
+# ---------------------------------------------------------------------------------------------- full-size golden vectors
+@pytest.mark.parametrize("case", [("full_fhd_10f", 10, 1080, 1920, "standard_fhd", False), ("full_4k_9f", 9, 2160, 3840, "standard_4k", False),
+                                  ("full_4k_hdr_pq_foveated_9f", 9, 2160, 3840, "standard_hdr_pq", True)])
+def test_full_size_against_reference(fv_mod, golden, case):
+    """BASELINE.json frame sizes (configs[1], [2], [4]) against JOD / Q_per_ch produced by the UNMODIFIED reference on the CPU
+    (tools/gen_golden.py full): the first frames of the analytic clip the benchmark scores."""
+    name, N, H, W, disp, fov = case
+    g = golden(name)
+    t, r = synth_pair_numpy(N, H, W)
+    kw = {}
+    if fov:
+        t, r = 0.1 + 0.65 * t, 0.1 + 0.65 * r
+        kw["fixation_point"] = g["gaze"]
+    jod, st = fv_mod.fvvdp(display_name=disp, foveated=fov).predict(t, r, frames_per_second=30, **kw)
+    check_jod(jod, g["jod"])
+    check_q(st["Q_per_ch"], g["Q_per_ch"], tol=1e-3 if fov else 2e-4)
+    # the same clip resident on the GPU (TMA-staged level 0)
+    jod2, st2 = fv_mod.fvvdp(display_name=disp, foveated=fov).predict(torch.from_numpy(t).cuda(), torch.from_numpy(r).cuda(), frames_per_second=30, **kw)
+    check_jod(jod2, g["jod"])
+    check_q(st2["Q_per_ch"], g["Q_per_ch"], tol=1e-3 if fov else 2e-4)
+
+
 # ---------------------------------------------------------------------------------------------- full-size properties
 def test_full_size_properties_4k(fv_mod):
     """BASELINE config 3 frame size (3840x2160, standard_4k), 12 frames resident on the GPU:

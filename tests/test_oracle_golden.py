@@ -244,6 +244,15 @@ def test_custom_geometry_foveated(golden):
     _check_q(st["Q_per_ch"], g["Q_per_ch"], tol=1e-3)
 
 
+def test_full_hd_against_reference(golden):
+    """BASELINE configs[1] frame size: 1920x1080, standard_fhd, 30 fps, the first 10 frames of the benchmark's analytic clip."""
+    g = golden("full_fhd_10f")
+    t, r = synth_pair_numpy(10, 1080, 1920)
+    jod, st = O.predict(t, r, frames_per_second=30, display_name="standard_fhd")
+    assert abs(jod - float(g["jod"])) / float(g["jod"]) < JOD_RTOL
+    _check_q(st["Q_per_ch"], g["Q_per_ch"])
+
+
 def test_pu_psnr(golden):
     """PU21-PSNR (pupsnr.py:52-79, utils.py:157-202) against the reference on sRGB, PQ and uint8 RGB content."""
     g = golden("pu_psnr")

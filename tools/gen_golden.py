@@ -310,6 +310,23 @@ def gen_widened_cases():
     save("video_custom_geometry_foveated", jod=float(q), Q_per_ch=st["Q_per_ch"], gaze=gaze, rho_band=st["rho_band"])
 
 
+def gen_full_size_cases():
+    """BASELINE.json frame sizes through the unmodified reference (CPU): configs[1] 1920x1080 on standard_fhd and configs[2]
+    3840x2160 on standard_4k, 30 fps, a few frames of the same analytic clip the benchmark uses -- only JOD and Q_per_ch are kept."""
+    t, r = synth_pair_numpy(10, 1080, 1920)
+    fv = pyfvvdp.fvvdp(display_name="standard_fhd", device=CPU)
+    q, st = fv.predict(torch.tensor(t), torch.tensor(r), dim_order="BCFHW", frames_per_second=30)
+    save("full_fhd_10f", jod=float(q), Q_per_ch=st["Q_per_ch"], rho_band=st["rho_band"])
+    t, r = synth_pair_numpy(9, 2160, 3840)
+    fv = pyfvvdp.fvvdp(display_name="standard_4k", device=CPU)
+    q, st = fv.predict(torch.tensor(t), torch.tensor(r), dim_order="BCFHW", frames_per_second=30)
+    save("full_4k_9f", jod=float(q), Q_per_ch=st["Q_per_ch"], rho_band=st["rho_band"])
+    gaze = np.stack([np.linspace(0, 3839, 9), np.linspace(0, 2159, 9)], 1).astype(np.float32)
+    fv = pyfvvdp.fvvdp(display_name="standard_hdr_pq", device=CPU, foveated=True)
+    q, st = fv.predict(torch.tensor(0.1 + 0.65 * t), torch.tensor(0.1 + 0.65 * r), dim_order="BCFHW", frames_per_second=30, fixation_point=gaze)
+    save("full_4k_hdr_pq_foveated_9f", jod=float(q), Q_per_ch=st["Q_per_ch"], gaze=gaze)
+
+
 def gen_pu_psnr_cases():
     """PU21-PSNR through the reference's pu_psnr.predict_video_source (pupsnr.py:52-79) with its array video source."""
     from pyfvvdp.video_source import fvvdp_video_source_array
@@ -362,6 +379,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "widen":
         gen_widened_cases()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "full":
+        gen_full_size_cases()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "pupsnr":
         gen_pu_psnr_cases()
         sys.exit(0)
@@ -374,3 +394,4 @@ if __name__ == "__main__":
     gen_widened_cases()
     gen_yuv_cases()
     gen_pu_psnr_cases()
+    gen_full_size_cases()
