@@ -165,6 +165,19 @@ def test_heatmap_colour_maps(fv_mod, golden, mode):
     np.testing.assert_allclose(hm.mean(axis=(0, 2, 3, 4)), g["hm_mean"], atol=3e-4)
 
 
+@pytest.mark.parametrize("mode", ["raw", "threshold"])
+def test_heatmap_does_not_depend_on_the_block_cut(fv_mod, mode):
+    """Heat maps of a clip scored in blocks of 3 frames (difference-map pyramids and context frames are per block) equal
+    those of the clip scored in one block; the fixation point may be a float64 torch tensor."""
+    t, r = synth_pair_numpy(8, 135, 240)
+    gaze = torch.tensor(np.stack([np.linspace(10, 200, 8), np.linspace(5, 120, 8)], 1), dtype=torch.float64)
+    one, s1 = fv_mod.fvvdp(display_name="standard_fhd", heatmap=mode, foveated=True, block_frames=8).predict(t, r, frames_per_second=30, fixation_point=gaze)
+    cut, s3 = fv_mod.fvvdp(display_name="standard_fhd", heatmap=mode, foveated=True, block_frames=3).predict(t, r, frames_per_second=30, fixation_point=gaze)
+    assert float(one) == float(cut) and np.array_equal(s1["Q_per_ch"], s3["Q_per_ch"])
+    assert s1["heatmap"].shape == (1, 1 if mode == "raw" else 3, 8, 135, 240)
+    assert torch.equal(s1["heatmap"], s3["heatmap"])
+
+
 def test_heatmap_colour_map_low_dynamic_range(fv_mod, golden):
     g = golden("image_fhd_heatmap_threshold_lowdr")
     t, r = synth_pair_numpy(1, 270, 480)
