@@ -811,8 +811,16 @@ extern "C" int fvvdp_b200_yuv_to_luminance(const fvvdp_b200_yuv_desc* d, const v
   p.Yscale = d->Y_peak - d->Y_black; p.Y_black = d->Y_black; p.Y_peak = d->Y_peak; p.gamma = d->gamma; p.L_min = d->L_min; p.L_max = d->L_max;
   for (int i = 0; i < 3; ++i) p.rgb2y[i] = d->rgb2y[i];
   p.lum = lum_out; p.rgb = rgb_out;
-  dim3 grid((d->width + 31) / 32, (d->height + 7) / 8);
-  yuv_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(p);
+  dim3 grid(((d->width + 1) / 2 + 31) / 32, (d->height + 7) / 8);
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  switch (lum_out ? d->eotf : FVVDP_B200_EOTF_NONE) {
+    case FVVDP_B200_EOTF_NONE: yuv_kernel<FVVDP_B200_EOTF_NONE><<<grid, 256, 0, st>>>(p); break;
+    case FVVDP_B200_EOTF_SRGB: yuv_kernel<FVVDP_B200_EOTF_SRGB><<<grid, 256, 0, st>>>(p); break;
+    case FVVDP_B200_EOTF_GAMMA: yuv_kernel<FVVDP_B200_EOTF_GAMMA><<<grid, 256, 0, st>>>(p); break;
+    case FVVDP_B200_EOTF_PQ: yuv_kernel<FVVDP_B200_EOTF_PQ><<<grid, 256, 0, st>>>(p); break;
+    case FVVDP_B200_EOTF_LINEAR: yuv_kernel<FVVDP_B200_EOTF_LINEAR><<<grid, 256, 0, st>>>(p); break;
+    default: yuv_kernel<FVVDP_B200_EOTF_ABSOLUTE><<<grid, 256, 0, st>>>(p); break;
+  }
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "yuv_kernel launch: %s", cudaGetErrorString(le));
   return FVVDP_B200_OK;

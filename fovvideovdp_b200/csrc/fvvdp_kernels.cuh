@@ -665,48 +665,64 @@ __device__ __forceinline__ float yuv_sample(const void* p, long long i, int is16
 __device__ __forceinline__ float yuv_chroma(const YuvParams& p, const void* plane, int cy, int cx) {
   return fminf(fmaxf(p.wc * yuv_sample(plane, (long long)cy * p.cw + cx, p.is16) - p.oc, -0.5f), 0.5f);
 }
-__device__ __forceinline__ float eotf_dyn(float v, int kind, const YuvParams& p) {
-  switch (kind) {
-    case FVVDP_B200_EOTF_NONE: return v;
-    case FVVDP_B200_EOTF_ABSOLUTE: return fminf(fmaxf(v, p.L_min), p.L_max);
-    case FVVDP_B200_EOTF_LINEAR: return fminf(fmaxf(v, 0.005f), p.Y_peak) + p.Y_black;
-    case FVVDP_B200_EOTF_SRGB: {
-      const float lin = (v > 0.04045f) ? fast_pow((v + 0.055f) / 1.055f, 2.4f) : v / 12.92f;
-      return fmaf(p.Yscale, lin, p.Y_black);
-    }
-    case FVVDP_B200_EOTF_GAMMA: return fmaf(p.Yscale, fast_pow(v, p.gamma), p.Y_black);
-    default: {  // PQ, fvvdp_display_model.py:100-112
-      const float t = fast_pow(v, 1.0f / 78.843750000000000f);
-      const float L = 10000.0f * fast_pow(fmaxf(t - 0.83593750000000000f, 0.0f) / (18.851562500000000f - 18.687500000000000f * t), 1.0f / 0.15930175781250000f);
-      return fminf(fmaxf(L, 0.005f), p.Y_peak) + p.Y_black;
-    }
+// display EOTF of one clipped R'G'B' sample (KIND = fvvdp_b200_eotf); PQ takes its quotient in the log2 domain
+template <int KIND>
+__device__ __forceinline__ float yuv_eotf(float v, const YuvParams& p) {
+  if (KIND == FVVDP_B200_EOTF_NONE) return v;
+  if (KIND == FVVDP_B200_EOTF_ABSOLUTE) return fminf(fmaxf(v, p.L_min), p.L_max);
+  if (KIND == FVVDP_B200_EOTF_LINEAR) return fminf(fmaxf(v, 0.005f), p.Y_peak) + p.Y_black;
+  if (KIND == FVVDP_B200_EOTF_SRGB) {
+    const float lin = (v > 0.04045f) ? fast_exp2(2.4f * fast_log2(fmaf(v, 1.0f / 1.055f, 0.055f / 1.055f))) : v * (1.0f / 12.92f);
+    return fmaf(p.Yscale, lin, p.Y_black);
   }
+  if (KIND == FVVDP_B200_EOTF_GAMMA) return fmaf(p.Yscale, fast_pow(v, p.gamma), p.Y_black);
+  // PQ, fvvdp_display_model.py:100-112: L = 1e4 (max(t - c1, 0) / (c2 - c3 t))^(1/n), t = V^(1/m)
+  const float t = fast_exp2(fast_log2(v) * (1.0f / 78.843750000000000f));
+  const float L = fast_exp2(fmaf(fast_log2(fmaxf(t - 0.83593750000000000f, 0.0f)) - fast_log2(fmaf(-18.687500000000000f, t, 18.851562500000000f)),
+                                 1.0f / 0.15930175781250000f, 13.287712379549449f));
+  return fminf(fmaxf(L, 0.005f), p.Y_peak) + p.Y_black;
 }
 
+// one thread: two horizontally adjacent pixels (they share the rows of the chroma taps)
+template <int KIND>
 __global__ void __launch_bounds__(256) yuv_kernel(const YuvParams p) {
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int x = 2 * (blockIdx.x * 32 + (threadIdx.x & 31)), y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= p.W || y >= p.H) return;
-  const long long i = (long long)y * p.W + x;
-  const float Y = fminf(fmaxf(p.wy * yuv_sample(p.y, i, p.is16) - p.oy, 0.0f), 1.0f);
-  float cb, cr;
+  const bool two = x + 1 < p.W;
+  float cb[2], cr[2];
   if (p.is420) {
     // bilinear, align_corners = False: source coordinate max((dst + 0.5) / 2 - 0.5, 0); neighbour clamped to the last sample
-    const float sy = fmaxf(0.5f * (float)y - 0.25f, 0.0f), sx = fmaxf(0.5f * (float)x - 0.25f, 0.0f);
-    const int y0 = (int)sy, x0 = (int)sx, y1 = min(y0 + 1, p.ch - 1), x1 = min(x0 + 1, p.cw - 1);
-    const float ly = sy - (float)y0, lx = sx - (float)x0;
-    cb = (1.0f - ly) * ((1.0f - lx) * yuv_chroma(p, p.u, y0, x0) + lx * yuv_chroma(p, p.u, y0, x1)) +
-         ly * ((1.0f - lx) * yuv_chroma(p, p.u, y1, x0) + lx * yuv_chroma(p, p.u, y1, x1));
-    cr = (1.0f - ly) * ((1.0f - lx) * yuv_chroma(p, p.v, y0, x0) + lx * yuv_chroma(p, p.v, y0, x1)) +
-         ly * ((1.0f - lx) * yuv_chroma(p, p.v, y1, x0) + lx * yuv_chroma(p, p.v, y1, x1));
-  } else {
-    cb = yuv_chroma(p, p.u, y, x);
-    cr = yuv_chroma(p, p.v, y, x);
-  }
-  float rgb[3];
+    const float sy = fmaxf(0.5f * (float)y - 0.25f, 0.0f);
+    const int y0 = (int)sy, y1 = min(y0 + 1, p.ch - 1);
+    const float ly = sy - (float)y0;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) rgb[c] = fminf(fmaxf(p.m[3 * c] * Y + p.m[3 * c + 1] * cb + p.m[3 * c + 2] * cr, 0.0f), 1.0f);
-  if (p.rgb) { p.rgb[3 * i] = rgb[0]; p.rgb[3 * i + 1] = rgb[1]; p.rgb[3 * i + 2] = rgb[2]; }
-  if (p.lum) p.lum[i] = eotf_dyn(rgb[0], p.eotf, p) * p.rgb2y[0] + eotf_dyn(rgb[1], p.eotf, p) * p.rgb2y[1] + eotf_dyn(rgb[2], p.eotf, p) * p.rgb2y[2];
+    for (int k = 0; k < 2; ++k) {
+      const float sx = fmaxf(0.5f * (float)(x + k) - 0.25f, 0.0f);
+      const int x0 = (int)sx, x1 = min(x0 + 1, p.cw - 1);
+      const float lx = sx - (float)x0;
+      cb[k] = (1.0f - ly) * ((1.0f - lx) * yuv_chroma(p, p.u, y0, x0) + lx * yuv_chroma(p, p.u, y0, x1)) +
+              ly * ((1.0f - lx) * yuv_chroma(p, p.u, y1, x0) + lx * yuv_chroma(p, p.u, y1, x1));
+      cr[k] = (1.0f - ly) * ((1.0f - lx) * yuv_chroma(p, p.v, y0, x0) + lx * yuv_chroma(p, p.v, y0, x1)) +
+              ly * ((1.0f - lx) * yuv_chroma(p, p.v, y1, x0) + lx * yuv_chroma(p, p.v, y1, x1));
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      cb[k] = yuv_chroma(p, p.u, y, min(x + k, p.W - 1));
+      cr[k] = yuv_chroma(p, p.v, y, min(x + k, p.W - 1));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (k == 1 && !two) break;
+    const long long i = (long long)y * p.W + x + k;
+    const float Y = fminf(fmaxf(p.wy * yuv_sample(p.y, i, p.is16) - p.oy, 0.0f), 1.0f);
+    float rgb[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) rgb[c] = fminf(fmaxf(p.m[3 * c] * Y + p.m[3 * c + 1] * cb[k] + p.m[3 * c + 2] * cr[k], 0.0f), 1.0f);
+    if (p.rgb) { p.rgb[3 * i] = rgb[0]; p.rgb[3 * i + 1] = rgb[1]; p.rgb[3 * i + 2] = rgb[2]; }
+    if (p.lum) p.lum[i] = yuv_eotf<KIND>(rgb[0], p) * p.rgb2y[0] + yuv_eotf<KIND>(rgb[1], p) * p.rgb2y[1] + yuv_eotf<KIND>(rgb[2], p) * p.rgb2y[2];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
