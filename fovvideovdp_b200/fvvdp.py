@@ -422,8 +422,10 @@ class fvvdp:
         ctx = self._context(key, lambda: self._make_config(width, height, n_levels, freqs, temp_ch, fl, F, spec, dtype, C, T))
 
         stream = torch.cuda.current_stream(dev).cuda_stream
-        Q_per_ch = torch.zeros((n_bands, 2, N_frames), dtype=torch.float32, device=dev)
-        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        # one buffer: the pooled energies and, behind them, the flag word -- one allocation, one device->host read
+        result = torch.zeros(n_bands * 2 * N_frames + 1, dtype=torch.float32, device=dev)
+        Q_per_ch = result[:-1].view(n_bands, 2, N_frames)
+        flags = result[-1:].view(torch.int32)
         heatmap = None
         if self.do_heatmap:
             hm_ch = 1 if self.heatmap == "raw" else 3  # fvvdp.py:236
@@ -493,9 +495,9 @@ class fvvdp:
                              bytes_algorithmic_last_block=alg, bytes_plan_last_block=plan, frames_scored=f_end - f_begin)
 
         stats = {}
-        host = torch.cat([Q_per_ch.reshape(-1), flags.to(torch.float32)]).cpu().numpy()  # one device->host read
+        host = result.cpu().numpy()  # the one device->host read of the call
         stats["Q_per_ch"] = host[:-1].reshape(n_bands, 2, N_frames)
-        if host[-1] != 0:
+        if host[-1:].view(np.uint32)[0] != 0:
             logging.warning("Pixel outside the valid range 0-1")
         stats["rho_band"] = freqs
         stats["frames_per_second"] = fps
