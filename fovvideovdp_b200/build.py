@@ -8,11 +8,12 @@ from concurrent.futures import ThreadPoolExecutor
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-HEADERS = [os.path.join(CSRC, h) for h in ("fvvdp_common.cuh", "fvvdp_kernels.cuh", "fvvdp_fused.cuh", "fvvdp_fused_launch.h")] + \
+HEADERS = [os.path.join(CSRC, h) for h in ("fvvdp_common.cuh", "fvvdp_kernels.cuh", "fvvdp_fused.cuh", "fvvdp_fused_launch.h", "fvvdp_ws.cuh", "fvvdp_ws_geometry.h")] + \
     [os.path.join(os.path.dirname(PKG), "include", "fvvdp_b200.h")]
 # (object name, source, extra defines)
 UNITS = [("fvvdp_b200", "fvvdp_b200.cu", []), ("fused_dispatch", "fvvdp_fused_dispatch.cu", [])] + \
-    [(f"fused_{k}_{v}", "fvvdp_fused_inst.cu", [f"-DFUSED_KIND={k}", f"-DFUSED_VIDEO={v}"]) for k in (0, 2, 3) for v in range(3)]
+    [(f"fused_{k}_{v}", "fvvdp_fused_inst.cu", [f"-DFUSED_KIND={k}", f"-DFUSED_VIDEO={v}"]) for k in (0, 2, 3) for v in range(3)] + \
+    [(f"ws_{k}", "fvvdp_ws_inst.cu", [f"-DWS_KIND={k}"]) for k in (2, 3)]
 DEPS = HEADERS + [os.path.join(CSRC, u[1]) for u in UNITS]
 OBJ_DIR = os.path.join(PKG, "_lib", "obj")
 LIB = os.environ.get("FVVDP_B200_LIB") or os.path.join(PKG, "_lib", "libfvvdp_b200.so")  # override: experiment builds

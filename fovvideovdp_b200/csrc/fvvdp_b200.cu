@@ -13,6 +13,7 @@
 #include "fvvdp_fused.cuh"
 #include "fvvdp_fused_launch.h"
 #include "fvvdp_kernels.cuh"
+#include "fvvdp_ws_geometry.h"
 
 using namespace fvvdp;
 
@@ -27,6 +28,10 @@ struct fvvdp_b200_ctx {
   int pitch[FVVDP_B200_MAX_LEVELS] = {};
   float* cell = nullptr;                       // fused: [n_bands][32][8] CSF cells over log2 Y
   CUtensorMap pmap[FVVDP_B200_MAX_LEVELS];     // fused: TMA descriptors of P[l] (2x + stream, y, slot), box = staged tile
+  CUtensorMap pmap_ws[FVVDP_B200_MAX_LEVELS];  //   the same tensors with the staged-tile box of the warp-specialised kernel
+  int ws_max_level = -1;                       // warp-specialised kernel on levels 0..ws_max_level (video, <= 8 taps, no debug outputs)
+  int ntiles_used[FVVDP_B200_MAX_LEVELS] = {}; // tiles of the kernel that scored each level of the last block
+  bool no_dup_skip = false;                    // A/B switch FVVDP_B200_NO_DUP_SKIP
   float* G[FVVDP_B200_MAX_LEVELS] = {};        // v1 (and taps): G[0] = R; [T][nch][h_l][w_l]
   float* partial[FVVDP_B200_MAX_LEVELS] = {};  // [T][2][ntiles_l]
   float* tapC[FVVDP_B200_MAX_LEVELS] = {};
@@ -115,10 +120,11 @@ static encode_tiled_fn get_encode_tiled() {
   return fn;
 }
 // 3-D float tensor (dims[0] innermost, strides in bytes for dims 1..), box = staged tile (box0 x LH x 1), zero fill outside
-static bool make_tile_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, int box0) {
+static bool make_tile_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, int box0,
+                          int box1 = fused::LH) {
   encode_tiled_fn fn = get_encode_tiled();
   if (!fn) return false;
-  cuuint32_t box[4] = {(cuuint32_t)box0, (cuuint32_t)fused::LH, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)box0, (cuuint32_t)box1, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -175,8 +181,15 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
   const int T = c->T, nch = c->nch;
   int hh = cfg->height, ww = cfg->width;
   {
+    // A/B switches, read once: FVVDP_B200_PATH=v1 (general kernels) | fused (no warp-specialised kernel);
+    // FVVDP_B200_WS_LEVELS=n (warp-specialised kernel on levels < n only)
     const char* force = getenv("FVVDP_B200_PATH");
     c->fused = cfg->filter_len <= fused::MAXRING && !(force && strcmp(force, "v1") == 0);
+    const bool ws_ok = c->fused && !(force && strcmp(force, "fused") == 0) && cfg->temp_ch == 2 && cfg->filter_len >= 2 &&
+                       cfg->filter_len <= ws::RP + 1 && !cfg->want_taps && !cfg->want_dmap;
+    const char* wl = getenv("FVVDP_B200_WS_LEVELS");
+    c->ws_max_level = ws_ok ? (wl ? atoi(wl) - 1 : FVVDP_B200_MAX_LEVELS) : -1;
+    c->no_dup_skip = getenv("FVVDP_B200_NO_DUP_SKIP") != nullptr;
   }
   const int tile_w = c->fused ? fused::TW : TW, tile_h = c->fused ? fused::TH : TH;
   for (int l = 0; l < cfg->n_levels; ++l) {
@@ -196,7 +209,8 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
       CUC(cudaMemset(c->P[l], 0, sizeof(float) * n));
       const cuuint64_t dims[3] = {(cuuint64_t)(2 * c->lw[l]), (cuuint64_t)c->lh[l], (cuuint64_t)(T + cfg->filter_len - 1)};
       const cuuint64_t str[2] = {(cuuint64_t)c->pitch[l] * 4, (cuuint64_t)c->lh[l] * c->pitch[l] * 4};
-      if (!make_tile_map(&c->pmap[l], c->P[l], 3, dims, str, 2 * fused::LW)) {
+      if (!make_tile_map(&c->pmap[l], c->P[l], 3, dims, str, 2 * fused::LW) ||
+          !make_tile_map(&c->pmap_ws[l], c->P[l], 3, dims, str, 2 * ws::LW, ws::LH)) {
         fail(nullptr, FVVDP_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed for pyramid level %d", l);
         free_ctx(c);
         return FVVDP_B200_ERR_CUDA;
@@ -320,6 +334,7 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
     }
   }
   CUC(fused::configure_band_kernels());
+  CUC(ws::configure_band_ws_kernels());
   CUC(cudaFuncSetAttribute(level_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)level_smem_bytes(4)));
   CUC(cudaFuncSetAttribute(level_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)level_smem_bytes(4)));
   CUC(cudaFuncSetAttribute(level_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)level_smem_bytes(2)));
@@ -486,14 +501,16 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
           const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)((hi - lo) / g + 1)};
           const cuuint64_t str[2] = {(cuuint64_t)strides[1] * 4, (cuuint64_t)g};
           if (!make_tile_map(&bp.tmap[st], (const void*)lo, 3, dims, str, fused::LW)) l0_tma = false;
+          if (l0_tma && ctx->ws_max_level >= 0 && !make_tile_map(&bp.tmap_ws[st], (const void*)lo, 3, dims, str, ws::LW, ws::LH)) l0_tma = false;
         }
       }
       (void)base; (void)step;
     }
     bp.n_frames = n_frames; bp.fl = fl;
     bp.ring_phase = (int)(((q_col0 - (fl - 1)) % ring_len + ring_len) % ring_len);  // slot 0 is the frame shown at time q_col0 - (fl-1)
+    bp.ring_phase_ws = (int)(((q_col0 - (fl - 1)) % ws::RP + ws::RP) % ws::RP);
     while (bp.dup_prefix + 1 < n_slots && test_slots[bp.dup_prefix + 1] == test_slots[0] && ref_slots[bp.dup_prefix + 1] == ref_slots[0]) bp.dup_prefix++;
-    if (getenv("FVVDP_B200_NO_DUP_SKIP")) bp.dup_prefix = 0;  // A/B switch
+    if (ctx->no_dup_skip) bp.dup_prefix = 0;  // A/B switch
     bp.sC = strides[0]; bp.sH = strides[1]; bp.sW = strides[2];
     bp.C = cfg.in_channels; bp.dtype = cfg.in_dtype; bp.eotf = cfg.eotf;
     bp.Yscale = cfg.Y_peak - cfg.Y_black; bp.Y_black = cfg.Y_black; bp.Y_peak = cfg.Y_peak; bp.gamma = cfg.gamma;
@@ -518,10 +535,14 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
       bp.partial = ctx->partial[l];
       bp.h = ctx->lh[l]; bp.w = ctx->lw[l]; bp.h2 = ctx->lh[l + 1]; bp.w2 = ctx->lw[l + 1];
       bp.h_odd = bp.h & 1;
-      const int tiles = ctx->tiles_x[l] * ctx->tiles_y[l];
+      // the warp-specialised kernel (one CTA of 24 warps per SM, 32x64 tiles) where it applies; it stages with TMA only
+      const bool use_ws = l <= ctx->ws_max_level && (l > 0 || l0_tma || !contig);
+      const int tx = use_ws ? (bp.w + ws::TW - 1) / ws::TW : ctx->tiles_x[l], ty = use_ws ? (bp.h + ws::TH - 1) / ws::TH : ctx->tiles_y[l];
+      const int tiles = tx * ty;
       bp.ntiles = tiles;
+      ctx->ntiles_used[l] = tiles;
       // small levels: split the time walk so that the grid still fills the machine (each chunk re-walks fl-1 frames)
-      int nchunks = (4 * 148 + tiles - 1) / tiles;
+      int nchunks = ((use_ws ? 1 : 4) * 148 + tiles - 1) / tiles;
       const int max_chunks = (n_frames + 3) / 4;
       if (nchunks > max_chunks) nchunks = max_chunks;
       if (nchunks < 1) nchunks = 1;
@@ -547,7 +568,8 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
           CU(cudaMemsetAsync(ctx->P[0], 0, sizeof(float) * n, st));
           const cuuint64_t dims[3] = {(cuuint64_t)(2 * W), (cuuint64_t)H, (cuuint64_t)(ctx->T + cfg.filter_len - 1)};
           const cuuint64_t str[2] = {(cuuint64_t)ctx->pitch[0] * 4, (cuuint64_t)H * ctx->pitch[0] * 4};
-          if (!make_tile_map(&ctx->pmap[0], ctx->P[0], 3, dims, str, 2 * fused::LW)) return fail(ctx, FVVDP_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the luminance planes");
+          if (!make_tile_map(&ctx->pmap[0], ctx->P[0], 3, dims, str, 2 * fused::LW) ||
+              !make_tile_map(&ctx->pmap_ws[0], ctx->P[0], 3, dims, str, 2 * ws::LW, ws::LH)) return fail(ctx, FVVDP_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the luminance planes");
         }
         {
           ProfScope prof(ctx, 0, st);
@@ -559,11 +581,13 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
         }
         kind = fused::IN_PYRAMID_TMA;
         bp.tmap[0] = ctx->pmap[0];
+        bp.tmap_ws[0] = ctx->pmap_ws[0];
       }
-      if (l >= 1) bp.tmap[0] = ctx->pmap[l];
-      dim3 grid(ctx->tiles_x[l], ctx->tiles_y[l], nchunks);
+      if (l >= 1) { bp.tmap[0] = ctx->pmap[l]; bp.tmap_ws[0] = ctx->pmap_ws[l]; }
+      dim3 grid(tx, ty, nchunks);
       ProfScope prof(ctx, 1 + l, st);
-      cudaError_t le2 = fused::launch_band(kind, mode, cfg.foveated != 0, extra, bp, grid, st);
+      cudaError_t le2 = use_ws ? ws::launch_band_ws(kind, cfg.foveated != 0, bp, grid, st)
+                               : fused::launch_band(kind, mode, cfg.foveated != 0, extra, bp, grid, st);
       if (le2 != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "band_kernel[%d] launch: %s", l, cudaGetErrorString(le2));
       ctx->launches++;
     }
@@ -621,6 +645,7 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
     const bool h_odd = lp.h & 1, w_odd = lp.w & 1;
     lp.quirk = (h_odd && !w_odd) ? 1 : ((!h_odd && w_odd) ? 2 : 0);
     lp.ntiles = ctx->tiles_x[l] * ctx->tiles_y[l];
+    ctx->ntiles_used[l] = lp.ntiles;
     lp.band_mul = (l == 0) ? 1.0f : 2.0f;  // get_band, fvvdp_lpyr_dec.py:57-63 (the base band is never scored)
     lp.rho_band = cfg.band_freq[l];
     lp.ax = ctx->ax;
@@ -662,7 +687,7 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
   memset(&fin, 0, sizeof(fin));
   for (int l = 0; l < ctx->n_bands; ++l) {
     fin.partial[l] = ctx->partial[l];
-    fin.ntiles[l] = ctx->tiles_x[l] * ctx->tiles_y[l];
+    fin.ntiles[l] = ctx->ntiles_used[l];
     fin.npix[l] = (double)ctx->lh[l] * ctx->lw[l];
   }
   fin.q_out = q_out; fin.q_stride = q_stride; fin.q_col0 = q_col0;

@@ -60,6 +60,7 @@ enum InputKind { IN_LEVEL0_CPASYNC = 0, IN_PYRAMID_TMA = 2, IN_LEVEL0_TMA = 3 };
 struct BandParams {
   // ---- TMA descriptors: [0] pyramid planes (3-D: 2x+stream, y, slot) or level-0 test frames (3-D: x, y, frame); [1] level-0 reference frames
   CUtensorMap tmap[2];
+  CUtensorMap tmap_ws[2];                     // the same tensors with the staged-tile box of the warp-specialised kernel (fvvdp_ws.cuh)
   // ---- input ----
   const void* slot[2][FVVDP_B200_MAX_SLOTS];   // level 0 without TMA: [test|ref][slot] frame base pointers
   unsigned short slot_frame[2][FVVDP_B200_MAX_SLOTS];  // level 0 with TMA: frame coordinate of each slot
@@ -75,6 +76,7 @@ struct BandParams {
   int ring_phase;                             // slot s sits at ring position (s + ring_phase) mod ring length: the position follows
                                               //   the frame's index in the CLIP, so the summation order of the temporal filters (and
                                               //   with it every rounding) does not depend on how the clip is cut into blocks / ranks
+  int ring_phase_ws;                          // the same for the 7-position rings of the warp-specialised kernel
   u64 wext[2][2 * MAXRING];                    // [temporal channel][i]: (w, w) packed weight of AGE (i mod ring length), 0 = newest frame;
                                               //   ring position j has age (rp - j) mod ring length when the newest frame sits at position rp: weight wext[rp + RL - j]
   // ---- level-0 input format ----
