@@ -3,6 +3,7 @@ device buffers are passed as integer addresses (tensor.data_ptr()).  There is NO
 library is missing and cannot be built, or no CUDA device exists, the caller gets a RuntimeError."""
 import ctypes as C
 import os
+import threading
 
 from . import build as _build
 
@@ -76,8 +77,19 @@ def library_path():
     return _build.LIB
 
 
+_load_lock = threading.Lock()
+
+
 def load_library():
     """dlopen libfvvdp_b200.so (building it first if the sources are newer).  Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _load_lock:  # worker threads of run_fvvdp.score_pairs may arrive together: one of them builds / loads
+        return _load_library_locked()
+
+
+def _load_library_locked():
     global _lib
     if _lib is not None:
         return _lib

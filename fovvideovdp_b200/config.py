@@ -33,6 +33,8 @@ class config_files:
 
 
 _packaged = {}
+# calibration the packaged CSF tables were computed for (csf_cache/o{0,5}_sn1_5_cm0_604562_gpu0.mat, tools/import_reference_data.py)
+CSF_LUT_KEY = {"csf_sigma": -1.5, "k_cm": 0.604562}
 
 
 def _packaged_data():

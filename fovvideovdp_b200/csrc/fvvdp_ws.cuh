@@ -35,9 +35,16 @@ using fused::IN_PYRAMID_TMA; using fused::IN_LEVEL0_TMA;
 
 constexpr int NH = TH / 2 + 2, NW = TW / 2 + 2; // reduced tile with 1-px halo: origin (jy0-1, jx0-1)
 constexpr int NE = NH * NW;                     // 612
-constexpr int NCW = 16, NPW = 8;                // consumer / producer warps
+#ifndef WS_NPW
+#define WS_NPW 8
+#define WS_CREGS 96
+#define WS_PREGS 48
+#endif
+constexpr int NCW = 16, NPW = WS_NPW;           // consumer / producer warps
 constexpr int NCT = NCW * 32, NPT = NPW * 32, NT = NCT + NPT;
-constexpr int CONSUMER_REGS = 96, PRODUCER_REGS = 48;   // 512 * 96 + 256 * 48 = 768 * 80
+// registers per thread after setmaxnreg; the CTA's pool is NT x (65536 / NT rounded down to 8):
+//   8 producer warps: 512 * 96 + 256 * 48 = 768 * 80;  12 producer warps: 512 * 96 + 384 * 40 = 896 * 72
+constexpr int CONSUMER_REGS = WS_CREGS, PRODUCER_REGS = WS_PREGS;
 constexpr int MAXCHUNK = fused::MAXCHUNK;
 constexpr int LV4 = LW / 4;                     // 4-pixel chunks per staged row
 constexpr int NPC = LH * LV4;                   // 720
@@ -45,8 +52,9 @@ constexpr int NLD = (NPC + NPT - 1) / NPT;      // 3
 constexpr int NCOL = (NE + NPT - 1) / NPT;      // 3
 constexpr int PLANE = LH * LW;                  // one stream of a landing buffer (floats)
 constexpr int TILE_FLOATS = 2 * PLANE;          // one staged tile, both streams (23040 bytes)
-constexpr int ROW_CP = LW / 2;                  // row pass: column pairs (36) x 6 segments of 3 reduced rows
-constexpr int ROW_THREADS = ROW_CP * (NH / 3);  // 216
+constexpr int ROW_CP = LW / 2;                  // row pass: column pairs (36) x segments of ROW_SEG reduced rows
+constexpr int ROW_SEG = NPW >= 12 ? 2 : 3;
+constexpr int ROW_THREADS = ROW_CP * (NH / ROW_SEG);  // 216 / 324
 
 template <int KIND, bool FOV>
 struct Layout {
@@ -69,23 +77,38 @@ struct Layout {
 __device__ __forceinline__ void mbar_arrive(unsigned bar) {
   asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// wait with back-off: a warp that finds the barrier not ready yet sleeps instead of competing for issue slots
+__device__ __forceinline__ void mbar_wait_backoff(unsigned bar, unsigned parity) {
+#ifdef WS_BACKOFF
+  unsigned done;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  while (!done) {
+    __nanosleep(WS_BACKOFF);
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  }
+#else
+  mbar_wait(bar, parity);
+#endif
+}
 template <int ID, int COUNT>
 __device__ __forceinline__ void named_bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
 
 // One 4-pixel position chunk: landing buffer (two planes) -> EOTF -> luminance tile ((test, ref) interleaved).
-// The range of the raw samples ("Pixel outside the valid range 0-1", fvvdp_display_model.py:149-151) is tracked on the bit
-// patterns: a float lies in [0, 1] iff its pattern, read as unsigned, is <= that of 1.0f (negative values have the sign bit
-// set); -0.0f is cleared first.
-template <int EOTF>
-__device__ __forceinline__ void eotf_chunk(unsigned raw, unsigned lum, bool inside, const BandParams& p, unsigned& vbits) {
+// The range of the raw samples ("Pixel outside the valid range 0-1", fvvdp_display_model.py:149-151) is tracked with
+// three-input min / max (FMNMX3): one instruction per sample.
+template <int EOTF, bool INSIDE>
+__device__ __forceinline__ void eotf_chunk(unsigned raw, unsigned lum, bool inside, const BandParams& p, float& vmin, float& vmax) {
   const float4 a = lds128(raw), b = lds128(raw + PLANE * 4);
   float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
   if (eotf_checks_range(EOTF)) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) vbits = max(vbits, __float_as_uint(x[j] + 0.0f));  // x + 0 turns -0 into +0 (round to nearest)
+    for (int j = 0; j < 8; j += 2) {
+      vmin = fminf(fminf(vmin, x[j]), x[j + 1]);
+      vmax = fmaxf(fmaxf(vmax, x[j]), x[j + 1]);
+    }
   }
   eotf8<EOTF>(x, p);
-  if (!inside) {
+  if (!INSIDE && !inside) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = 0.0f;
   }
@@ -193,7 +216,7 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
     const float K0 = 0.05f, K1 = 0.25f, K3 = 0.25f, K4 = 0.05f;
     const bool rows_interior = (jy0 - 1 >= 1) && (jy0 + TH / 2 <= h2 - 2);
     const bool cols_interior = (jx0 - 1 >= 1) && (jx0 + TW / 2 <= w2 - 2);
-    unsigned vbits = 0u;  // largest bit pattern of the raw level-0 samples this thread converted
+    float vmin = 0.0f, vmax = 1.0f;  // range of the raw level-0 samples this thread converted
     // LANDING: which of this thread's 4-pixel position chunks lie in the image (outside it the tile holds the zero padding)
     unsigned inside_mask = 0u;
     if (LANDING) {
@@ -223,7 +246,7 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
       }
     }
     // row pass: column pair and first reduced row of this thread (ptid < ROW_THREADS)
-    const int rw_cp = ptid % ROW_CP, rw_a0 = 3 * (ptid / ROW_CP);
+    const int rw_cp = ptid % ROW_CP, rw_a0 = ROW_SEG * (ptid / ROW_CP);
 
     auto slot_of = [&](int i) { return s_lo + i + (i > 0 ? dup : 0); };
     // start staging the tile of iteration i
@@ -262,8 +285,14 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
         const unsigned raw = sRaw_u32 + (i & 1) * (TILE_FLOATS * 4) + 16 * ptid, lum = sL_u32 + lb * (TILE_FLOATS * 4) + 32 * ptid;
         const bool halo_inside = (ty0 >= 4) && (ty0 + TH + 4 <= h) && (tx0 >= 4) && (tx0 + TW + 4 <= w);
 #define FVVDP_EOTF_PASS(E)                                                                                                     \
-  _Pragma("unroll") for (int k = 0; k < NLD; ++k)                                                                              \
-    if (k < NLD - 1 || ptid + k * NPT < NPC) eotf_chunk<E>(raw + k * (NPT * 16), lum + k * (NPT * 32), halo_inside || ((inside_mask >> k) & 1u), p, vbits);
+  if (halo_inside) {                                                                                                           \
+    _Pragma("unroll") for (int k = 0; k < NLD; ++k)                                                                            \
+      if (k < NLD - 1 || ptid + k * NPT < NPC) eotf_chunk<E, true>(raw + k * (NPT * 16), lum + k * (NPT * 32), true, p, vmin, vmax); \
+  } else {                                                                                                                     \
+    _Pragma("unroll") for (int k = 0; k < NLD; ++k)                                                                            \
+      if (k < NLD - 1 || ptid + k * NPT < NPC)                                                                                 \
+        eotf_chunk<E, false>(raw + k * (NPT * 16), lum + k * (NPT * 32), (inside_mask >> k) & 1u, p, vmin, vmax);              \
+  }
         switch (p.eotf) {  // uniform; one specialised conversion loop per EOTF
           case FVVDP_B200_EOTF_NONE: FVVDP_EOTF_PASS(FVVDP_B200_EOTF_NONE) break;
           case FVVDP_B200_EOTF_SRGB: FVVDP_EOTF_PASS(FVVDP_B200_EOTF_SRGB) break;
@@ -287,7 +316,7 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
           ulonglong2 g0 = *reinterpret_cast<const ulonglong2*>(g), g1 = *reinterpret_cast<const ulonglong2*>(g + 2 * LW),
                      g2 = *reinterpret_cast<const ulonglong2*>(g + 4 * LW);
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
+          for (int j = 0; j < ROW_SEG; ++j) {
             const ulonglong2 g3 = *reinterpret_cast<const ulonglong2*>(g + (2 * j + 3) * (2 * LW)),
                              g4 = *reinterpret_cast<const ulonglong2*>(g + (2 * j + 4) * (2 * LW));
             ulonglong2 o;
@@ -297,7 +326,7 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
             g0 = g2; g1 = g3; g2 = g4;
           }
         } else {
-          for (int j = 0; j < 3; ++j) {
+          for (int j = 0; j < ROW_SEG; ++j) {
             const int a = rw_a0 + j;
             const int jc = min(max(jy0 - 1 + a, 0), h2 - 1);  // expand clamps the coarse index
             const float* g = col + (2 * (jc - jy0) + 2) * (2 * LW);
@@ -325,17 +354,19 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
       if (!LANDING) mbar_wait(bar_empty + 8 * lb, (lround & 1) ^ 1);  // sNc[lb] is free
       {
         float* gout = (p.Pn != nullptr && s >= s_lo + ((bz > 0) ? p.fl - 1 : 0)) ? p.Pn + (long long)s * p.Pn_slot_stride : nullptr;
-        float* nc = sNc + lb * (4 * NE);
+        float* nc = sNc + lb * (4 * NE) + 2 * ptid;
+        float* ring_o = sNr + 2 * ptid;  // this thread's elements: ptid + k * NPT
+        u64 ov[NCOL];
 #pragma unroll
         for (int k = 0; k < NCOL; ++k) {
+          ov[k] = 0ull;
           if (k < NCOL - 1 || cl_src[k] >= 0) {  // only the last round is partial
-            const int o = ptid + k * NPT;
             const float* v = sV + (cl_src[k] & 0xFFFFFFF);
             const ulonglong2 v01 = *reinterpret_cast<const ulonglong2*>(v), v23 = *reinterpret_cast<const ulonglong2*>(v + 4);
             const u64 v4 = *reinterpret_cast<const u64*>(v + 8);
-            u64 ov = tap5(v01.x, v01.y, v23.x, v23.y, v4);
+            ov[k] = tap5(v01.x, v01.y, v23.x, v23.y, v4);
             if (!cols_interior) {
-              float ot = lo_of(ov), orf = hi_of(ov);
+              float ot = lo_of(ov[k]), orf = hi_of(ov[k]);
               if (cl_src[k] & (1 << 28)) { ot += K1 * v[4] + K0 * v[6]; orf += K1 * v[5] + K0 * v[7]; }
               if (cl_src[k] & (2 << 28)) {
                 const float* e = sV + ((cl_src[k] & 0xFFFFFFF) / (2 * LW)) * (2 * LW) + 2 * (w - 1 - tx0 + 4);  // y[w-1] of this row
@@ -343,37 +374,54 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
                 ot += p.h_odd ? (K3 * e[0] + K4 * e[-2]) : K4 * e[0];
                 orf += p.h_odd ? (K3 * e[1] + K4 * e[-1]) : K4 * e[1];
               }
-              ov = pk(ot, orf);
+              ov[k] = pk(ot, orf);
             }
-            if (gout != nullptr && cl_g[k] >= 0) *reinterpret_cast<u64*>(gout + cl_g[k]) = ov;
-            float* ring_o = sNr + 2 * o;
-            if (first_dup) {
-#pragma unroll
-              for (int j = 0; j < RP; ++j) *reinterpret_cast<u64*>(ring_o + j * (2 * NE)) = ov;
-              for (int d = 1; d <= dup; ++d)
-                if (gout != nullptr && cl_g[k] >= 0) *reinterpret_cast<u64*>(gout + d * p.Pn_slot_stride + cl_g[k]) = ov;
-            } else {
-              if (emit) {
-                u64 r0, r1;
-                switch (rp) {
-#define FVVDP_CASE(J) case J: coarse_step<J>(ring_o, ov, p, r0, r1); break;
-                  FVVDP_CASE(0) FVVDP_CASE(1) FVVDP_CASE(2) FVVDP_CASE(3) FVVDP_CASE(4) FVVDP_CASE(5)
-                  default: coarse_step<6>(ring_o, ov, p, r0, r1); break;
-#undef FVVDP_CASE
-                }
-                *reinterpret_cast<u64*>(nc + 2 * o) = r0;
-                *reinterpret_cast<u64*>(nc + 2 * NE + 2 * o) = r1;
-              }
-              *reinterpret_cast<u64*>(ring_o + rp * (2 * NE)) = ov;
+            if (gout != nullptr && cl_g[k] >= 0) {
+              *reinterpret_cast<u64*>(gout + cl_g[k]) = ov[k];
+              if (first_dup)
+                for (int d = 1; d <= dup; ++d) *reinterpret_cast<u64*>(gout + d * p.Pn_slot_stride + cl_g[k]) = ov[k];
             }
           }
+        }
+        if (first_dup) {
+#pragma unroll
+          for (int k = 0; k < NCOL; ++k)
+            if (k < NCOL - 1 || cl_src[k] >= 0) {
+#pragma unroll
+              for (int j = 0; j < RP; ++j) *reinterpret_cast<u64*>(ring_o + k * (2 * NPT) + j * (2 * NE)) = ov[k];
+            }
+        } else {
+          if (emit) {
+            // one code version per ring position: the filter weights are uniform-register operands, loaded once for all rounds
+#define FVVDP_ROUNDS(J)                                                                       \
+  _Pragma("unroll") for (int k = 0; k < NCOL; ++k)                                            \
+    if (k < NCOL - 1 || cl_src[k] >= 0) {                                                     \
+      u64 r0, r1;                                                                             \
+      coarse_step<J>(ring_o + k * (2 * NPT), ov[k], p, r0, r1);                               \
+      *reinterpret_cast<u64*>(nc + k * (2 * NPT)) = r0;                                       \
+      *reinterpret_cast<u64*>(nc + 2 * NE + k * (2 * NPT)) = r1;                              \
+    }
+            switch (rp) {
+              case 0: FVVDP_ROUNDS(0) break;
+              case 1: FVVDP_ROUNDS(1) break;
+              case 2: FVVDP_ROUNDS(2) break;
+              case 3: FVVDP_ROUNDS(3) break;
+              case 4: FVVDP_ROUNDS(4) break;
+              case 5: FVVDP_ROUNDS(5) break;
+              default: FVVDP_ROUNDS(6) break;
+            }
+#undef FVVDP_ROUNDS
+          }
+#pragma unroll
+          for (int k = 0; k < NCOL; ++k)
+            if (k < NCOL - 1 || cl_src[k] >= 0) *reinterpret_cast<u64*>(ring_o + k * (2 * NPT) + rp * (2 * NE)) = ov[k];
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + 8 * lb);
       rp = (rp + 1 == RP) ? 0 : rp + 1;
     }
-    if (KIND != IN_PYRAMID_TMA && eotf_checks_range(p.eotf) && vbits > 0x3F800000u && p.flags) atomicOr(p.flags, 1u);
+    if (KIND != IN_PYRAMID_TMA && eotf_checks_range(p.eotf) && (vmin < 0.0f || vmax > 1.0f) && p.flags) atomicOr(p.flags, 1u);
     return;
   }
 
@@ -425,7 +473,7 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
     const int lb = i % NLB, lround = i / NLB;
     if (i == 1) rp = (s + p.ring_phase_ws) % RP;
     if (!LANDING) mbar_wait(bar0 + 8 * lb, lround & 1);   // the tile itself was written by TMA
-    mbar_wait(bar_full + 8 * lb, lround & 1);
+    mbar_wait_backoff(bar_full + 8 * lb, lround & 1);
     const float* sLb = sL + lb * TILE_FLOATS;
     u64 X[4];
     {

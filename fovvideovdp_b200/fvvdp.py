@@ -280,6 +280,11 @@ class fvvdp:
         if self.local_adapt != "gpyr" or self.contrast != "weber" or self.masking_model != "min_mutual_masking_perc_norm2" or self.pu_dilate != 0:
             raise RuntimeError("Unsupported metric configuration: the B200 core implements local_adapt='gpyr', contrast='weber', "
                                "masking_model='min_mutual_masking_perc_norm2', pu_dilate=0")
+        # the packaged CSF look-up tables were computed for one (csf_sigma, k_cm) pair; the reference keys its cache files on
+        # them (fvvdp.py:502-518) and fails when no file matches -- never score with the wrong sensitivity table
+        if abs(self.csf_sigma - config.CSF_LUT_KEY["csf_sigma"]) > 1e-6 or abs(self.k_cm - config.CSF_LUT_KEY["k_cm"]) > 1e-6:
+            raise RuntimeError("CSF look-up table for csf_sigma={}, k_cm={} not found (the packaged table is for csf_sigma={}, k_cm={})".format(
+                self.csf_sigma, self.k_cm, config.CSF_LUT_KEY["csf_sigma"], config.CSF_LUT_KEY["k_cm"]))
         self._drop_ctx()
 
     def set_display_model(self, display_name="standard_4k", display_photometry=None, display_geometry=None):
@@ -313,7 +318,7 @@ class fvvdp:
             self._ctx_key = key
         return self._ctx
 
-    def _make_config(self, W, H, n_levels, freqs, temp_ch, fl, F, spec, dtype, C, T):
+    def _make_config(self, W, H, n_levels, freqs, temp_ch, fl, F, spec, dtype, C, T, rgb2y):
         cfg = _native.Config()
         cfg.abi_version = _native.ABI_VERSION
         cfg.width, cfg.height, cfg.n_levels = W, H, n_levels
@@ -329,7 +334,7 @@ class fvvdp:
         cfg.gamma = spec.get("gamma", 2.2)
         cfg.L_min = spec.get("L_min", 0.0)
         cfg.L_max = spec.get("L_max", 0.0)
-        w = config.rgb2y(self.color_space) if C == 3 else [1.0, 0.0, 0.0]
+        w = rgb2y if C == 3 else [1.0, 0.0, 0.0]
         for i in range(3):
             cfg.rgb2y[i] = w[i]
         cfg.in_dtype, cfg.in_channels = _DTYPES[dtype], C
@@ -396,8 +401,11 @@ class fvvdp:
         if raw:
             C = 3 if vid_source.is_color else 1
             dtype = frames.dtype
+            # the RGB -> luminance weights are the SOURCE's (video_source.py:87,206), not the metric's colour space
+            rgb2y = tuple(float(v) for v in vid_source.color_to_luminance)
         else:
             spec, C, dtype = dict(kind="none"), 1, torch.float32
+            rgb2y = (1.0, 0.0, 0.0)
 
         # frames this process scores
         f_begin, f_end = 0, N_frames
@@ -417,9 +425,9 @@ class fvvdp:
 
         geo = self.display_geometry
         key = (width, height, n_levels, float(self.pix_per_deg), temp_ch, fl, F_bytes, tuple(sorted(spec.items())), dtype, C, T,
-               self.foveated, self.heatmap if self.do_heatmap else None, self.debug_taps, self.color_space,
+               self.foveated, self.heatmap if self.do_heatmap else None, self.debug_taps, rgb2y,
                (tuple(geo.display_size_m), geo.distance_m, geometry_is_stock(geo)) if self.foveated else None)
-        ctx = self._context(key, lambda: self._make_config(width, height, n_levels, freqs, temp_ch, fl, F, spec, dtype, C, T))
+        ctx = self._context(key, lambda: self._make_config(width, height, n_levels, freqs, temp_ch, fl, F, spec, dtype, C, T, rgb2y))
 
         stream = torch.cuda.current_stream(dev).cuda_stream
         # one buffer: the pooled energies and, behind them, the flag word -- one allocation, one device->host read

@@ -58,7 +58,8 @@ class pu_psnr:
                 T.record_stream(torch.cuda.current_stream(dev))
                 R.record_stream(torch.cuda.current_stream(dev))
             sq = acc.cpu().numpy()  # one device->host read
-        psnr = sum(20.0 * math.log10(self.peak / math.sqrt(float(s) / n)) for s in sq) / N_frames  # pupsnr.py:66-79
+        # pupsnr.py:66-79; identical frames (zero error) give +inf like the reference's torch arithmetic, not a ZeroDivisionError
+        psnr = sum((20.0 * math.log10(self.peak / math.sqrt(float(s) / n)) if s > 0 else math.inf) for s in sq) / N_frames
         return torch.tensor(psnr, dtype=torch.float32, device=dev), None
 
     def short_name(self):

@@ -28,8 +28,18 @@ def load_image_as_array(imgfile):
     except ImportError:
         pass
     if img is None:
+        ext = os.path.splitext(imgfile)[1].lower()
+        if ext in (".exr", ".hdr", ".dds"):
+            raise RuntimeError(f'"{imgfile}": {ext} images need an HDR-capable reader (OpenCV with OpenEXR, or imageio); none is available here')
         from PIL import Image
-        img = np.array(Image.open(imgfile))
+        im = Image.open(imgfile)
+        if im.mode in ("P", "PA", "LA", "1"):  # palette indices / grey+alpha are not pixel values
+            im = im.convert("RGB" if im.mode in ("P", "PA") else "L")
+        elif im.mode.startswith("I;16") or im.mode == "I":
+            pass  # 16-bit grey survives np.array()
+        img = np.array(im)
+        if im.mode == "I":
+            img = img.astype(np.uint16)
     if img.ndim == 3 and img.shape[2] > 3:
         logging.warning(f"Input image {imgfile} has more than 3 channels (alpha?). Ignoring the extra channels.")
         img = img[:, :, :3]
@@ -44,7 +54,7 @@ class fvvdp_video_source_file(fvvdp_video_source):
         assert os.path.isfile(test_fname), f'File does not exists: "{test_fname}"'
         assert os.path.isfile(reference_fname), f'File does not exists: "{reference_fname}"'
         ext_t, ext_r = os.path.splitext(test_fname)[1].lower(), os.path.splitext(reference_fname)[1].lower()
-        if ext_t in IMAGE_EXTENSIONS:
+        if ext_t in IMAGE_EXTENSIONS or ext_t in (".exr", ".hdr", ".dds"):
             assert ext_r in IMAGE_EXTENSIONS, "Test is an image, but reference is a video"
             if color_space_name == "auto":
                 color_space_name = "sRGB"
@@ -59,8 +69,20 @@ class fvvdp_video_source_file(fvvdp_video_source):
                                                       color_space_name=color_space_name, frames=frames, full_screen_resize=full_screen_resize,
                                                       resize_resolution=resize_resolution, verbose=verbose)
             else:
-                raise RuntimeError(f'"{test_fname}" needs the reference\'s ffmpeg reader (pyfvvdp.fvvdp_video_source_file); pass that '
-                                   "source to predict_video_source() or convert the clip to raw .yuv")
+                # any other container: the reference's own ffmpeg reader, when that package is installed (plumbing that stays
+                # with the reference); it hands luminance frames to the metric through get_*_frame()
+                ref_cls = None
+                try:
+                    import pyfvvdp
+                    ref_cls = getattr(pyfvvdp, "_reference_classes", {}).get("fvvdp_video_source_file") or pyfvvdp.fvvdp_video_source_file
+                except ImportError:
+                    pass
+                if ref_cls is None or ref_cls is fvvdp_video_source_file:
+                    raise RuntimeError(f'"{test_fname}" needs the reference\'s ffmpeg reader (pyfvvdp.fvvdp_video_source_file); pass that '
+                                       "source to predict_video_source() or convert the clip to raw .yuv")
+                self.vs = ref_cls(test_fname, reference_fname, display_photometry=display_photometry, color_space_name=color_space_name,
+                                  frames=frames, full_screen_resize=full_screen_resize, resize_resolution=resize_resolution, preload=preload,
+                                  ffmpeg_cc=ffmpeg_cc, verbose=verbose)
 
     def get_video_size(self):
         return self.vs.get_video_size()

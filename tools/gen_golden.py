@@ -6,6 +6,7 @@ CUDA path).  Inputs are analytic / seeded so only outputs (and small inputs) are
     python tools/gen_golden.py            # rewrites every fixture
     python tools/gen_golden.py widen      # only the fixtures of the widened surface (heat-map colour maps, custom geometry)
     python tools/gen_golden.py yuv        # only the raw .yuv video-source fixtures
+    python tools/gen_golden.py round2     # only the fixtures added in round 2 (GOG, 120 fps, colour-space mismatch, the 64-frame 4K bench clip)
 
 Large tap tensors are stored as strided sub-samples ([::SY, ::SX]) to keep the fixtures small.
 """
@@ -327,6 +328,37 @@ def gen_full_size_cases():
     save("full_4k_hdr_pq_foveated_9f", jod=float(q), Q_per_ch=st["Q_per_ch"], gaze=gaze)
 
 
+def gen_round2_cases():
+    """Fixtures added in round 2: the benchmark clip itself (64 frames of 3840x2160, BASELINE configs[2]), the GOG photometry
+    (fvvdp_display_model.py:253-279) with a gamma and with its sRGB branch, 120 fps (30-tap temporal window, fvvdp.py:228), and a
+    source whose colour space differs from the metric's (the source's RGB->Y weights apply, video_source.py:87,206)."""
+    from pyfvvdp.fvvdp_display_model import fvvdp_display_photo_gog
+    from pyfvvdp.video_source import fvvdp_video_source_array
+    t, r = synth_pair_numpy(8, 270, 480)
+    for name, gamma in (("gog_gamma", 2.4), ("gog_srgb", -1)):
+        dp = fvvdp_display_photo_gog(300.0, contrast=500, gamma=gamma, E_ambient=100, k_refl=0.005)
+        fv = pyfvvdp.fvvdp(display_name="standard_fhd", display_photometry=dp, device=CPU)
+        q, st = fv.predict(torch.tensor(t), torch.tensor(r), dim_order="BCFHW", frames_per_second=30)
+        save(f"video_{name}", jod=float(q), Q_per_ch=st["Q_per_ch"], gog=[300.0, 500.0, gamma, 100.0, 0.005])
+    for (N, H, W) in ((9, 135, 240), (40, 270, 480)):
+        t, r = synth_pair_numpy(N, H, W)
+        fv = pyfvvdp.fvvdp(display_name="standard_fhd", device=CPU)
+        q, st = fv.predict(torch.tensor(t), torch.tensor(r), dim_order="BCFHW", frames_per_second=120)
+        save(f"video_120fps_{N}x{H}x{W}", jod=float(q), Q_per_ch=st["Q_per_ch"])
+    rng = np.random.default_rng(5)
+    t8 = rng.integers(0, 256, (6, 96, 160, 3), dtype=np.uint8)
+    r8 = np.clip(t8.astype(np.int32) + rng.integers(-12, 13, t8.shape), 0, 255).astype(np.uint8)
+    fv = pyfvvdp.fvvdp(display_name="standard_4k", device=CPU)  # metric left at color_space="sRGB"
+    vs = fvvdp_video_source_array(torch.tensor(t8), torch.tensor(r8), 30, dim_order="FHWC", display_photometry=fv.display_photometry,
+                                  color_space_name="BT.2020")
+    q, st = fv.predict_video_source(vs)
+    save("video_source_bt2020_metric_srgb", jod=float(q), Q_per_ch=st["Q_per_ch"], test=t8, ref=r8)
+    t, r = synth_pair_numpy(64, 2160, 3840)
+    fv = pyfvvdp.fvvdp(display_name="standard_4k", device=CPU)
+    q, st = fv.predict(torch.tensor(t), torch.tensor(r), dim_order="BCFHW", frames_per_second=30)
+    save("full_4k_64f", jod=float(q), Q_per_ch=st["Q_per_ch"], rho_band=st["rho_band"])
+
+
 def gen_pu_psnr_cases():
     """PU21-PSNR through the reference's pu_psnr.predict_video_source (pupsnr.py:52-79) with its array video source."""
     from pyfvvdp.video_source import fvvdp_video_source_array
@@ -382,6 +414,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "full":
         gen_full_size_cases()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":
+        gen_round2_cases()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "pupsnr":
         gen_pu_psnr_cases()
         sys.exit(0)
@@ -395,3 +430,4 @@ if __name__ == "__main__":
     gen_yuv_cases()
     gen_pu_psnr_cases()
     gen_full_size_cases()
+    gen_round2_cases()
