@@ -182,13 +182,13 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
   int hh = cfg->height, ww = cfg->width;
   {
     // A/B switches, read once: FVVDP_B200_PATH=v1 (general kernels) | fused (no warp-specialised kernel);
-    // FVVDP_B200_WS_LEVELS=n (warp-specialised kernel on levels < n only)
+    // FVVDP_B200_WS_LEVELS=n (warp-specialised kernel on levels < n; default 1: on the pyramid levels it only ties the fused kernel)
     const char* force = getenv("FVVDP_B200_PATH");
     c->fused = cfg->filter_len <= fused::MAXRING && !(force && strcmp(force, "v1") == 0);
     const bool ws_ok = c->fused && !(force && strcmp(force, "fused") == 0) && cfg->temp_ch == 2 && cfg->filter_len >= 2 &&
                        cfg->filter_len <= ws::RP + 1 && !cfg->want_taps && !cfg->want_dmap;
     const char* wl = getenv("FVVDP_B200_WS_LEVELS");
-    c->ws_max_level = ws_ok ? (wl ? atoi(wl) - 1 : FVVDP_B200_MAX_LEVELS) : -1;
+    c->ws_max_level = ws_ok ? (wl ? atoi(wl) - 1 : 0) : -1;
     c->no_dup_skip = getenv("FVVDP_B200_NO_DUP_SKIP") != nullptr;
   }
   const int tile_w = c->fused ? fused::TW : TW, tile_h = c->fused ? fused::TH : TH;
@@ -520,6 +520,14 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
     bp.y0 = ctx->ax.x0[1]; bp.inv_dy = ctx->ax.inv_dx[1]; bp.lg_y_hi = log2f(cfg.csf_Y_range[1]);
     bp.mask_p = cfg.mask_p; bp.mask_q[0] = cfg.mask_q[0]; bp.mask_q[1] = cfg.mask_q[1];
     bp.log2_mask_c = log2f(cfg.mask_c_mul); bp.beta = cfg.beta; bp.w_transient = cfg.w_transient;
+    {
+      auto pack2 = [](float lo, float hi) { uint32_t a, b; memcpy(&a, &lo, 4); memcpy(&b, &hi, 4); return ((unsigned long long)b << 32) | a; };
+      bp.m_q = pack2(cfg.mask_q[0], cfg.mask_q[1]);
+      bp.m_qlmc = pack2(cfg.mask_q[0] * bp.log2_mask_c, cfg.mask_q[1] * bp.log2_mask_c);
+      bp.m_bp = pack2(cfg.beta * cfg.mask_p, cfg.beta * cfg.mask_p);
+      bp.m_nbeta = pack2(-cfg.beta, -cfg.beta);
+      bp.m_cap = cfg.beta * 13.287712379549449f;
+    }
     bp.ax = ctx->ax; bp.lut4 = ctx->lut4; bp.log2_sens_mul = ctx->log2_sens_mul;
     if (cfg.foveated) {
       const double delta = (1.0 / cfg.ppd_centre) / 2.0 * M_PI / 180.0;

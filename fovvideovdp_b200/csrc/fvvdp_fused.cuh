@@ -30,6 +30,10 @@
 
 #include "fvvdp_common.cuh"
 
+#ifndef FVVDP_WAIT_HINT_NS
+#define FVVDP_WAIT_HINT_NS 20000
+#endif
+
 namespace fvvdp {
 namespace fused {
 
@@ -91,6 +95,9 @@ struct BandParams {
   float log2_m;                               // log2(band multiplier), fvvdp_lpyr_dec.py:57-63
   float band_mul;
   float mask_p, mask_q[2], log2_mask_c, beta, w_transient;
+  // the same constants as (sustained, transient) pairs for the packed masking maths of the warp-specialised kernel:
+  u64 m_q, m_qlmc, m_bp, m_nbeta;             // (q0, q1); (q0, q1) * log2 c; (beta p, beta p); (-beta, -beta)
+  float m_cap;                                // beta * log2(1e4)
   // foveated
   CsfAxes ax;
   const float4* lut4;                         // [rho][ecc][Y] (t0, dt0, t1, dt1): log2(S * sens_mul) of both temporal channels + step to Y+1
@@ -173,13 +180,15 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  // try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires) instead of
+  // spinning through the issue slots of the warps that have work
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "FVVDP_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra FVVDP_DONE;\n\t"
       "bra FVVDP_WAIT;\n\t"
-      "FVVDP_DONE:\n\t}" ::"r"(bar), "r"(parity)
+      "FVVDP_DONE:\n\t}" ::"r"(bar), "r"(parity), "r"(FVVDP_WAIT_HINT_NS)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2) {

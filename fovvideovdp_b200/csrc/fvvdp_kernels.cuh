@@ -737,13 +737,14 @@ __device__ __forceinline__ float pu_encode(float Y, const PuParams& q) {
   Y = fminf(fmaxf(Y, q.L_min), q.L_max);
   const float yp = fast_exp2(q.p[3] * fast_log2(Y));
   const float r = (q.p[0] + q.p[1] * yp) / (1.0f + q.p[2] * yp);
-  return q.p[6] * (fast_exp2(q.p[4] * fast_log2(r)) - q.p[5]);
+  return fast_exp2(q.p[4] * fast_log2(r));  // PU21 = p6 * (this - p5): the callers work on differences, where p5 cancels
 }
 __global__ void __launch_bounds__(256) pu_sqerr_kernel(const float* __restrict__ t, const float* __restrict__ r, long long n, PuParams q,
                                                        double* __restrict__ acc) {
   float s = 0.0f;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += 256ll * gridDim.x) {
-    const float d = pu_encode(__ldg(t + i), q) - pu_encode(__ldg(r + i), q);
+    // p6 * ((a - p5) - (b - p5)) = p6 * (a - b): exactly 0 for identical frames (a fused multiply-add of the two scaled terms is not)
+    const float d = q.p[6] * (pu_encode(__ldg(t + i), q) - pu_encode(__ldg(r + i), q));
     s = fmaf(d, d, s);
   }
   double v = (double)s;

@@ -35,10 +35,28 @@ using fused::IN_PYRAMID_TMA; using fused::IN_LEVEL0_TMA;
 
 constexpr int NH = TH / 2 + 2, NW = TW / 2 + 2; // reduced tile with 1-px halo: origin (jy0-1, jx0-1)
 constexpr int NE = NH * NW;                     // 612
+#ifndef WS_BACKOFF
+#define WS_BACKOFF 0    // ns a consumer warp sleeps between two looks at a barrier that is not ready (0: hardware-suspended try_wait only)
+#endif
+// Warp split and registers per thread after setmaxnreg (the CTA's pool is NT x (65536 / NT rounded down to 8)).  Each
+// translation unit instantiates ONE input kind, so the split is chosen per kind:
+//   level 0 (EOTF pass in the producers): 12 producer warps, 512 * 88 + 384 * 48 <= 896 * 72
+//   pyramid levels (no EOTF pass):         8 producer warps, 512 * 96 + 256 * 48 = 768 * 80
+#if defined(WS_KIND) && WS_KIND == 2 && defined(WS2_NPW)   // experiment builds: override for the pyramid-level unit only
+#define WS_NPW WS2_NPW
+#define WS_CREGS WS2_CREGS
+#define WS_PREGS WS2_PREGS
+#endif
 #ifndef WS_NPW
+#if defined(WS_KIND) && WS_KIND == 2
 #define WS_NPW 8
 #define WS_CREGS 96
 #define WS_PREGS 48
+#else
+#define WS_NPW 12
+#define WS_CREGS 88
+#define WS_PREGS 48
+#endif
 #endif
 constexpr int NCW = 16, NPW = WS_NPW;           // consumer / producer warps
 constexpr int NCT = NCW * 32, NPT = NPW * 32, NT = NCT + NPT;
@@ -53,17 +71,20 @@ constexpr int NCOL = (NE + NPT - 1) / NPT;      // 3
 constexpr int PLANE = LH * LW;                  // one stream of a landing buffer (floats)
 constexpr int TILE_FLOATS = 2 * PLANE;          // one staged tile, both streams (23040 bytes)
 constexpr int ROW_CP = LW / 2;                  // row pass: column pairs (36) x segments of ROW_SEG reduced rows
-constexpr int ROW_SEG = NPW >= 12 ? 2 : 3;
+constexpr int ROW_SEG = NPW >= 12 ? 2 : (NPW >= 8 ? 3 : 6);   // 324 / 216 / 108 threads
 constexpr int ROW_THREADS = ROW_CP * (NH / ROW_SEG);  // 216 / 324
 
 template <int KIND, bool FOV>
 struct Layout {
   static constexpr bool LANDING = KIND == IN_LEVEL0_TMA;     // raw planes land first, the EOTF pass interleaves them
-  static constexpr int NLB = (LANDING && FOV) ? 2 : 3;       // luminance / filtered-reduced-tile buffers (frames in flight between the roles)
+  // luminance / filtered-reduced-tile buffers (frames in flight between the roles).  The pyramid levels stage with TMA straight
+  // into these buffers, AHEAD = NLB - 2 frames ahead: the buffer that is refilled was released two iterations ago, so the
+  // thread that issues the copies never waits for the consumers
+  static constexpr int NLB = LANDING ? (FOV ? 2 : 3) : 4;
+  static constexpr int AHEAD = LANDING ? 2 : NLB - 2;
   static constexpr int oL = 0;                               // [NLB][LH][LW][2]
   static constexpr int oRaw = oL + NLB * TILE_FLOATS;        // LANDING: [2][2 streams][LH][LW]
-  static constexpr int NV = LANDING ? 1 : 2;                 // row-reduced tiles: without the EOTF pass (and its barrier) the row pass of the
-                                                             //   next frame may start while slower warps are still in this frame's column pass
+  static constexpr int NV = 2;                               // row-reduced tiles: the column pass of frame i-1 overlaps the row pass of frame i
   static constexpr int oV = oRaw + (LANDING ? 2 * TILE_FLOATS : 0);  // [NV][NH][LW][2] row-reduced
   static constexpr int oNr = oV + NV * 2 * NH * LW;          // [RP][NE][2] ring of reduced tiles
   static constexpr int oNc = oNr + RP * 2 * NE;              // [NLB][2][NE][2] temporally filtered reduced tiles
@@ -79,7 +100,7 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar) {
 }
 // wait with back-off: a warp that finds the barrier not ready yet sleeps instead of competing for issue slots
 __device__ __forceinline__ void mbar_wait_backoff(unsigned bar, unsigned parity) {
-#ifdef WS_BACKOFF
+#if WS_BACKOFF > 0
   unsigned done;
   asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   while (!done) {
@@ -101,11 +122,14 @@ __device__ __forceinline__ void eotf_chunk(unsigned raw, unsigned lum, bool insi
   const float4 a = lds128(raw), b = lds128(raw + PLANE * 4);
   float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
   if (eotf_checks_range(EOTF)) {
+#ifdef WS_NO_RANGE
+#else
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
       vmin = fminf(fminf(vmin, x[j]), x[j + 1]);
       vmax = fmaxf(fmaxf(vmax, x[j]), x[j + 1]);
     }
+#endif
   }
   eotf8<EOTF>(x, p);
   if (!INSIDE && !inside) {
@@ -168,7 +192,8 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
   float* sTab = smem + LY::oTab;
   float* sRed = smem + LY::oRed;
   float4* sFov = reinterpret_cast<float4*>(smem + LY::oFov);
-  __shared__ __align__(8) u64 bars[3 + 2 * 3];  // [0..2] tile landed (TMA), [3..5] full (producers -> consumers), [6..8] empty
+  __shared__ __align__(8) u64 bars[4 + 2 * 4 + 4];  // [0..3] tile landed (TMA), [4..7] full (producers -> consumers), [8..11] empty,
+                                                    // [12..13] EOTF pass done, [14..15] row pass done (among the producer warps)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int bx, by, bz;  // read once through volatile asm (see fused::band_kernel)
@@ -187,24 +212,30 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
   const int n_iter = s_hi - s_lo - dup;
   unsigned bar0 = smem_u32(&bars[0]), sL_u32 = smem_u32(sL), sRaw_u32 = smem_u32(smem + LY::oRaw);
   asm volatile("" : "+r"(bar0), "+r"(sL_u32), "+r"(sRaw_u32));
-  const unsigned bar_full = bar0 + 24, bar_empty = bar0 + 48;
+  const unsigned bar_full = bar0 + 32, bar_empty = bar0 + 64, bar_conv = bar0 + 96, bar_row = bar0 + 112;
   // ring position of the first slot (the position follows the frame's index in the clip), advanced as the slots go by
   int rp_first = (s_lo + p.ring_phase_ws) % RP;
 
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(bar0 + 8 * i, 1);
       mbar_init(bar_full + 8 * i, NPW);
       mbar_init(bar_empty + 8 * i, NCW);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_conv + 8 * i, NPW);
+      mbar_init(bar_row + 8 * i, NPW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 32) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(p.cell) + 2 * tid);
     const float4 b = __ldg(reinterpret_cast<const float4*>(p.cell) + 2 * tid + 1);
-    reinterpret_cast<float4*>(sTab)[2 * tid] = a;
-    reinterpret_cast<float4*>(sTab)[2 * tid + 1] = b;
+    // p.cell holds {Y_log, 1/step, t0, dt0, t1, dt1, 0, 0}; here the two channels' entries and steps sit side by side
+    reinterpret_cast<float4*>(sTab)[2 * tid] = make_float4(a.x, a.y, 0.0f, 0.0f);
+    reinterpret_cast<float4*>(sTab)[2 * tid + 1] = make_float4(a.z, b.x, a.w, b.y);
   }
   for (int i = tid; i < RP * 2 * NE; i += NT) sNr[i] = 0.0f;  // window positions that are never loaded must hold finite values
   __syncthreads();
@@ -249,8 +280,8 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
     const int rw_cp = ptid % ROW_CP, rw_a0 = ROW_SEG * (ptid / ROW_CP);
 
     auto slot_of = [&](int i) { return s_lo + i + (i > 0 ? dup : 0); };
-    // start staging the tile of iteration i
-    auto issue_load = [&](int i) {
+    // start staging the tile of iteration i (lb = i mod NLB)
+    auto issue_load = [&](int i, int lb) {
       const int slot = slot_of(i);
       if (LANDING) {
         const int rb = i & 1;
@@ -259,31 +290,89 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
         tma_load_3d(dst, &p.tmap_ws[0], bar, tx0 - 4, ty0 - 4, (int)p.slot_frame[0][slot]);
         tma_load_3d(dst + PLANE * 4, &p.tmap_ws[1], bar, tx0 - 4, ty0 - 4, (int)p.slot_frame[1][slot]);
       } else {
-        const int lb = i % NLB;
         const unsigned bar = bar0 + 8 * lb;
         mbar_expect_tx(bar, TILE_FLOATS * 4);
         tma_load_3d(sL_u32 + lb * (TILE_FLOATS * 4), &p.tmap_ws[0], bar, 2 * (tx0 - 4), ty0 - 4, slot);
       }
     };
     if (ptid == 0) {
-      const int ahead = LANDING ? 2 : NLB - 1;
-      for (int i = 0; i < ahead && i < n_iter; ++i) issue_load(i);
+      for (int i = 0; i < LY::AHEAD && i < n_iter; ++i) issue_load(i, i);
     }
+    const bool halo_inside = (ty0 >= 4) && (ty0 + TH + 4 <= h) && (tx0 >= 4) && (tx0 + TW + 4 <= w);
 
-    int rp = rp_first;
+    // ---- stage C of iteration j: reduce, columns -> ring position rp (+ next level out), then the temporal filters of the
+    //      same elements (this thread's own: no barrier in between) -> sNc[lb]; hand the frame to the consumers
+    auto stage_c = [&](int j, int lb, unsigned lpar, int rp) {
+      const int s = slot_of(j);
+      const bool first_dup = (j == 0) && dup > 0;
+      const bool emit = s >= f_lo + p.fl - 1;
+      mbar_wait(bar_row + 8 * (j & 1), (j >> 1) & 1);                // every warp has finished the row pass of iteration j
+      if (!LANDING) mbar_wait(bar_empty + 8 * lb, lpar ^ 1);          // sNc[lb] is free (LANDING: waited for before the EOTF pass)
+      const float* sV = sV0 + (j & 1) * (2 * NH * LW);
+      float* gout = (p.Pn != nullptr && s >= s_lo + ((bz > 0) ? p.fl - 1 : 0)) ? p.Pn + (long long)s * p.Pn_slot_stride : nullptr;
+      float* nc = sNc + lb * (4 * NE);
+#pragma unroll
+      for (int k = 0; k < NCOL; ++k) {
+        if (k < NCOL - 1 || cl_src[k] >= 0) {  // only the last round is partial
+          const int o = ptid + k * NPT;
+          const float* v = sV + (cl_src[k] & 0xFFFFFFF);
+          const ulonglong2 v01 = *reinterpret_cast<const ulonglong2*>(v), v23 = *reinterpret_cast<const ulonglong2*>(v + 4);
+          const u64 v4 = *reinterpret_cast<const u64*>(v + 8);
+          u64 ov = tap5(v01.x, v01.y, v23.x, v23.y, v4);
+          if (!cols_interior) {
+            float ot = lo_of(ov), orf = hi_of(ov);
+            if (cl_src[k] & (1 << 28)) { ot += K1 * v[4] + K0 * v[6]; orf += K1 * v[5] + K0 * v[7]; }
+            if (cl_src[k] & (2 << 28)) {
+              const float* e = sV + ((cl_src[k] & 0xFFFFFFF) / (2 * LW)) * (2 * LW) + 2 * (w - 1 - tx0 + 4);  // y[w-1] of this row
+              // keyed on the ROW count, fvvdp_lpyr_dec.py:202
+              ot += p.h_odd ? (K3 * e[0] + K4 * e[-2]) : K4 * e[0];
+              orf += p.h_odd ? (K3 * e[1] + K4 * e[-1]) : K4 * e[1];
+            }
+            ov = pk(ot, orf);
+          }
+          if (gout != nullptr && cl_g[k] >= 0) *reinterpret_cast<u64*>(gout + cl_g[k]) = ov;
+          float* ring_o = sNr + 2 * o;
+          if (first_dup) {
+#pragma unroll
+            for (int q = 0; q < RP; ++q) *reinterpret_cast<u64*>(ring_o + q * (2 * NE)) = ov;
+            for (int d = 1; d <= dup; ++d)
+              if (gout != nullptr && cl_g[k] >= 0) *reinterpret_cast<u64*>(gout + d * p.Pn_slot_stride + cl_g[k]) = ov;
+          } else {
+            if (emit) {
+              u64 r0, r1;
+              switch (rp) {
+#define FVVDP_CASE(J) case J: coarse_step<J>(ring_o, ov, p, r0, r1); break;
+                FVVDP_CASE(0) FVVDP_CASE(1) FVVDP_CASE(2) FVVDP_CASE(3) FVVDP_CASE(4) FVVDP_CASE(5)
+                default: coarse_step<6>(ring_o, ov, p, r0, r1); break;
+#undef FVVDP_CASE
+              }
+              *reinterpret_cast<u64*>(nc + 2 * o) = r0;
+              *reinterpret_cast<u64*>(nc + 2 * NE + 2 * o) = r1;
+            }
+            *reinterpret_cast<u64*>(ring_o + rp * (2 * NE)) = ov;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * lb);
+    };
+
+    // The producers' own stages are software-pipelined: the column pass and filters of frame i-1 sit between the EOTF pass of
+    // frame i and the row pass of frame i, and the two hand-offs between the stages (EOTF -> rows, rows -> columns) are split
+    // arrive / wait pairs on mbarriers, so a warp that is early at one of them has the other stage's work to do meanwhile.
+    int lb = 0, rp = rp_first;          // luminance buffer / ring position of iteration i
+    unsigned lpar = 0;                  // phase parity of the full / empty barriers of buffer lb in iteration i
+    int plb = 0, prp = 0;               // the same of iteration i - 1
+    unsigned plpar = 0;
     for (int i = 0; i < n_iter; ++i) {
-      const int s = slot_of(i);
-      const int lb = i % NLB, lround = i / NLB;
       const float* sLb = sL + lb * TILE_FLOATS;
-      float* sV = sV0 + (LY::NV == 2 ? (i & 1) * (2 * NH * LW) : 0);
-      const bool first_dup = (i == 0) && dup > 0;
-      if (i == 1) rp = (s + p.ring_phase_ws) % RP;
-      // ---- stage A: luminance tile of slot s complete in buffer lb
+      float* sV = sV0 + (i & 1) * (2 * NH * LW);
+      if (i == 1) rp = (slot_of(1) + p.ring_phase_ws) % RP;
+      // ---- stage A: display EOTF, landing buffer -> luminance tile of iteration i
       if (LANDING) {
-        mbar_wait(bar_empty + 8 * lb, (lround & 1) ^ 1);   // the consumers are done with the frame that used this buffer
+        mbar_wait(bar_empty + 8 * lb, lpar ^ 1);   // the consumers are done with the frame that used this buffer
         mbar_wait(bar0 + 8 * (i & 1), (i >> 1) & 1);
         const unsigned raw = sRaw_u32 + (i & 1) * (TILE_FLOATS * 4) + 16 * ptid, lum = sL_u32 + lb * (TILE_FLOATS * 4) + 32 * ptid;
-        const bool halo_inside = (ty0 >= 4) && (ty0 + TH + 4 <= h) && (tx0 >= 4) && (tx0 + TW + 4 <= w);
 #define FVVDP_EOTF_PASS(E)                                                                                                     \
   if (halo_inside) {                                                                                                           \
     _Pragma("unroll") for (int k = 0; k < NLD; ++k)                                                                            \
@@ -302,12 +391,18 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
           default: FVVDP_EOTF_PASS(FVVDP_B200_EOTF_ABSOLUTE) break;
         }
 #undef FVVDP_EOTF_PASS
-        named_bar_sync<1, NPT>();  // luminance tile complete; the landing buffer may be refilled
-        if (ptid == 0 && i + 2 < n_iter) issue_load(i + 2);
-      } else {
-        mbar_wait(bar0 + 8 * lb, lround & 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_conv + 8 * (i & 1));
       }
+      // ---- stage C of the previous iteration
+      if (i > 0) stage_c(i - 1, plb, plpar, prp);
       // ---- stage B: reduce, rows: sV[a][c] = sum_k K[k] L[2a+k][c] (zero padding + edge terms)
+      if (LANDING) {
+        mbar_wait(bar_conv + 8 * (i & 1), (i >> 1) & 1);   // luminance tile complete; the landing buffer may be refilled
+        if (ptid == 0 && i + 2 < n_iter) issue_load(i + 2, 0);
+      } else {
+        mbar_wait(bar0 + 8 * lb, lpar);
+      }
       if (ptid < ROW_THREADS) {
         const float* col = sLb + 4 * rw_cp;   // two adjacent columns, (test, ref) pairs
         float* out = sV + 4 * rw_cp;
@@ -343,84 +438,20 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
           }
         }
       }
-      named_bar_sync<1, NPT>();  // row-reduced tile complete (and every reader of the previous one is past its column pass)
-      if (!LANDING && ptid == 0 && i + NLB - 1 < n_iter) {
-        // the buffer of iteration i-1 takes the tile of iteration i+NLB-1 once the consumers have released it
-        if (i >= 1) mbar_wait(bar_empty + 8 * ((i - 1) % NLB), ((i - 1) / NLB) & 1);
-        issue_load(i + NLB - 1);
-      }
-      // ---- stage C: reduce, columns -> ring position rp (+ next level out), then the temporal filters of the same elements
-      const bool emit = s >= f_lo + p.fl - 1;
-      if (!LANDING) mbar_wait(bar_empty + 8 * lb, (lround & 1) ^ 1);  // sNc[lb] is free
-      {
-        float* gout = (p.Pn != nullptr && s >= s_lo + ((bz > 0) ? p.fl - 1 : 0)) ? p.Pn + (long long)s * p.Pn_slot_stride : nullptr;
-        float* nc = sNc + lb * (4 * NE) + 2 * ptid;
-        float* ring_o = sNr + 2 * ptid;  // this thread's elements: ptid + k * NPT
-        u64 ov[NCOL];
-#pragma unroll
-        for (int k = 0; k < NCOL; ++k) {
-          ov[k] = 0ull;
-          if (k < NCOL - 1 || cl_src[k] >= 0) {  // only the last round is partial
-            const float* v = sV + (cl_src[k] & 0xFFFFFFF);
-            const ulonglong2 v01 = *reinterpret_cast<const ulonglong2*>(v), v23 = *reinterpret_cast<const ulonglong2*>(v + 4);
-            const u64 v4 = *reinterpret_cast<const u64*>(v + 8);
-            ov[k] = tap5(v01.x, v01.y, v23.x, v23.y, v4);
-            if (!cols_interior) {
-              float ot = lo_of(ov[k]), orf = hi_of(ov[k]);
-              if (cl_src[k] & (1 << 28)) { ot += K1 * v[4] + K0 * v[6]; orf += K1 * v[5] + K0 * v[7]; }
-              if (cl_src[k] & (2 << 28)) {
-                const float* e = sV + ((cl_src[k] & 0xFFFFFFF) / (2 * LW)) * (2 * LW) + 2 * (w - 1 - tx0 + 4);  // y[w-1] of this row
-                // keyed on the ROW count, fvvdp_lpyr_dec.py:202
-                ot += p.h_odd ? (K3 * e[0] + K4 * e[-2]) : K4 * e[0];
-                orf += p.h_odd ? (K3 * e[1] + K4 * e[-1]) : K4 * e[1];
-              }
-              ov[k] = pk(ot, orf);
-            }
-            if (gout != nullptr && cl_g[k] >= 0) {
-              *reinterpret_cast<u64*>(gout + cl_g[k]) = ov[k];
-              if (first_dup)
-                for (int d = 1; d <= dup; ++d) *reinterpret_cast<u64*>(gout + d * p.Pn_slot_stride + cl_g[k]) = ov[k];
-            }
-          }
-        }
-        if (first_dup) {
-#pragma unroll
-          for (int k = 0; k < NCOL; ++k)
-            if (k < NCOL - 1 || cl_src[k] >= 0) {
-#pragma unroll
-              for (int j = 0; j < RP; ++j) *reinterpret_cast<u64*>(ring_o + k * (2 * NPT) + j * (2 * NE)) = ov[k];
-            }
-        } else {
-          if (emit) {
-            // one code version per ring position: the filter weights are uniform-register operands, loaded once for all rounds
-#define FVVDP_ROUNDS(J)                                                                       \
-  _Pragma("unroll") for (int k = 0; k < NCOL; ++k)                                            \
-    if (k < NCOL - 1 || cl_src[k] >= 0) {                                                     \
-      u64 r0, r1;                                                                             \
-      coarse_step<J>(ring_o + k * (2 * NPT), ov[k], p, r0, r1);                               \
-      *reinterpret_cast<u64*>(nc + k * (2 * NPT)) = r0;                                       \
-      *reinterpret_cast<u64*>(nc + 2 * NE + k * (2 * NPT)) = r1;                              \
-    }
-            switch (rp) {
-              case 0: FVVDP_ROUNDS(0) break;
-              case 1: FVVDP_ROUNDS(1) break;
-              case 2: FVVDP_ROUNDS(2) break;
-              case 3: FVVDP_ROUNDS(3) break;
-              case 4: FVVDP_ROUNDS(4) break;
-              case 5: FVVDP_ROUNDS(5) break;
-              default: FVVDP_ROUNDS(6) break;
-            }
-#undef FVVDP_ROUNDS
-          }
-#pragma unroll
-          for (int k = 0; k < NCOL; ++k)
-            if (k < NCOL - 1 || cl_src[k] >= 0) *reinterpret_cast<u64*>(ring_o + k * (2 * NPT) + rp * (2 * NE)) = ov[k];
-        }
-      }
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full + 8 * lb);
+      if (lane == 0) mbar_arrive(bar_row + 8 * (i & 1));
+      if (!LANDING && ptid == 0 && i + LY::AHEAD < n_iter) {
+        // the tile of iteration i + AHEAD goes into the buffer of iteration i - 2: every warp is past the row pass of that
+        // iteration (stage C above waited for the one after it), and the consumers released it long ago (the wait is a formality)
+        const int tb = (lb + LY::AHEAD) % NLB;
+        if (i >= 2) mbar_wait(bar_empty + 8 * tb, (lb + LY::AHEAD >= NLB) ? lpar : (lpar ^ 1u));
+        issue_load(i + LY::AHEAD, tb);
+      }
+      plb = lb; plpar = lpar; prp = rp;
+      if (++lb == NLB) { lb = 0; lpar ^= 1u; }
       rp = (rp + 1 == RP) ? 0 : rp + 1;
     }
+    stage_c(n_iter - 1, plb, plpar, prp);
     if (KIND != IN_PYRAMID_TMA && eotf_checks_range(p.eotf) && (vmin < 0.0f || vmax > 1.0f) && p.flags) atomicOr(p.flags, 1u);
     return;
   }
@@ -467,13 +498,24 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
 #pragma unroll
     for (int e = 0; e < 4; ++e) ring[k][e] = 0ull;
 
-  int rp = rp_first;
-  for (int i = 0; i < n_iter; ++i) {
+  // per-frame partial sums: one warp-shuffle butterfly per frame, one pass over the warps at the end.  The two channel sums
+  // share the butterfly: after the first exchange the lower half-warp carries channel 0, the upper half channel 1.
+  u64 pend2 = 0ull;
+  int pend_row = -1;
+  auto warp_sums = [&](u64 a2, int row) {
+    const bool up = lane >= 16;
+    float v = (up ? hi_of(a2) : lo_of(a2)) + __shfl_xor_sync(0xffffffffu, up ? lo_of(a2) : hi_of(a2), 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((lane & 15) == 0) sRed[(row * 2 + (up ? 1 : 0)) * NCW + warp] = v;
+  };
+  int rp = rp_first, lb = 0;
+  unsigned lpar = 0;
+  for (int i = 0; i < n_iter; ++i, lpar ^= (lb + 1 == NLB ? 1u : 0u), lb = (lb + 1 == NLB ? 0 : lb + 1)) {
     const int s = s_lo + i + (i > 0 ? dup : 0);
-    const int lb = i % NLB, lround = i / NLB;
     if (i == 1) rp = (s + p.ring_phase_ws) % RP;
-    if (!LANDING) mbar_wait(bar0 + 8 * lb, lround & 1);   // the tile itself was written by TMA
-    mbar_wait_backoff(bar_full + 8 * lb, lround & 1);
+    if (!LANDING) mbar_wait(bar0 + 8 * lb, lpar);   // the tile itself was written by TMA
+    mbar_wait_backoff(bar_full + 8 * lb, lpar);
     const float* sLb = sL + lb * TILE_FLOATS;
     u64 X[4];
     {
@@ -507,6 +549,7 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
     }
     rp = (rp + 1 == RP) ? 0 : rp + 1;
     const int fi = s - (p.fl - 1);  // output frame
+    if (pend_row >= 0) warp_sums(pend2, pend_row);  // the previous frame's sums (independent of everything around it)
 
     // ---- expand of the filtered coarse tile (both temporal channels) -> bands; then the buffers go back to the producers
     const u64 c01 = pk(0.1f, 0.1f), c08 = pk(0.8f, 0.8f), c05 = pk(0.5f, 0.5f), cm1 = pk(-1.0f, -1.0f);
@@ -536,82 +579,75 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty + 8 * lb);
+    if (!tile_full) {  // pixels outside the image: a zero band gives log2|T' - R'| = -inf and D^beta = 0
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (!valid[e]) { Bp[0][e] = 0ull; Bp[1][e] = 0ull; }
+    }
 
-    // ---- contrast, CSF, masking, pooling ----
-    float acc[2] = {0.0f, 0.0f};
-    float lgL[4], fj[4];
-    int cj[4];
-    float lsf[2][4];  // FOV: log2 S per temporal channel
+    // ---- contrast, CSF, masking, pooling.  Everything that is the same formula for the two temporal channels runs on
+    //      (sustained, transient) pairs; with S' = S * sensitivity_correction, m = band multiplier, c = 10^mask_c:
+    //        base   = log2 S' + log2 m - log2 L_bkg
+    //        log2 |T' - R'| = log2 |bT - bR| + base,   log2 M = log2 min(|bT|, |bR|) + base + log2 c      (fvvdp.py:583-588)
+    //        beta log2 D = beta p log2|T' - R'| - beta log2(1 + M^q), capped at beta log2 1e4              (:593-595)
+    u64 acc2 = 0ull;
 #pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-      float B[2][4];
+    for (int e = 0; e < 4; ++e) {
+      const float lgL = fast_log2(Lb[e]);
+      const float yq = fminf(lgL, p.lg_y_hi);
+      u64 lS2;  // log2 S' of the two channels
+      if (!FOV) {
+        const int cj = min((int)((yq - p.y0) * p.inv_dy), 30) * 8;  // L_bkg >= 0.1 lies above the first axis point: no lower clamp
+        const float2 xi = *reinterpret_cast<const float2*>(sTab + cj);
+        const float fj = (yq - xi.x) * xi.y;
+        const ulonglong2 td = *reinterpret_cast<const ulonglong2*>(sTab + cj + 4);  // (t0, t1), (dt0, dt1)
+        lS2 = ffma2(pk(fj, fj), td.y, td.x);
+      } else {
+        const float4 fc = sFov[e * NCT + tid];
+        int jj, kk;
+        float fy, fe;
+        locate_direct(yq, p.ax.x[1], p.ax.inv[1], p.ax.x0[1], p.ax.inv_dx[1], jj, fy);
+        const float ex = fc.x - p.gaze[fi][0], ey = fc.y - p.gaze[fi][1];
+        const float ecc = fast_sqrt(fmaf(ex, ex, ey * ey));  // eccentricity [deg] (fvvdp.py:432)
+        const float eq = fast_sqrt(fminf(fmaxf(ecc, p.ax.lo[2]), p.ax.hi[2]));
+        locate_direct(eq, p.ax.x[2], p.ax.inv[2], p.ax.x0[2], p.ax.inv_dx[2], kk, fe);
+        // trilinear look-up of both temporal channels: 4 (rho, ecc) corners, each record holds the Y entry and its step
+        const float4* v = p.lut4 + __float_as_int(fc.w) + kk * 32 + jj;
+        const float4 c00 = __ldg(v), c01v = __ldg(v + 32), c10 = __ldg(v + 1024), c11 = __ldg(v + 1056);
+        const float fr = fc.z;
+        float ls[2];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        B[0][e] = lo_of(Bp[cc][e]);
-        B[1][e] = hi_of(Bp[cc][e]);
-      }
-      if (cc == 0) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          lgL[e] = fast_log2(Lb[e]);
-          const float yq = fminf(lgL[e], p.lg_y_hi);
-          if (!FOV) {
-            cj[e] = min((int)((yq - p.y0) * p.inv_dy), 30) * 8;  // L_bkg >= 0.1 lies above the first axis point: no lower clamp
-            const float2 xi = *reinterpret_cast<const float2*>(sTab + cj[e]);
-            fj[e] = (yq - xi.x) * xi.y;
-          } else {
-            const float4 fc = sFov[e * NCT + tid];
-            int jj, kk;
-            float fy, fe;
-            locate_direct(yq, p.ax.x[1], p.ax.inv[1], p.ax.x0[1], p.ax.inv_dx[1], jj, fy);
-            const float ex = fc.x - p.gaze[fi][0], ey = fc.y - p.gaze[fi][1];
-            const float ecc = fast_sqrt(fmaf(ex, ex, ey * ey));  // eccentricity [deg] (fvvdp.py:432)
-            const float eq = fast_sqrt(fminf(fmaxf(ecc, p.ax.lo[2]), p.ax.hi[2]));
-            locate_direct(eq, p.ax.x[2], p.ax.inv[2], p.ax.x0[2], p.ax.inv_dx[2], kk, fe);
-            // trilinear look-up of both temporal channels: 4 (rho, ecc) corners, each record holds the Y entry and its step
-            const float4* v = p.lut4 + __float_as_int(fc.w) + kk * 32 + jj;
-            const float4 c00 = __ldg(v), c01v = __ldg(v + 32), c10 = __ldg(v + 1024), c11 = __ldg(v + 1056);
-            const float fr = fc.z;
-#pragma unroll
-            for (int c2 = 0; c2 < 2; ++c2) {
-              const float t00 = c2 ? fmaf(fy, c00.w, c00.z) : fmaf(fy, c00.y, c00.x), t01 = c2 ? fmaf(fy, c01v.w, c01v.z) : fmaf(fy, c01v.y, c01v.x);
-              const float t10 = c2 ? fmaf(fy, c10.w, c10.z) : fmaf(fy, c10.y, c10.x), t11 = c2 ? fmaf(fy, c11.w, c11.z) : fmaf(fy, c11.y, c11.x);
-              const float lo = fmaf(fr, t10 - t00, t00), hi = fmaf(fr, t11 - t01, t01);  // along rho at ecc cell kk, kk + 1
-              lsf[c2][e] = fmaf(fe, hi - lo, lo);
-            }
-          }
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const float t00 = c2 ? fmaf(fy, c00.w, c00.z) : fmaf(fy, c00.y, c00.x), t01 = c2 ? fmaf(fy, c01v.w, c01v.z) : fmaf(fy, c01v.y, c01v.x);
+          const float t10 = c2 ? fmaf(fy, c10.w, c10.z) : fmaf(fy, c10.y, c10.x), t11 = c2 ? fmaf(fy, c11.w, c11.z) : fmaf(fy, c11.y, c11.x);
+          const float lo = fmaf(fr, t10 - t00, t00), hi = fmaf(fr, t11 - t01, t01);  // along rho at ecc cell kk, kk + 1
+          ls[c2] = fmaf(fe, hi - lo, lo);
         }
+        lS2 = pk(ls[0], ls[1]);
       }
+      const float ce = p.log2_m - lgL;
+      const u64 base2 = fadd2(lS2, pk(ce, ce));
+      // T_f = min(band/L_bkg, 1000) * m  (fvvdp_lpyr_dec.py:268, :57-63); T/N = T_f * S  (fvvdp.py:583-584)
+      const float lim = 1000.0f * Lb[e];
+      float lgd[2], lgm[2];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float lS;  // log2 of (sensitivity x sensitivity_correction)
-        if (!FOV) {
-          const float2 td = *reinterpret_cast<const float2*>(sTab + cj[e] + 2 + 2 * cc);
-          lS = fmaf(fj[e], td.y, td.x);
-        } else {
-          lS = lsf[cc][e];
-        }
-        // T_f = min(band/L_bkg, 1000) * m  (:268, :57-63); T/N = T_f * S  (fvvdp.py:583-584)
-        const float lim = 1000.0f * Lb[e];
-        const float bT = fminf(B[0][e], lim), bR = fminf(B[1][e], lim);
-        const float lSL = lS + (p.log2_m - lgL[e]);
-        const float ld = fast_log2((tile_full || valid[e]) ? fabsf(bT - bR) : 0.0f) + lSL;  // log2 |T' - R'|
-        const float lM = fast_log2(fminf(fabsf(bT), fabsf(bR))) + (lSL + p.log2_mask_c);  // log2 M  (:588)
-        const float Mq = fast_exp2(p.mask_q[cc] * lM);
-        const float lD = fminf(fmaf(p.mask_p, ld, -fast_log2(1.0f + Mq)), 13.287712379549449f);  // D <= 1e4 (:593-595)
-        acc[cc] += fast_exp2(p.beta * lD);
+      for (int cc = 0; cc < 2; ++cc) {
+        const float bT = fminf(lo_of(Bp[cc][e]), lim), bR = fminf(hi_of(Bp[cc][e]), lim);
+        lgd[cc] = fast_log2(fabsf(bT - bR));
+        lgm[cc] = fast_log2(fminf(fabsf(bT), fabsf(bR)));
       }
+      const u64 X = ffma2(p.m_bp, pk(lgd[0], lgd[1]), fmul2(p.m_bp, base2));          // beta p log2 |T' - R'|
+      const u64 qM = ffma2(p.m_q, pk(lgm[0], lgm[1]), ffma2(p.m_q, base2, p.m_qlmc));   // q log2 M
+      const u64 one2 = pk(1.0f, 1.0f);
+      const u64 s1 = fadd2(pk(fast_exp2(lo_of(qM)), fast_exp2(hi_of(qM))), one2);       // 1 + M^q
+      const u64 lD = ffma2(p.m_nbeta, pk(fast_log2(lo_of(s1)), fast_log2(hi_of(s1))), X);
+      u64 D2 = pk(fast_exp2(fminf(lo_of(lD), p.m_cap)), fast_exp2(fminf(hi_of(lD), p.m_cap)));   // D^beta
+      acc2 = fadd2(acc2, D2);
     }
-    // ---- per-frame partial sums: warp shuffle now, one pass over the warps at the end.  The two channel sums share
-    //      the butterfly: after the first exchange the lower half-warp carries channel 0, the upper half channel 1.
-    {
-      const bool up = lane >= 16;
-      float v = (up ? acc[1] : acc[0]) + __shfl_xor_sync(0xffffffffu, up ? acc[0] : acc[1], 16);
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if ((lane & 15) == 0) sRed[((fi - f_lo) * 2 + (up ? 1 : 0)) * NCW + warp] = v;
-    }
+    pend2 = acc2;      // reduced over the warp in the next iteration, under the latency of its shared-memory loads
+    pend_row = fi - f_lo;
   }
+  if (pend_row >= 0) warp_sums(pend2, pend_row);
   named_bar_sync<2, NCT>();
   for (int i = tid; i < (f_hi - f_lo) * 2; i += NCT) {
     float v = 0.0f;

@@ -521,3 +521,106 @@ def test_full_size_properties_4k(fv_mod):
     jod_s, st_s = fv.predict(stat_t, stat_r, frames_per_second=30)
     q = st_s["Q_per_ch"]
     assert np.abs(q - q[:, :, :1]).max() <= 1e-6 * q.max()  # the transient response of a static clip is itself ~1e-5 of the sustained one
+
+
+# ---------------------------------------------------------------------------------------------- round 2: more reference fixtures
+def check_q_per_band(Q, gQ, tol):
+    """Every band and temporal channel against ITS OWN maximum over the frames (a weak band cannot hide behind a strong one)."""
+    scale = np.maximum(np.abs(gQ).max(axis=2, keepdims=True), 1e-9)
+    err = np.abs(Q - gQ) / scale
+    assert err.max() < tol, err.max(axis=2)
+
+
+def test_bench_clip_64_frames_against_reference(fv_mod, golden):
+    """The benchmark's own clip (BASELINE configs[2]: 3840x2160 x 64 frames, standard_4k, 30 fps) against JOD / Q_per_ch of the
+    UNMODIFIED reference on the CPU (tools/gen_golden.py round2), resident on the GPU as bench.py scores it."""
+    g = golden("full_4k_64f")
+    t, r = synth_pair_torch(64, 2160, 3840, torch.device("cuda:0"))
+    jod, st = fv_mod.fvvdp(display_name="standard_4k").predict(t, r, frames_per_second=30)
+    check_jod(jod, g["jod"])
+    check_q(st["Q_per_ch"], g["Q_per_ch"])
+    check_q_per_band(st["Q_per_ch"], g["Q_per_ch"], 1e-3)
+
+
+@pytest.mark.parametrize("name", ["gog_gamma", "gog_srgb"])
+def test_gog_photometry(fv_mod, golden, name):
+    """fvvdp_display_photo_gog (fvvdp_display_model.py:253-279): gamma branch and the sRGB branch (gamma = -1)."""
+    g = golden(f"video_{name}")
+    Y_peak, contrast, gamma, E_amb, k_refl = [float(v) for v in g["gog"]]
+    dp = fv_mod.fvvdp_display_photo_gog(Y_peak, contrast=contrast, gamma=gamma if gamma > 0 else -1, E_ambient=E_amb, k_refl=k_refl)
+    t, r = synth_pair_numpy(8, 270, 480)
+    jod, st = fv_mod.fvvdp(display_name="standard_fhd", display_photometry=dp).predict(t, r, frames_per_second=30)
+    check_jod(jod, g["jod"])
+    check_q(st["Q_per_ch"], g["Q_per_ch"])
+
+
+@pytest.mark.parametrize("shape", [(9, 135, 240), (40, 270, 480)])
+def test_120_fps_against_reference(fv_mod, golden, shape):
+    """120 fps: a 30-tap temporal window (fvvdp.py:228), clips shorter and longer than the window."""
+    N, H, W = shape
+    g = golden(f"video_120fps_{N}x{H}x{W}")
+    t, r = synth_pair_numpy(N, H, W)
+    jod, st = fv_mod.fvvdp(display_name="standard_fhd").predict(t, r, frames_per_second=120)
+    check_jod(jod, g["jod"])
+    check_q(st["Q_per_ch"], g["Q_per_ch"])
+
+
+def test_source_colour_space_overrides_metric(fv_mod, golden):
+    """RGB -> luminance weights come from the video SOURCE (video_source.py:87,206), not from the metric's colour space:
+    a BT.2020 array source scored by a metric left at sRGB."""
+    g = golden("video_source_bt2020_metric_srgb")
+    fv = fv_mod.fvvdp(display_name="standard_4k")
+    vs = fv_mod.fvvdp_video_source_array(g["test"], g["ref"], 30, dim_order="FHWC", display_photometry=fv.display_photometry, color_space_name="BT.2020")
+    jod, st = fv.predict_video_source(vs)
+    check_jod(jod, g["jod"])
+    check_q(st["Q_per_ch"], g["Q_per_ch"])
+    # and it differs from what sRGB weights would give
+    jod_srgb, _ = fv.predict(g["test"], g["ref"], dim_order="FHWC", frames_per_second=30)
+    assert abs(float(jod_srgb) - float(g["jod"])) > 1e-4
+
+
+def test_pu_psnr_identical_frames(fv_mod):
+    t, _ = synth_pair_numpy(3, 64, 96)
+    q, _ = fv_mod.pu_psnr(display_name="standard_4k").predict(t, t, frames_per_second=30)
+    assert float(q) == float("inf")
+
+
+# ---------------------------------------------------------------------------------------------- kernel paths
+@pytest.mark.parametrize("levels", ["7", "0"])
+def test_kernel_paths_agree_with_reference(fv_mod, golden, monkeypatch, levels):
+    """The warp-specialised kernel on every pyramid level (FVVDP_B200_WS_LEVELS=7; by default it runs level 0 only) and the
+    fused kernel alone (=0) against the same reference fixtures, incl. non-replicate padding (warm-up walk of the rings),
+    short clips, and the 4K frame size; block cuts stay bit-identical on either path."""
+    monkeypatch.setenv("FVVDP_B200_WS_LEVELS", levels)
+    for pad in ("replicate", "pingpong", "circular"):
+        g = golden(f"video_fhd_{pad}")
+        t, r = synth_pair_numpy(12, 270, 480)
+        jod, st = fv_mod.fvvdp(display_name="standard_fhd", temp_padding=pad).predict(torch.from_numpy(t).cuda(), torch.from_numpy(r).cuda(), frames_per_second=30)
+        check_jod(jod, g["jod"])
+        check_q(st["Q_per_ch"], g["Q_per_ch"])
+    g = golden("video_short_25fps_pingpong")
+    t, r = synth_pair_numpy(5, 270, 480)
+    jod, st = fv_mod.fvvdp(display_name="standard_fhd", temp_padding="pingpong").predict(torch.from_numpy(t).cuda(), torch.from_numpy(r).cuda(), frames_per_second=25)
+    check_jod(jod, g["jod"])
+    g = golden("full_4k_9f")
+    t, r = synth_pair_torch(9, 2160, 3840, torch.device("cuda:0"))
+    jod, st = fv_mod.fvvdp(display_name="standard_4k").predict(t, r, frames_per_second=30)
+    check_jod(jod, g["jod"])
+    check_q_per_band(st["Q_per_ch"], g["Q_per_ch"], 1e-3)
+    jod4, st4 = fv_mod.fvvdp(display_name="standard_4k", block_frames=4).predict(t, r, frames_per_second=30)
+    assert np.array_equal(st4["Q_per_ch"], st["Q_per_ch"])
+
+
+def test_sharded_clip_equals_single_gpu_nccl(fv_mod):
+    """Frame blocks on two GPUs (one process each, NCCL all-reduce of the pooled energies) == the single-GPU result, bit for bit.
+    Needs two visible GPUs; the single-GPU test box skips it (tools/check_sharding_nccl.py is the same check under torchrun)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
+                        "29533", os.path.join(root, "tools", "check_sharding_nccl.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "MISMATCH" not in r.stdout
