@@ -290,13 +290,19 @@ def run_ours(args, W, H):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    from fovvideovdp_b200.fvvdp import frame_block
+
     F = args.frames
     fl = 8
     n_total = F * world
-    first = rank * F
+
+    def my_block(n_frames):  # the cut predict_video_source() makes (work-balanced: ranks > 0 also walk the 7-frame temporal halo)
+        return frame_block(n_frames, rank, world, halo=fl - 1, first_halo=1)
+
+    first, last = my_block(n_total)
     halo = min(first, fl - 1)
-    # this rank's frames [first - halo, first + F) of the n_total-frame clip, generated on the device
-    t, r = synth_pair_torch(F + halo, H, W, dev, first_frame=first - halo)
+    # this rank's frames [first - halo, last) of the n_total-frame clip, generated on the device
+    t, r = synth_pair_torch(last - first + halo, H, W, dev, first_frame=first - halo)
     fv = m.fvvdp(display_name=args.display, device=dev, shard_frames=world > 1)
 
     def source(tt, rr, first_frame=first - halo, total=n_total, metric=fv):
@@ -342,7 +348,7 @@ def run_ours(args, W, H):
     peak, peak_src = measured_peaks()
     top = max(prof.items(), key=lambda kv: kv[1][0])
     total_ms = sum(v[0] for v in prof.values())
-    frames_per_launch = F * args.steps / top[1][1]
+    frames_per_launch = (last - first) * args.steps / top[1][1]
     alg_bytes = 2.0 * H * W * 4 * frames_per_launch
     dur_s = top[1][0] / top[1][1] / 1000.0
     achieved = alg_bytes / dur_s / 1e9
@@ -383,7 +389,7 @@ def run_ours(args, W, H):
     strong = None
     if extras and (W, H) == (3840, 2160):
         N256 = 256
-        b0, b1 = (rank * N256) // world, ((rank + 1) * N256) // world
+        b0, b1 = my_block(N256)
         h0 = min(b0, fl - 1)
         del vs_dev
         t = r = None
@@ -396,7 +402,7 @@ def run_ours(args, W, H):
                   "ms_per_clip": ms_256 / 3, "jod": jod_256, "scaling": "strong"}
         del ts, rs, vs256
         torch.cuda.empty_cache()
-        t, r = synth_pair_torch(F + halo, H, W, dev, first_frame=first - halo)
+        t, r = synth_pair_torch(last - first + halo, H, W, dev, first_frame=first - halo)
 
     # ---- the other single-GPU configurations of BASELINE.json
     other = None
@@ -411,7 +417,7 @@ def run_ours(args, W, H):
         other["configs[1] 1920x1080x%d fp32, standard_fhd" % F] = {"value": F * 10 / (ms2 / 1000.0), "unit": "frames/s", "jod": jod2}
         del t2, r2, vs2, fv2
         # foveated HDR: PQ code values 0.1 + 0.65 v, gaze moving corner to corner (ex_foveated_video.py:36-37)
-        tq, rq = 0.1 + 0.65 * t[:, :, halo:], 0.1 + 0.65 * r[:, :, halo:]
+        tq, rq = 0.1 + 0.65 * t[:, :, halo:halo + F], 0.1 + 0.65 * r[:, :, halo:halo + F]
         fv5 = m.fvvdp(display_name="standard_hdr_pq", device=dev, foveated=True)
         gaze = np.stack([np.linspace(0, W - 1, F), np.linspace(0, H - 1, F)], 1).astype(np.float32)
         vs5 = source(tq, rq, first_frame=0, total=F, metric=fv5)
@@ -462,7 +468,7 @@ def run_ours(args, W, H):
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_string(W, H, F, n_total, args.display, world),
-                       "frames_per_gpu": F, "block_frames": info.get("block_frames"), "l2": "inputs exceed L2 (2 x %.1f GB per step)" % (F * H * W * 4 / 1e9),
+                       "frames_per_gpu": F, "frames_this_rank": last - first, "block_frames": info.get("block_frames"), "l2": "inputs exceed L2 (2 x %.1f GB per step)" % (F * H * W * 4 / 1e9),
                        "parallelism": f"frame blocks over {world} GPU(s), one all-reduce of the pooled energies" if world > 1 else "single GPU"},
             "jod": jod, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "sustained": sustained, "strong_256": strong, "other_configs": other, "reference_cuda": ref_cuda,

@@ -10,7 +10,7 @@ from . import build as _build
 ABI_VERSION = 1
 MAX_LEVELS = 16
 MAX_FILTER_LEN = 32
-MAX_BLOCK_FRAMES = 64
+MAX_BLOCK_FRAMES = 96
 MAX_SLOTS = MAX_BLOCK_FRAMES + MAX_FILTER_LEN
 
 EOTF_CODES = {"none": 0, "sRGB": 1, "gamma": 2, "PQ": 3, "linear": 4, "absolute": 5}

@@ -457,7 +457,7 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
   cudaError_t le = cudaSuccess;
   if (ctx->fused) {
     // ---- fused band kernels: one launch per pyramid level (fvvdp_fused.cuh) ----
-    static_assert(sizeof(fused::BandParams) <= 4080, "kernel parameter space");
+    static_assert(sizeof(fused::BandParams) <= 16384, "kernel parameter space (32764 bytes since CUDA 12.1 on sm_70+)");
     fused::BandParams bp;
     memset(&bp, 0, sizeof(bp));
     bool aligned = true;

@@ -43,7 +43,7 @@ constexpr int NH = TH / 2 + 2, NW = TW / 2 + 2; // reduced tile with 1-px halo: 
 constexpr int NE = NH * NW;                     // 340
 constexpr int RING = 8;                         // temporal window kept on chip by the 256-thread kernels (one 2x2 quad per thread)
 constexpr int MAXRING = 16;                     // ... and by the 512-thread kernels (two pixels per thread; 60 fps clips)
-constexpr int MAXCHUNK = 64;                    // output frames walked by one CTA
+constexpr int MAXCHUNK = FVVDP_B200_MAX_BLOCK_FRAMES;  // output frames walked by one CTA
 constexpr int LV4 = LW / 4;                     // 4-pixel chunks per staged row
 constexpr int NPC = LH * LV4;                   // 4-pixel position chunks of a staged tile (432)
 // threads per CTA / pixels per thread: up to 8 taps the thread owns a 2x2 quad (8 x 4 ring registers pairs), beyond that

@@ -40,7 +40,7 @@ constexpr int NE = NH * NW;                     // 612
 #endif
 // Warp split and registers per thread after setmaxnreg (the CTA's pool is NT x (65536 / NT rounded down to 8)).  Each
 // translation unit instantiates ONE input kind, so the split is chosen per kind:
-//   level 0 (EOTF pass in the producers): 12 producer warps, 512 * 88 + 384 * 48 <= 896 * 72
+//   level 0 (EOTF pass in the producers): 12 producer warps, 512 * 96 + 384 * 40 = 896 * 72   (the consumers are the bound)
 //   pyramid levels (no EOTF pass):         8 producer warps, 512 * 96 + 256 * 48 = 768 * 80
 #if defined(WS_KIND) && WS_KIND == 2 && defined(WS2_NPW)   // experiment builds: override for the pyramid-level unit only
 #define WS_NPW WS2_NPW
@@ -54,8 +54,8 @@ constexpr int NE = NH * NW;                     // 612
 #define WS_PREGS 48
 #else
 #define WS_NPW 12
-#define WS_CREGS 88
-#define WS_PREGS 48
+#define WS_CREGS 96
+#define WS_PREGS 40
 #endif
 #endif
 constexpr int NCW = 16, NPW = WS_NPW;           // consumer / producer warps
@@ -80,7 +80,7 @@ struct Layout {
   // luminance / filtered-reduced-tile buffers (frames in flight between the roles).  The pyramid levels stage with TMA straight
   // into these buffers, AHEAD = NLB - 2 frames ahead: the buffer that is refilled was released two iterations ago, so the
   // thread that issues the copies never waits for the consumers
-  static constexpr int NLB = LANDING ? (FOV ? 2 : 3) : 4;
+  static constexpr int NLB = LANDING ? (FOV ? 2 : 3) : (FOV ? 3 : 4);   // what fits beside the foveation constants
   static constexpr int AHEAD = LANDING ? 2 : NLB - 2;
   static constexpr int oL = 0;                               // [NLB][LH][LW][2]
   static constexpr int oRaw = oL + NLB * TILE_FLOATS;        // LANDING: [2][2 streams][LH][LW]
@@ -93,6 +93,7 @@ struct Layout {
   static constexpr int oFov = oRed + MAXCHUNK * 2 * NCW;     // FOV: float4 [4][NCT]
   static constexpr int total = oFov + (FOV ? 4 * 4 * NCT : 0);
   static constexpr size_t bytes = sizeof(float) * (size_t)total;
+  static_assert(bytes + 1024 <= 227 * 1024, "shared memory of one CTA");
 };
 
 __device__ __forceinline__ void mbar_arrive(unsigned bar) {

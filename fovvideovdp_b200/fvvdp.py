@@ -92,10 +92,26 @@ def initial_window(n_frames, filter_len, temp_padding):
     raise RuntimeError('Unknown padding method "{}"'.format(temp_padding))
 
 
-def frame_block(n_frames, rank, world_size):
-    """Contiguous block of frames [begin, end) scored by `rank` when a clip is sharded over `world_size`
-    processes."""
-    return (rank * n_frames) // world_size, ((rank + 1) * n_frames) // world_size
+HALO_SLOT_COST = 0.6   # a temporal-halo frame (staged, converted, reduced, filtered into the rings, not scored) relative to a scored one
+
+
+def frame_block(n_frames, rank, world_size, halo=0, first_halo=None, halo_cost=HALO_SLOT_COST):
+    """Contiguous block of frames [begin, end) scored by `rank` when a clip is sharded over `world_size` processes
+    (SURVEY.md section 8e).  With `halo` > 0 the cut balances the WORK instead of the frame count: every rank but the first walks
+    `halo` extra frames (the temporal window before its block) at `halo_cost` of a scored frame each, the first rank `first_halo`
+    of them (1 with replicate padding, where the repeated first frame is reduced once), so the first rank takes a few frames
+    more and all ranks reach the all-reduce together."""
+    if halo <= 0 or world_size == 1:
+        return (rank * n_frames) // world_size, ((rank + 1) * n_frames) // world_size
+    first_halo = halo if first_halo is None else first_halo
+    extra = [halo_cost * (first_halo if r == 0 else halo) for r in range(world_size)]
+    share = (n_frames + sum(extra)) / world_size          # work units per rank
+    bounds, acc = [0], 0.0
+    for r in range(world_size - 1):
+        acc += max(share - extra[r], 1.0)
+        bounds.append(min(max(int(round(acc)), bounds[-1] + 1), n_frames - (world_size - 1 - r)))
+    bounds.append(n_frames)
+    return bounds[rank], bounds[rank + 1]
 
 
 class _FrameSet:
@@ -413,7 +429,8 @@ class fvvdp:
         if self.shard_frames and torch.distributed.is_available() and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size()
             if world > 1 and N_frames >= world:
-                f_begin, f_end = frame_block(N_frames, torch.distributed.get_rank(), world)
+                f_begin, f_end = frame_block(N_frames, torch.distributed.get_rank(), world, halo=fl - 1,
+                                             first_halo=1 if self.temp_padding == "replicate" else fl - 1)
             else:
                 world = 1  # replicas only: every rank scores the whole (short) clip
 
@@ -444,12 +461,12 @@ class fvvdp:
             fov_maps = self._custom_foveation_maps(ctx, n_bands, freqs)  # kept alive until the end of this call
         first = initial_window(N_frames, fl, self.temp_padding) if not is_image else [0]
 
-        def frame_at(t):  # frame shown at time t (t <= 0 falls into the temporal padding)
-            return t if t >= 1 else first[fl - 1 + t]
+        # frame shown at time t = -(fl-1) .. N-1 (t <= 0 falls into the temporal padding): timeline[t + fl - 1]
+        timeline = list(first[:fl]) + list(range(1, N_frames))
 
         def block_slots(f0):
             n = min(T, f_end - f0)
-            return n, [frame_at(f0 - (fl - 1) + s) for s in range(n + fl - 1)]
+            return n, timeline[f0:f0 + n + fl - 1]
 
         def prefetch(f0):  # frames of the block starting at f0 -> device (host sources: on the upload stream)
             frames.fetch_all(block_slots(f0)[1])

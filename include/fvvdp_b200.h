@@ -35,7 +35,7 @@ extern "C" {
 #define FVVDP_B200_ABI_VERSION 1
 #define FVVDP_B200_MAX_LEVELS 16
 #define FVVDP_B200_MAX_FILTER_LEN 32
-#define FVVDP_B200_MAX_BLOCK_FRAMES 64
+#define FVVDP_B200_MAX_BLOCK_FRAMES 96
 #define FVVDP_B200_MAX_SLOTS (FVVDP_B200_MAX_BLOCK_FRAMES + FVVDP_B200_MAX_FILTER_LEN)
 
 typedef enum {

@@ -91,6 +91,23 @@ def test_window_rule_matches_oracle(pad):
             assert got == want
 
 
+def test_frame_block_work_balanced():
+    """With a temporal halo the cut balances work, not frames: contiguous, complete, non-empty, and the first rank (whose halo is
+    one repeated frame under replicate padding) takes the most frames."""
+    for N in (8, 9, 37, 128, 256, 512):
+        for G in (2, 4, 8):
+            if N < G:
+                continue
+            blocks = [frame_block(N, r, G, halo=7, first_halo=1) for r in range(G)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == N
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(G - 1)) and all(b > a for a, b in blocks)
+            sizes = [b - a for a, b in blocks]
+            assert sizes[0] == max(sizes) and max(sizes) - min(sizes) <= 5
+            work = [sz + 0.6 * (1 if r == 0 else 7) for r, sz in enumerate(sizes)]
+            if N >= 16 * G:
+                assert max(work) - min(work) <= 1.5
+
+
 def test_frame_block_partition():
     for N in (1, 7, 64, 255, 256):
         for G in (1, 2, 3, 8):

@@ -17,8 +17,9 @@ for spec in sys.argv[1:]:
     obj = os.path.join(d, "obj")
     shutil.rmtree(d, ignore_errors=True)
     os.makedirs(obj)
+    rebuild_all = "FUSED" in flags  # flags of the fused kernels: every unit is recompiled
     for f in os.listdir(main_obj):
-        if not f.startswith("ws_"):
+        if not f.startswith("ws_") and not rebuild_all:
             shutil.copy2(os.path.join(main_obj, f), os.path.join(obj, f))
     b.OBJ_DIR = obj
     b.LIB = os.path.join(d, "libfvvdp_b200.so")
