@@ -21,7 +21,7 @@ EXPORTS = ["fvvdp_b200_create", "fvvdp_b200_score_block", "fvvdp_b200_heatmap", 
            "fvvdp_b200_level_size", "fvvdp_b200_launch_count", "fvvdp_b200_traffic_model", "fvvdp_b200_destroy",
            "fvvdp_b200_last_error", "fvvdp_b200_abi_version", "fvvdp_b200_pool_jod",
            "fvvdp_b200_profile", "fvvdp_b200_profile_read", "fvvdp_b200_heatmap_visualize", "fvvdp_b200_set_foveation_maps",
-           "fvvdp_b200_yuv_to_luminance", "fvvdp_b200_pu_sq_err"]
+           "fvvdp_b200_yuv_to_luminance", "fvvdp_b200_pu_sq_err", "fvvdp_b200_pu_sq_err_frames"]
 COLORMAPS = {"threshold": 0, "supra-threshold": 1}
 PROFILE_CLASSES = MAX_LEVELS + 2
 
@@ -241,6 +241,25 @@ def pu_sq_err(test_ptr, ref_ptr, n, params: PuParams, acc_ptr, device_index, str
                                   C.c_void_p(stream))
     if rc != 0:
         raise RuntimeError(f"fvvdp_b200_pu_sq_err failed ({rc}): {last_error(None)}")
+
+
+class FrameFormat(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("in_dtype", C.c_int32), ("in_channels", C.c_int32), ("eotf", C.c_int32),
+                ("Y_peak", C.c_float), ("Y_black", C.c_float), ("gamma", C.c_float), ("L_min", C.c_float), ("L_max", C.c_float),
+                ("rgb2y", C.c_float * 3)]
+
+
+def pu_sq_err_frames(fmt: FrameFormat, test_ptrs, ref_ptrs, strides, params: PuParams, out_ptr, device_index, stream):
+    """out[i] (device double) += sum((PU(test_i) - PU(ref_i))^2) for a block of frames in their own dtype / layout."""
+    lib = load_library()
+    n = len(test_ptrs)
+    tp = (C.c_void_p * n)(*test_ptrs)
+    rp = (C.c_void_p * n)(*ref_ptrs)
+    st = (C.c_int64 * 3)(*[int(v) for v in strides])
+    lib.fvvdp_b200_pu_sq_err_frames.restype = C.c_int
+    rc = lib.fvvdp_b200_pu_sq_err_frames(C.byref(fmt), tp, rp, st, C.c_int(n), C.byref(params), C.c_void_p(out_ptr), C.c_int(device_index), C.c_void_p(stream))
+    if rc != 0:
+        raise RuntimeError(f"fvvdp_b200_pu_sq_err_frames failed ({rc}): {last_error(None)}")
 
 
 def pool_jod(q_ptr, n_bands, n_frames, q_stride, params: PoolParams, device_index, out_ptr, stream):

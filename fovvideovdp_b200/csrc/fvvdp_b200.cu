@@ -875,6 +875,39 @@ extern "C" int fvvdp_b200_pu_sq_err(const float* lum_test, const float* lum_ref,
   return FVVDP_B200_OK;
 }
 
+extern "C" int fvvdp_b200_pu_sq_err_frames(const fvvdp_b200_frame_format* fmt, const void* const* test_frames, const void* const* ref_frames,
+                                           const int64_t strides[3], int n_frames, const fvvdp_b200_pu_params* params, double* sq_err_out,
+                                           int cuda_device, void* cuda_stream) {
+  fvvdp_b200_ctx* ctx = nullptr;  // ctx-free: errors are reported through fvvdp_b200_last_error(NULL)
+  if (!fmt || !test_frames || !ref_frames || !strides || !params || !sq_err_out) return fail(ctx, FVVDP_B200_ERR_INVALID, "null argument");
+  if (n_frames < 1 || n_frames > FVVDP_B200_MAX_SLOTS) return fail(ctx, FVVDP_B200_ERR_INVALID, "n_frames %d not in 1..%d", n_frames, FVVDP_B200_MAX_SLOTS);
+  if (fmt->width < 1 || fmt->height < 1) return fail(ctx, FVVDP_B200_ERR_INVALID, "bad frame size %dx%d", fmt->width, fmt->height);
+  if (fmt->in_channels != 1 && fmt->in_channels != 3) return fail(ctx, FVVDP_B200_ERR_INVALID, "The content must have either 1 or 3 colour channels.");
+  if (fmt->in_dtype < 0 || fmt->in_dtype > 2) return fail(ctx, FVVDP_B200_ERR_INVALID, "Only uint8, uint16 and float32 is currently supported");
+  if (fmt->eotf < 0 || fmt->eotf > 5) return fail(ctx, FVVDP_B200_ERR_INVALID, "Unknown EOTF %d", fmt->eotf);
+  CU(cudaSetDevice(cuda_device));
+  fused::BandParams bp;
+  memset(&bp, 0, sizeof(bp));
+  bool aligned = true;
+  for (int s = 0; s < n_frames; ++s) {
+    if (!test_frames[s] || !ref_frames[s]) return fail(ctx, FVVDP_B200_ERR_INVALID, "null frame pointer %d", s);
+    bp.slot[0][s] = test_frames[s];
+    bp.slot[1][s] = ref_frames[s];
+    aligned = aligned && (((uintptr_t)test_frames[s] | (uintptr_t)ref_frames[s]) % 16 == 0);
+  }
+  bp.w = fmt->width; bp.h = fmt->height;
+  bp.sC = strides[0]; bp.sH = strides[1]; bp.sW = strides[2];
+  bp.C = fmt->in_channels; bp.dtype = fmt->in_dtype; bp.eotf = fmt->eotf;
+  bp.Yscale = fmt->Y_peak - fmt->Y_black; bp.Y_black = fmt->Y_black; bp.Y_peak = fmt->Y_peak; bp.gamma = fmt->gamma;
+  bp.L_min = fmt->L_min; bp.L_max = fmt->L_max;
+  for (int i = 0; i < 3; ++i) bp.rgb2y[i] = fmt->rgb2y[i];
+  const bool vec_ok = strides[2] == 1 && aligned && strides[1] % 4 == 0 && (fmt->in_channels == 1 || strides[0] % 4 == 0);
+  static_assert(sizeof(fvvdp_b200_pu_params) == sizeof(PuParams), "PU21 parameter block");
+  cudaError_t le = fused::launch_pu_frames(bp, params, sq_err_out, n_frames, vec_ok, (cudaStream_t)cuda_stream);
+  if (le != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "pu_frames_kernel launch: %s", cudaGetErrorString(le));
+  return FVVDP_B200_OK;
+}
+
 extern "C" int fvvdp_b200_pool_jod(const float* q, int n_bands, int64_t n_frames, int64_t q_stride, const fvvdp_b200_pool_params* params,
                                    int cuda_device, float* jod_out, void* cuda_stream) {
   fvvdp_b200_ctx* ctx = nullptr;  // ctx-free: errors are reported through fvvdp_b200_last_error(NULL)

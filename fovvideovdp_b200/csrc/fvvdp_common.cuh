@@ -45,4 +45,16 @@ struct CsfAxes {           // device pointers, 32 entries each
 };
 
 
+// PU21 encoding (utils.py:157-202): PU(Y) = p6 (((p0 + p1 Y^p3) / (1 + p2 Y^p3))^p4 - p5), Y clipped to [L_min, L_max]
+struct PuParams {
+  float p[7];
+  float L_min, L_max;
+};
+__device__ __forceinline__ float pu_encode(float Y, const PuParams& q) {
+  Y = fminf(fmaxf(Y, q.L_min), q.L_max);
+  const float yp = fast_exp2(q.p[3] * fast_log2(Y));
+  const float r = (q.p[0] + q.p[1] * yp) / (1.0f + q.p[2] * yp);
+  return fast_exp2(q.p[4] * fast_log2(r));  // PU21 = p6 * (this - p5): the callers work on differences, where p5 cancels
+}
+
 }  // namespace fvvdp

@@ -303,6 +303,13 @@ __device__ __forceinline__ void locate_direct(float q, const float* __restrict__
   f = fmaxf((q - __ldg(x + j)) * __ldg(inv + j + 1), 0.0f);
 }
 
+// the same with the axis staged in shared memory as (x[j], 1 / (x[j+1] - x[j] + 1e-6)) pairs
+__device__ __forceinline__ void locate_smem(float q, const float* __restrict__ ax, float x0, float inv_dx, int& j, float& f) {
+  j = min(max((int)((q - x0) * inv_dx), 0), 30);
+  const float2 a = *reinterpret_cast<const float2*>(ax + 2 * j);
+  f = fmaxf((q - a.x) * a.y, 0.0f);
+}
+
 // ------------------------------------------------------------------------------------------------ temporal rings
 template <int FL>
 struct Ring {
@@ -404,7 +411,12 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
     mbar_init(bar0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < 32) {
+  if (FOV && tid < 64) {
+    // foveated: the Y and eccentricity axes of the CSF table as (x[j], 1 / (x[j+1] - x[j] + 1e-6)) pairs (interp.py:11-20)
+    const int ax = 1 + (tid >> 5), j = tid & 31;
+    reinterpret_cast<float2*>(sTab)[tid] = make_float2(__ldg(p.ax.x[ax] + j), j < 31 ? __ldg(p.ax.inv[ax] + j + 1) : 0.0f);
+  }
+  if (!FOV && tid < 32) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(p.cell) + 2 * tid);
     const float4 b = __ldg(reinterpret_cast<const float4*>(p.cell) + 2 * tid + 1);
     reinterpret_cast<float4*>(sTab)[2 * tid] = a;
@@ -742,11 +754,11 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
             const float4 fc = sFov[e * NT + tid];
             int jj, kk;
             float fy, fe;
-            locate_direct(yq, p.ax.x[1], p.ax.inv[1], p.ax.x0[1], p.ax.inv_dx[1], jj, fy);
+            locate_smem(yq, sTab, p.ax.x0[1], p.ax.inv_dx[1], jj, fy);
             const float ex = fc.x - p.gaze[fi][0], ey = fc.y - p.gaze[fi][1];
             const float ecc = fast_sqrt(fmaf(ex, ex, ey * ey));  // eccentricity [deg] (fvvdp.py:432)
             const float eq = fast_sqrt(fminf(fmaxf(ecc, p.ax.lo[2]), p.ax.hi[2]));
-            locate_direct(eq, p.ax.x[2], p.ax.inv[2], p.ax.x0[2], p.ax.inv_dx[2], kk, fe);
+            locate_smem(eq, sTab + 64, p.ax.x0[2], p.ax.inv_dx[2], kk, fe);
             // trilinear look-up of both temporal channels: 4 (rho, ecc) corners, each record holds the Y entry and its step
             const float4* v = p.lut4 + __float_as_int(fc.w) + kk * 32 + jj;
             const float4 c00 = __ldg(v), c01 = __ldg(v + 32), c10 = __ldg(v + 1024), c11 = __ldg(v + 1056);

@@ -134,6 +134,98 @@ cudaError_t launch_luminance(const BandParams& p, float* out, long long slot_str
   return cudaErrorInvalidValue;
 }
 
+// ------------------------------------------------------------------------------------------------ PU21-PSNR, whole frame blocks
+// pupsnr.py:52-79 for a block of frames in ONE launch: sample -> [0,1] -> display EOTF -> RGB2Y (the arithmetic of the luminance
+// front end above) -> PU21 encoding of both streams -> squared difference, summed per frame in double precision.  No luminance
+// plane is written or read back: the frames are read once, in their own dtype and layout.
+template <int DT, int C, bool VEC, int KIND>
+__device__ __forceinline__ float pu_body(const BandParams& p, const PuParams& q, const float* sLut) {
+  constexpr int PX = VEC ? 4 : 1;
+  const int x = (blockIdx.x * 32 + (threadIdx.x & 31)) * PX, y = blockIdx.y * 8 + (threadIdx.x >> 5), slot = blockIdx.z;
+  float s = 0.0f;
+  if (x < p.w && y < p.h) {
+    float lum[2][PX];
+#pragma unroll
+    for (int st = 0; st < 2; ++st) {
+      const void* base = p.slot[st][slot];
+      const long long off = (long long)y * p.sH + (long long)x * p.sW;
+      float acc[PX];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float v[PX];
+        if (VEC) {
+          float v4[4];
+          samples4_at<DT>(base, off + c * p.sC, v4);
+#pragma unroll
+          for (int i = 0; i < PX; ++i) v[i] = v4[i];
+        } else {
+          v[0] = sample_at<DT>(base, off + c * p.sC);
+        }
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+          const float L = DT == FVVDP_B200_U8 ? sLut[(int)v[i]] : eotf_k<KIND>(v[i], p);
+          acc[i] = C == 1 ? L : (c == 0 ? L * p.rgb2y[0] : acc[i] + L * p.rgb2y[c]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < PX; ++i) lum[st][i] = acc[i];
+    }
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+      const float d = q.p[6] * (pu_encode(lum[0][i], q) - pu_encode(lum[1][i], q));
+      s = fmaf(d, d, s);
+    }
+  }
+  return s;
+}
+
+template <int DT, int C, bool VEC>
+__global__ void __launch_bounds__(256) pu_frames_kernel(const __grid_constant__ BandParams p, const PuParams q, double* __restrict__ out) {
+  __shared__ float sLut[256];
+  __shared__ double sSum[8];
+  float s = 0.0f;
+#define FVVDP_PU(K)                                                                \
+  case K:                                                                          \
+    if (DT == FVVDP_B200_U8) {                                                     \
+      sLut[threadIdx.x] = eotf_k<K>((float)threadIdx.x / 255.0f, p);               \
+      __syncthreads();                                                             \
+    }                                                                              \
+    s = pu_body<DT, C, VEC, K>(p, q, sLut);                                        \
+    break;
+  switch (p.eotf) {  // uniform
+    FVVDP_PU(FVVDP_B200_EOTF_NONE) FVVDP_PU(FVVDP_B200_EOTF_SRGB) FVVDP_PU(FVVDP_B200_EOTF_GAMMA) FVVDP_PU(FVVDP_B200_EOTF_PQ)
+    FVVDP_PU(FVVDP_B200_EOTF_LINEAR) FVVDP_PU(FVVDP_B200_EOTF_ABSOLUTE)
+  }
+#undef FVVDP_PU
+  double v = (double)s;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sSum[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sSum[k];
+    atomicAdd(out + blockIdx.z, t);
+  }
+}
+
+cudaError_t launch_pu_frames(const BandParams& p, const void* pu_params, double* out, int n_frames, bool rows_vectorisable, cudaStream_t st) {
+  const bool vec = rows_vectorisable && p.w % 4 == 0;
+  dim3 grid(((vec ? p.w / 4 : p.w) + 31) / 32, (p.h + 7) / 8, n_frames);
+  const PuParams& q = *reinterpret_cast<const PuParams*>(pu_params);
+#define FVVDP_LAUNCH(DT_, NC_)                                                                  \
+  if (p.dtype == DT_ && p.C == NC_) {                                                           \
+    if (vec) pu_frames_kernel<DT_, NC_, true><<<grid, 256, 0, st>>>(p, q, out);                 \
+    else pu_frames_kernel<DT_, NC_, false><<<grid, 256, 0, st>>>(p, q, out);                    \
+    return cudaGetLastError();                                                                  \
+  }
+  FVVDP_LAUNCH(FVVDP_B200_F32, 1) FVVDP_LAUNCH(FVVDP_B200_F32, 3) FVVDP_LAUNCH(FVVDP_B200_U8, 1) FVVDP_LAUNCH(FVVDP_B200_U8, 3)
+  FVVDP_LAUNCH(FVVDP_B200_U16, 1) FVVDP_LAUNCH(FVVDP_B200_U16, 3)
+#undef FVVDP_LAUNCH
+  return cudaErrorInvalidValue;
+}
+
 cudaError_t configure_band_kernels() {
   cudaError_t e;
 #define CONF(k, v) if ((e = configure_band_##k##_##v()) != cudaSuccess) return e;

@@ -12,6 +12,8 @@ cudaError_t launch_band(int input_kind, int mode, bool foveated, bool extra, con
 cudaError_t configure_band_kernels();
 // level-0 input of any dtype / channel count / strides -> luminance planes in the pyramid layout (slots x h x pitch floats)
 // rows_vectorisable: unit pixel stride, row / channel strides and frame addresses aligned for 4-pixel vector loads
+// PU21 squared error of n_frames frame pairs (p.slot pointers, level-0 input format of p), one double per frame added to out
+cudaError_t launch_pu_frames(const BandParams& p, const void* pu_params, double* out, int n_frames, bool rows_vectorisable, cudaStream_t st);
 cudaError_t launch_luminance(const BandParams& p, float* out, long long slot_stride, int pitch, int n_slots, bool rows_vectorisable, cudaStream_t st);
 }  // namespace fused
 }  // namespace fvvdp

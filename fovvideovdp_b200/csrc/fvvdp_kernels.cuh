@@ -729,16 +729,6 @@ __global__ void __launch_bounds__(256) yuv_kernel(const YuvParams p) {
 // K_pu: PU21-PSNR frame term (pupsnr.py:52-79, utils.py:157-202): sum over the frame of (PU(T) - PU(R))^2 with
 // PU(Y) = p6 (((p0 + p1 Y^p3) / (1 + p2 Y^p3))^p4 - p5), Y clipped to [L_min, L_max]
 // ------------------------------------------------------------------------------------------------
-struct PuParams {
-  float p[7];
-  float L_min, L_max;
-};
-__device__ __forceinline__ float pu_encode(float Y, const PuParams& q) {
-  Y = fminf(fmaxf(Y, q.L_min), q.L_max);
-  const float yp = fast_exp2(q.p[3] * fast_log2(Y));
-  const float r = (q.p[0] + q.p[1] * yp) / (1.0f + q.p[2] * yp);
-  return fast_exp2(q.p[4] * fast_log2(r));  // PU21 = p6 * (this - p5): the callers work on differences, where p5 cancels
-}
 __global__ void __launch_bounds__(256) pu_sqerr_kernel(const float* __restrict__ t, const float* __restrict__ r, long long n, PuParams q,
                                                        double* __restrict__ acc) {
   float s = 0.0f;

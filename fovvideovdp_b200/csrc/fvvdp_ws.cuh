@@ -31,7 +31,7 @@ using fused::u64;
 using fused::pk; using fused::lo_of; using fused::hi_of; using fused::ffma2; using fused::fmul2; using fused::fadd2; using fused::tap5;
 using fused::lds128; using fused::sts128; using fused::smem_u32; using fused::mbar_init; using fused::mbar_expect_tx; using fused::mbar_wait;
 using fused::tma_load_3d; using fused::eotf8; using fused::eotf_checks_range; using fused::locate_direct;
-using fused::IN_PYRAMID_TMA; using fused::IN_LEVEL0_TMA;
+using fused::IN_PYRAMID_TMA; using fused::IN_LEVEL0_TMA; using fused::locate_smem;
 
 constexpr int NH = TH / 2 + 2, NW = TW / 2 + 2; // reduced tile with 1-px halo: origin (jy0-1, jx0-1)
 constexpr int NE = NH * NW;                     // 612
@@ -231,7 +231,12 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < 32) {
+  if (FOV && tid < 64) {
+    // foveated: the Y and eccentricity axes of the CSF table as (x[j], 1 / (x[j+1] - x[j] + 1e-6)) pairs (interp.py:11-20)
+    const int ax = 1 + (tid >> 5), j = tid & 31;
+    reinterpret_cast<float2*>(sTab)[tid] = make_float2(__ldg(p.ax.x[ax] + j), j < 31 ? __ldg(p.ax.inv[ax] + j + 1) : 0.0f);
+  }
+  if (!FOV && tid < 32) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(p.cell) + 2 * tid);
     const float4 b = __ldg(reinterpret_cast<const float4*>(p.cell) + 2 * tid + 1);
     // p.cell holds {Y_log, 1/step, t0, dt0, t1, dt1, 0, 0}; here the two channels' entries and steps sit side by side
@@ -607,11 +612,11 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
         const float4 fc = sFov[e * NCT + tid];
         int jj, kk;
         float fy, fe;
-        locate_direct(yq, p.ax.x[1], p.ax.inv[1], p.ax.x0[1], p.ax.inv_dx[1], jj, fy);
+        locate_smem(yq, sTab, p.ax.x0[1], p.ax.inv_dx[1], jj, fy);
         const float ex = fc.x - p.gaze[fi][0], ey = fc.y - p.gaze[fi][1];
         const float ecc = fast_sqrt(fmaf(ex, ex, ey * ey));  // eccentricity [deg] (fvvdp.py:432)
         const float eq = fast_sqrt(fminf(fmaxf(ecc, p.ax.lo[2]), p.ax.hi[2]));
-        locate_direct(eq, p.ax.x[2], p.ax.inv[2], p.ax.x0[2], p.ax.inv_dx[2], kk, fe);
+        locate_smem(eq, sTab + 64, p.ax.x0[2], p.ax.inv_dx[2], kk, fe);
         // trilinear look-up of both temporal channels: 4 (rho, ecc) corners, each record holds the Y entry and its step
         const float4* v = p.lut4 + __float_as_int(fc.w) + kk * 32 + jj;
         const float4 c00 = __ldg(v), c01v = __ldg(v + 32), c10 = __ldg(v + 1024), c11 = __ldg(v + 1056);

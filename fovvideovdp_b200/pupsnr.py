@@ -9,7 +9,9 @@ import torch
 
 from . import _native
 from .display_model import fvvdp_display_photometry
-from .video_source import fvvdp_video_source_array
+from .display_model import photometry_kernel_spec
+from .fvvdp import _DTYPES, _FrameSet
+from .video_source import fvvdp_video_source_array, is_array_source
 
 PU21_BANDING_GLARE = [234.0235618, 216.9339286, 0.0001091864237, 0.893206924, 0.06733984121, 1.444718567, 567.6315065]  # utils.py:175
 
@@ -43,14 +45,47 @@ class pu_psnr:
         return self.predict_video_source(vs, fixation_point=fixation_point, frame_padding=frame_padding)
 
     def predict_video_source(self, vid_source, fixation_point=None, frame_padding="replicate"):
-        _, _, N_frames = vid_source.get_video_size()
+        height, width, N_frames = vid_source.get_video_size()
         N_frames = int(N_frames)
         dev = self.device
+        spec = photometry_kernel_spec(vid_source.dm_photometry) if is_array_source(vid_source) else None
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             acc = torch.zeros(N_frames, dtype=torch.float64, device=dev)
             n = 0
-            for ff in range(N_frames):
+            if spec is not None:
+                # array source with a stock display model: whole blocks of frames in one launch, read in their own dtype and
+                # layout (EOTF, RGB -> Y and PU21 in the kernel; no luminance frames, no per-frame torch arithmetic)
+                frames = _FrameSet(vid_source, dev, True)
+                fmt = _native.FrameFormat()
+                fmt.width, fmt.height = int(width), int(height)
+                fmt.in_dtype, fmt.in_channels = _DTYPES[frames.dtype], 3 if vid_source.is_color else 1
+                fmt.eotf = _native.EOTF_CODES[spec["kind"]]
+                fmt.Y_peak, fmt.Y_black = spec.get("Y_peak", 0.0), spec.get("Y_black", 0.0)
+                fmt.gamma, fmt.L_min, fmt.L_max = spec.get("gamma", 2.2), spec.get("L_min", 0.0), spec.get("L_max", 0.0)
+                w = vid_source.color_to_luminance if vid_source.is_color else [1.0, 0.0, 0.0]
+                for i in range(3):
+                    fmt.rgb2y[i] = float(w[i])
+                first = getattr(vid_source, "first_frame", 0)
+                B = 32
+                for f0 in range(0, N_frames, B):
+                    idx = list(range(f0, min(N_frames, f0 + B)))
+                    frames.fetch_all(idx)
+                    ready = frames.uploaded()
+                    if ready is not None:
+                        torch.cuda.current_stream(dev).wait_event(ready)
+                    tp, rp = frames.block_pointers(idx)
+                    _native.pu_sq_err_frames(fmt, tp, rp, frames.strides, self._params, acc.data_ptr() + 8 * f0, dev.index, stream)
+                    scored = None
+                    if frames.up_stream is not None:
+                        scored = torch.cuda.Event()
+                        scored.record(torch.cuda.current_stream(dev))
+                    frames.retain_only(set(), scored)
+                n = int(height) * int(width)
+                N_loop = 0
+            else:
+                N_loop = N_frames
+            for ff in range(N_loop):
                 T = vid_source.get_test_frame(ff, device=dev).to(device=dev, dtype=torch.float32).contiguous()
                 R = vid_source.get_reference_frame(ff, device=dev).to(device=dev, dtype=torch.float32).contiguous()
                 n = T.numel()

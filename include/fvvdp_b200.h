@@ -187,6 +187,25 @@ typedef struct fvvdp_b200_pu_params {
 int fvvdp_b200_pu_sq_err(const float* lum_test, const float* lum_ref, int64_t n, const fvvdp_b200_pu_params* params,
                          double* sq_err_acc, int cuda_device, void* cuda_stream);
 
+/*
+ * PU21-PSNR for a block of frames in ONE launch, straight from the frames as the user holds them (replaces the per-frame loop
+ * of pupsnr.py:52-79 incl. get_test_frame/get_reference_frame -> display_photometry.forward, video_source.py:180-208):
+ * sample -> [0,1] -> display EOTF -> RGB2Y -> PU21 of both streams -> squared difference, sq_err_out[i] (DEVICE double, zeroed
+ * by the caller) += the sum over frame i.  Frames are DEVICE pointers with the element strides of score_block; n_frames <=
+ * FVVDP_B200_MAX_SLOTS per call.
+ */
+typedef struct fvvdp_b200_frame_format {
+  int32_t width, height;
+  int32_t in_dtype;           /* fvvdp_b200_dtype */
+  int32_t in_channels;        /* 1 or 3 */
+  int32_t eotf;               /* fvvdp_b200_eotf */
+  float Y_peak, Y_black, gamma, L_min, L_max;
+  float rgb2y[3];
+} fvvdp_b200_frame_format;
+int fvvdp_b200_pu_sq_err_frames(const fvvdp_b200_frame_format* fmt, const void* const* test_frames, const void* const* ref_frames,
+                                const int64_t strides[3], int n_frames, const fvvdp_b200_pu_params* params, double* sq_err_out,
+                                int cuda_device, void* cuda_stream);
+
 typedef struct fvvdp_b200_pool_params {
   float beta_sch, beta_tch, beta_t; /* Lp exponents over spatial bands, temporal channels, frames */
   float w_transient;                /* weight of the transient channel */
