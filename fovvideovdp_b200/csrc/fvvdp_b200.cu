@@ -29,6 +29,7 @@ struct fvvdp_b200_ctx {
   float* cell = nullptr;                       // fused: [n_bands][32][8] CSF cells over log2 Y
   CUtensorMap pmap[FVVDP_B200_MAX_LEVELS];     // fused: TMA descriptors of P[l] (2x + stream, y, slot), box = staged tile
   CUtensorMap pmap_ws[FVVDP_B200_MAX_LEVELS];  //   the same tensors with the staged-tile box of the warp-specialised kernel
+  int ws_th = 32, ws_rp = 7;                   //   its tile height / ring positions: ws (<= 8 taps) or ws16 (<= 16 taps)
   int ws_max_level = -1;                       // warp-specialised kernel on levels 0..ws_max_level (video, <= 8 taps, no debug outputs)
   int ntiles_used[FVVDP_B200_MAX_LEVELS] = {}; // tiles of the kernel that scored each level of the last block
   bool no_dup_skip = false;                    // A/B switch FVVDP_B200_NO_DUP_SKIP
@@ -182,13 +183,15 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
   int hh = cfg->height, ww = cfg->width;
   {
     // A/B switches, read once: FVVDP_B200_PATH=v1 (general kernels) | fused (no warp-specialised kernel);
-    // FVVDP_B200_WS_LEVELS=n (warp-specialised kernel on levels < n; default 1: on the pyramid levels it only ties the fused kernel)
+    // FVVDP_B200_WS_LEVELS=n (warp-specialised kernel on levels < n; default: level 0 only for windows of up to 8 taps, where it
+    // only ties the fused kernel on the pyramid levels, every level for 9..16 taps)
     const char* force = getenv("FVVDP_B200_PATH");
     c->fused = cfg->filter_len <= fused::MAXRING && !(force && strcmp(force, "v1") == 0);
     const bool ws_ok = c->fused && !(force && strcmp(force, "fused") == 0) && cfg->temp_ch == 2 && cfg->filter_len >= 2 &&
-                       cfg->filter_len <= ws::RP + 1 && !cfg->want_taps && !cfg->want_dmap;
+                       cfg->filter_len <= ws16::RP + 1 && !cfg->want_taps && !cfg->want_dmap;
+    if (cfg->filter_len > ws::RP + 1) { c->ws_th = ws16::TH; c->ws_rp = ws16::RP; }
     const char* wl = getenv("FVVDP_B200_WS_LEVELS");
-    c->ws_max_level = ws_ok ? (wl ? atoi(wl) - 1 : 0) : -1;
+    c->ws_max_level = ws_ok ? (wl ? atoi(wl) - 1 : (c->ws_rp == ws::RP ? 0 : FVVDP_B200_MAX_LEVELS)) : -1;
     c->no_dup_skip = getenv("FVVDP_B200_NO_DUP_SKIP") != nullptr;
   }
   const int tile_w = c->fused ? fused::TW : TW, tile_h = c->fused ? fused::TH : TH;
@@ -210,7 +213,7 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
       const cuuint64_t dims[3] = {(cuuint64_t)(2 * c->lw[l]), (cuuint64_t)c->lh[l], (cuuint64_t)(T + cfg->filter_len - 1)};
       const cuuint64_t str[2] = {(cuuint64_t)c->pitch[l] * 4, (cuuint64_t)c->lh[l] * c->pitch[l] * 4};
       if (!make_tile_map(&c->pmap[l], c->P[l], 3, dims, str, 2 * fused::LW) ||
-          !make_tile_map(&c->pmap_ws[l], c->P[l], 3, dims, str, 2 * ws::LW, ws::LH)) {
+          !make_tile_map(&c->pmap_ws[l], c->P[l], 3, dims, str, 2 * ws::LW, c->ws_th + 8)) {
         fail(nullptr, FVVDP_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed for pyramid level %d", l);
         free_ctx(c);
         return FVVDP_B200_ERR_CUDA;
@@ -335,6 +338,7 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
   }
   CUC(fused::configure_band_kernels());
   CUC(ws::configure_band_ws_kernels());
+  CUC(ws16::configure_band_ws_kernels());
   CUC(cudaFuncSetAttribute(level_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)level_smem_bytes(4)));
   CUC(cudaFuncSetAttribute(level_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)level_smem_bytes(4)));
   CUC(cudaFuncSetAttribute(level_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)level_smem_bytes(2)));
@@ -501,14 +505,14 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
           const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)((hi - lo) / g + 1)};
           const cuuint64_t str[2] = {(cuuint64_t)strides[1] * 4, (cuuint64_t)g};
           if (!make_tile_map(&bp.tmap[st], (const void*)lo, 3, dims, str, fused::LW)) l0_tma = false;
-          if (l0_tma && ctx->ws_max_level >= 0 && !make_tile_map(&bp.tmap_ws[st], (const void*)lo, 3, dims, str, ws::LW, ws::LH)) l0_tma = false;
+          if (l0_tma && ctx->ws_max_level >= 0 && !make_tile_map(&bp.tmap_ws[st], (const void*)lo, 3, dims, str, ws::LW, ctx->ws_th + 8)) l0_tma = false;
         }
       }
       (void)base; (void)step;
     }
     bp.n_frames = n_frames; bp.fl = fl;
     bp.ring_phase = (int)(((q_col0 - (fl - 1)) % ring_len + ring_len) % ring_len);  // slot 0 is the frame shown at time q_col0 - (fl-1)
-    bp.ring_phase_ws = (int)(((q_col0 - (fl - 1)) % ws::RP + ws::RP) % ws::RP);
+    bp.ring_phase_ws = (int)(((q_col0 - (fl - 1)) % ctx->ws_rp + ctx->ws_rp) % ctx->ws_rp);
     while (bp.dup_prefix + 1 < n_slots && test_slots[bp.dup_prefix + 1] == test_slots[0] && ref_slots[bp.dup_prefix + 1] == ref_slots[0]) bp.dup_prefix++;
     if (ctx->no_dup_skip) bp.dup_prefix = 0;  // A/B switch
     bp.sC = strides[0]; bp.sH = strides[1]; bp.sW = strides[2];
@@ -545,7 +549,7 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
       bp.h_odd = bp.h & 1;
       // the warp-specialised kernel (one CTA of 24 warps per SM, 32x64 tiles) where it applies; it stages with TMA only
       const bool use_ws = l <= ctx->ws_max_level && (l > 0 || l0_tma || !contig);
-      const int tx = use_ws ? (bp.w + ws::TW - 1) / ws::TW : ctx->tiles_x[l], ty = use_ws ? (bp.h + ws::TH - 1) / ws::TH : ctx->tiles_y[l];
+      const int tx = use_ws ? (bp.w + ws::TW - 1) / ws::TW : ctx->tiles_x[l], ty = use_ws ? (bp.h + ctx->ws_th - 1) / ctx->ws_th : ctx->tiles_y[l];
       const int tiles = tx * ty;
       bp.ntiles = tiles;
       ctx->ntiles_used[l] = tiles;
@@ -577,7 +581,7 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
           const cuuint64_t dims[3] = {(cuuint64_t)(2 * W), (cuuint64_t)H, (cuuint64_t)(ctx->T + cfg.filter_len - 1)};
           const cuuint64_t str[2] = {(cuuint64_t)ctx->pitch[0] * 4, (cuuint64_t)H * ctx->pitch[0] * 4};
           if (!make_tile_map(&ctx->pmap[0], ctx->P[0], 3, dims, str, 2 * fused::LW) ||
-              !make_tile_map(&ctx->pmap_ws[0], ctx->P[0], 3, dims, str, 2 * ws::LW, ws::LH)) return fail(ctx, FVVDP_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the luminance planes");
+              !make_tile_map(&ctx->pmap_ws[0], ctx->P[0], 3, dims, str, 2 * ws::LW, ctx->ws_th + 8)) return fail(ctx, FVVDP_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the luminance planes");
         }
         {
           ProfScope prof(ctx, 0, st);
@@ -594,7 +598,8 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
       if (l >= 1) { bp.tmap[0] = ctx->pmap[l]; bp.tmap_ws[0] = ctx->pmap_ws[l]; }
       dim3 grid(tx, ty, nchunks);
       ProfScope prof(ctx, 1 + l, st);
-      cudaError_t le2 = use_ws ? ws::launch_band_ws(kind, cfg.foveated != 0, bp, grid, st)
+      cudaError_t le2 = use_ws ? (ctx->ws_rp == ws::RP ? ws::launch_band_ws(kind, cfg.foveated != 0, bp, grid, st)
+                                                        : ws16::launch_band_ws(kind, cfg.foveated != 0, bp, grid, st))
                                : fused::launch_band(kind, mode, cfg.foveated != 0, extra, bp, grid, st);
       if (le2 != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "band_kernel[%d] launch: %s", l, cudaGetErrorString(le2));
       ctx->launches++;

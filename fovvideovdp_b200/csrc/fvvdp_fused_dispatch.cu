@@ -237,21 +237,24 @@ cudaError_t configure_band_kernels() {
 }  // namespace fused
 
 // ------------------------------------------------------------------------------------------------ warp-specialised kernels
-namespace ws {
-cudaError_t launch_band_ws_2(bool foveated, const fused::BandParams& p, dim3 grid, cudaStream_t st);
-cudaError_t launch_band_ws_3(bool foveated, const fused::BandParams& p, dim3 grid, cudaStream_t st);
-cudaError_t configure_band_ws_2();
-cudaError_t configure_band_ws_3();
-
-cudaError_t launch_band_ws(int input_kind, bool foveated, const fused::BandParams& p, dim3 grid, cudaStream_t st) {
-  if (input_kind == fused::IN_PYRAMID_TMA) return launch_band_ws_2(foveated, p, grid, st);
-  if (input_kind == fused::IN_LEVEL0_TMA) return launch_band_ws_3(foveated, p, grid, st);
-  return cudaErrorInvalidValue;
-}
-cudaError_t configure_band_ws_kernels() {
-  cudaError_t e = configure_band_ws_2();
-  return e != cudaSuccess ? e : configure_band_ws_3();
-}
-}  // namespace ws
+#define FVVDP_WS_DISPATCH(NS)                                                                                             \
+  namespace NS {                                                                                                           \
+  cudaError_t launch_band_ws_2(bool foveated, const fused::BandParams& p, dim3 grid, cudaStream_t st);                    \
+  cudaError_t launch_band_ws_3(bool foveated, const fused::BandParams& p, dim3 grid, cudaStream_t st);                    \
+  cudaError_t configure_band_ws_2();                                                                                       \
+  cudaError_t configure_band_ws_3();                                                                                       \
+  cudaError_t launch_band_ws(int input_kind, bool foveated, const fused::BandParams& p, dim3 grid, cudaStream_t st) {     \
+    if (input_kind == fused::IN_PYRAMID_TMA) return launch_band_ws_2(foveated, p, grid, st);                              \
+    if (input_kind == fused::IN_LEVEL0_TMA) return launch_band_ws_3(foveated, p, grid, st);                               \
+    return cudaErrorInvalidValue;                                                                                          \
+  }                                                                                                                        \
+  cudaError_t configure_band_ws_kernels() {                                                                                \
+    cudaError_t e = configure_band_ws_2();                                                                                 \
+    return e != cudaSuccess ? e : configure_band_ws_3();                                                                   \
+  }                                                                                                                        \
+  }
+FVVDP_WS_DISPATCH(ws)
+FVVDP_WS_DISPATCH(ws16)
+#undef FVVDP_WS_DISPATCH
 
 }  // namespace fvvdp

@@ -23,8 +23,17 @@
 #include "fvvdp_fused.cuh"
 #include "fvvdp_ws_geometry.h"
 
+#ifndef WS_TAPS16
+#define WS_TAPS16 0
+#endif
+#if WS_TAPS16
+#define WS_NS ws16
+#else
+#define WS_NS ws
+#endif
+
 namespace fvvdp {
-namespace ws {
+namespace WS_NS {
 
 using fused::BandParams;
 using fused::u64;
@@ -33,6 +42,7 @@ using fused::lds128; using fused::sts128; using fused::smem_u32; using fused::mb
 using fused::tma_load_3d; using fused::eotf8; using fused::eotf_checks_range; using fused::locate_direct;
 using fused::IN_PYRAMID_TMA; using fused::IN_LEVEL0_TMA; using fused::locate_smem;
 
+constexpr int PXT = TH / 8;                     // pixels per consumer thread: a 2x2 quad (32-row tiles) or one row of it (16-row tiles)
 constexpr int NH = TH / 2 + 2, NW = TW / 2 + 2; // reduced tile with 1-px halo: origin (jy0-1, jx0-1)
 constexpr int NE = NH * NW;                     // 612
 #ifndef WS_BACKOFF
@@ -71,7 +81,7 @@ constexpr int NCOL = (NE + NPT - 1) / NPT;      // 3
 constexpr int PLANE = LH * LW;                  // one stream of a landing buffer (floats)
 constexpr int TILE_FLOATS = 2 * PLANE;          // one staged tile, both streams (23040 bytes)
 constexpr int ROW_CP = LW / 2;                  // row pass: column pairs (36) x segments of ROW_SEG reduced rows
-constexpr int ROW_SEG = NPW >= 12 ? 2 : (NPW >= 8 ? 3 : 6);   // 324 / 216 / 108 threads
+constexpr int ROW_SEG = TH == 32 ? (NPW >= 12 ? 2 : (NPW >= 8 ? 3 : 6)) : (NPW >= 12 ? 1 : 2);   // NH / ROW_SEG segments x 36 column pairs <= NPT threads
 constexpr int ROW_THREADS = ROW_CP * (NH / ROW_SEG);  // 216 / 324
 
 template <int KIND, bool FOV>
@@ -90,8 +100,8 @@ struct Layout {
   static constexpr int oNc = oNr + RP * 2 * NE;              // [NLB][2][NE][2] temporally filtered reduced tiles
   static constexpr int oTab = oNc + NLB * 4 * NE;            // [32][8]
   static constexpr int oRed = oTab + 256;                    // [MAXCHUNK][2][NCW]
-  static constexpr int oFov = oRed + MAXCHUNK * 2 * NCW;     // FOV: float4 [4][NCT]
-  static constexpr int total = oFov + (FOV ? 4 * 4 * NCT : 0);
+  static constexpr int oFov = oRed + MAXCHUNK * 2 * NCW;     // FOV: float4 [PXT][NCT]
+  static constexpr int total = oFov + (FOV ? 4 * PXT * NCT : 0);
   static constexpr size_t bytes = sizeof(float) * (size_t)total;
   static_assert(bytes + 1024 <= 227 * 1024, "shared memory of one CTA");
 };
@@ -112,6 +122,38 @@ __device__ __forceinline__ void mbar_wait_backoff(unsigned bar, unsigned parity)
   mbar_wait(bar, parity);
 #endif
 }
+// switch over the ring position with one code version per position (J = compile-time position)
+#if WS_TAPS16
+#define FVVDP_RING_SWITCH(rp_, STMT)                                   \
+  switch (rp_) {                                                       \
+    case 0: { constexpr int J = 0; STMT; } break;                      \
+    case 1: { constexpr int J = 1; STMT; } break;                      \
+    case 2: { constexpr int J = 2; STMT; } break;                      \
+    case 3: { constexpr int J = 3; STMT; } break;                      \
+    case 4: { constexpr int J = 4; STMT; } break;                      \
+    case 5: { constexpr int J = 5; STMT; } break;                      \
+    case 6: { constexpr int J = 6; STMT; } break;                      \
+    case 7: { constexpr int J = 7; STMT; } break;                      \
+    case 8: { constexpr int J = 8; STMT; } break;                      \
+    case 9: { constexpr int J = 9; STMT; } break;                      \
+    case 10: { constexpr int J = 10; STMT; } break;                    \
+    case 11: { constexpr int J = 11; STMT; } break;                    \
+    case 12: { constexpr int J = 12; STMT; } break;                    \
+    case 13: { constexpr int J = 13; STMT; } break;                    \
+    default: { constexpr int J = 14; STMT; } break;                    \
+  }
+#else
+#define FVVDP_RING_SWITCH(rp_, STMT)                                   \
+  switch (rp_) {                                                       \
+    case 0: { constexpr int J = 0; STMT; } break;                      \
+    case 1: { constexpr int J = 1; STMT; } break;                      \
+    case 2: { constexpr int J = 2; STMT; } break;                      \
+    case 3: { constexpr int J = 3; STMT; } break;                      \
+    case 4: { constexpr int J = 4; STMT; } break;                      \
+    case 5: { constexpr int J = 5; STMT; } break;                      \
+    default: { constexpr int J = 6; STMT; } break;                     \
+  }
+#endif
 template <int ID, int COUNT>
 __device__ __forceinline__ void named_bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
 
@@ -146,10 +188,10 @@ __device__ __forceinline__ void eotf_chunk(unsigned raw, unsigned lum, bool insi
 //   sustained: ages 1..7 (all seven positions; the newest frame's tap is 1e-36 of the sum), transient: X and ages 1..6.
 // Then X replaces the oldest frame.
 template <int K, bool EMIT>
-__device__ __forceinline__ void ring_step(u64 (&ring)[RP][4], const u64 (&X)[4], const BandParams& p, u64 (&R)[2][4]) {
+__device__ __forceinline__ void ring_step(u64 (&ring)[RP][PXT], const u64 (&X)[PXT], const BandParams& p, u64 (&R)[2][PXT]) {
   if (EMIT) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < PXT; ++e) {
       u64 a0 = 0ull, a1 = fmul2(X[e], p.wext[1][0]);
 #pragma unroll
       for (int j = 0; j < RP; ++j) {
@@ -162,7 +204,7 @@ __device__ __forceinline__ void ring_step(u64 (&ring)[RP][4], const u64 (&X)[4],
     }
   }
 #pragma unroll
-  for (int e = 0; e < 4; ++e) ring[K][e] = X[e];
+  for (int e = 0; e < PXT; ++e) ring[K][e] = X[e];
 }
 
 // the producers' filter of one reduced-tile element: ring positions in shared memory (this thread's own element), v = newest
@@ -346,12 +388,7 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
           } else {
             if (emit) {
               u64 r0, r1;
-              switch (rp) {
-#define FVVDP_CASE(J) case J: coarse_step<J>(ring_o, ov, p, r0, r1); break;
-                FVVDP_CASE(0) FVVDP_CASE(1) FVVDP_CASE(2) FVVDP_CASE(3) FVVDP_CASE(4) FVVDP_CASE(5)
-                default: coarse_step<6>(ring_o, ov, p, r0, r1); break;
-#undef FVVDP_CASE
-              }
+              FVVDP_RING_SWITCH(rp, (coarse_step<J>(ring_o, ov, p, r0, r1)))
               *reinterpret_cast<u64*>(nc + 2 * o) = r0;
               *reinterpret_cast<u64*>(nc + 2 * NE + 2 * o) = r1;
             }
@@ -466,21 +503,22 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
   const int tile = by * gridDim.x + bx;
   // the quad of this thread
-  const int qa = warp, qb = lane;
-  const int qy = ty0 + 2 * qa, qx = tx0 + 2 * qb;
-  const int coff = 2 * ((4 + 2 * qa) * LW + 4 + 2 * qb);   // first pixel in the luminance tile (floats)
+  // (32-row tiles: warp = quad row; 16-row tiles: two warps per quad row, `half` selects the pixel row of the quad)
+  const int qa = PXT == 4 ? warp : (warp >> 1), qb = lane, half = PXT == 4 ? 0 : (warp & 1);
+  const int qy = ty0 + 2 * qa + half, qx = tx0 + 2 * qb;
+  const int coff = 2 * ((4 + 2 * qa + half) * LW + 4 + 2 * qb);   // first pixel in the luminance tile (floats)
   const int noff = 2 * (qa * NW + qb);                     // top-left of its 3x3 coarse neighbourhood
   const bool tile_full = (ty0 + TH <= h) && (tx0 + TW <= w);
-  bool valid[4];
+  bool valid[PXT];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) valid[e] = (qy + (e >> 1) < h) && (qx + (e & 1) < w);
+  for (int e = 0; e < PXT; ++e) valid[e] = (qy + (PXT == 4 ? (e >> 1) : 0) < h) && (qx + (e & 1) < w);
 
   if (FOV) {
     // per-pixel constants of the time walk: view direction and the rho cell / fraction of the CSF look-up
     // (rho = rho_band * resolution magnification, fvvdp.py:436-438)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int x = min(qx + (e & 1), w - 1), y = min(qy + (e >> 1), h - 1);
+    for (int e = 0; e < PXT; ++e) {
+      const int x = min(qx + (e & 1), w - 1), y = min(qy + (PXT == 4 ? (e >> 1) : 0), h - 1);
       float vx, vy, rq;
       if (p.vmap != nullptr) {  // maps computed by a fvvdp_display_geometry subclass
         const long long po = (long long)y * w + x;
@@ -498,11 +536,11 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
     }
   }
 
-  u64 ring[RP][4];
+  u64 ring[RP][PXT];
 #pragma unroll
   for (int k = 0; k < RP; ++k)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) ring[k][e] = 0ull;
+    for (int e = 0; e < PXT; ++e) ring[k][e] = 0ull;
 
   // per-frame partial sums: one warp-shuffle butterfly per frame, one pass over the warps at the end.  The two channel sums
   // share the butterfly: after the first exchange the lower half-warp carries channel 0, the upper half channel 1.
@@ -523,44 +561,43 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
     if (!LANDING) mbar_wait(bar0 + 8 * lb, lpar);   // the tile itself was written by TMA
     mbar_wait_backoff(bar_full + 8 * lb, lpar);
     const float* sLb = sL + lb * TILE_FLOATS;
-    u64 X[4];
+    u64 X[PXT];
     {
-      const ulonglong2 r0 = *reinterpret_cast<const ulonglong2*>(sLb + coff), r1 = *reinterpret_cast<const ulonglong2*>(sLb + coff + 2 * LW);
-      X[0] = r0.x; X[1] = r0.y; X[2] = r1.x; X[3] = r1.y;
+      const ulonglong2 r0 = *reinterpret_cast<const ulonglong2*>(sLb + coff);
+      X[0] = r0.x; X[1] = r0.y;
+      if (PXT == 4) {
+        const ulonglong2 r1 = *reinterpret_cast<const ulonglong2*>(sLb + coff + 2 * LW);
+        X[PXT - 2] = r1.x; X[PXT - 1] = r1.y;
+      }
     }
     const bool emit = s >= f_lo + p.fl - 1;
-    u64 R[2][4];
+    u64 R[2][PXT];
     if (!emit) {
       if (i == 0 && dup > 0) {  // every ring position starts as the first frame
 #pragma unroll
         for (int k = 0; k < RP; ++k)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) ring[k][e] = X[e];
+          for (int e = 0; e < PXT; ++e) ring[k][e] = X[e];
       } else {
 #pragma unroll
         for (int k = 0; k < RP; ++k)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) ring[k][e] = (k == rp) ? X[e] : ring[k][e];
+          for (int e = 0; e < PXT; ++e) ring[k][e] = (k == rp) ? X[e] : ring[k][e];
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_empty + 8 * lb);
       rp = (rp + 1 == RP) ? 0 : rp + 1;
       continue;
     }
-    switch (rp) {
-#define FVVDP_CASE(J) case J: ring_step<J, true>(ring, X, p, R); break;
-      FVVDP_CASE(0) FVVDP_CASE(1) FVVDP_CASE(2) FVVDP_CASE(3) FVVDP_CASE(4) FVVDP_CASE(5)
-      default: ring_step<6, true>(ring, X, p, R); break;
-#undef FVVDP_CASE
-    }
+    FVVDP_RING_SWITCH(rp, (ring_step<J, true>(ring, X, p, R)))
     rp = (rp + 1 == RP) ? 0 : rp + 1;
     const int fi = s - (p.fl - 1);  // output frame
     if (pend_row >= 0) warp_sums(pend2, pend_row);  // the previous frame's sums (independent of everything around it)
 
     // ---- expand of the filtered coarse tile (both temporal channels) -> bands; then the buffers go back to the producers
     const u64 c01 = pk(0.1f, 0.1f), c08 = pk(0.8f, 0.8f), c05 = pk(0.5f, 0.5f), cm1 = pk(-1.0f, -1.0f);
-    u64 Bp[2][4];  // band (G_l - E), (test, reference)
-    float Lb[4];
+    u64 Bp[2][PXT];  // band (G_l - E), (test, reference)
+    float Lb[PXT];
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
       const float* n = sNc + lb * (4 * NE) + cc * (2 * NE) + noff;
@@ -569,16 +606,22 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
       for (int c = 0; c < 3; ++c) {
         const u64 n0 = *reinterpret_cast<const u64*>(n + 2 * c), n1 = *reinterpret_cast<const u64*>(n + 2 * (NW + c)),
                   n2 = *reinterpret_cast<const u64*>(n + 2 * (2 * NW + c));
-        ve[c] = ffma2(c08, n1, fmul2(c01, fadd2(n0, n2)));  // even row: taps 2K[0], 2K[2], 2K[4]
-        vo[c] = fmul2(c05, fadd2(n1, n2));                  // odd row:  taps 2K[1], 2K[3]
+        if (PXT == 4 || half == 0) ve[c] = ffma2(c08, n1, fmul2(c01, fadd2(n0, n2)));  // even row: taps 2K[0], 2K[2], 2K[4]
+        if (PXT == 4 || half == 1) vo[c] = fmul2(c05, fadd2(n1, n2));                  // odd row:  taps 2K[1], 2K[3]
       }
-      u64 E[4];
-      E[0] = ffma2(c08, ve[1], fmul2(c01, fadd2(ve[0], ve[2])));
-      E[1] = fmul2(c05, fadd2(ve[1], ve[2]));
-      E[2] = ffma2(c08, vo[1], fmul2(c01, fadd2(vo[0], vo[2])));
-      E[3] = fmul2(c05, fadd2(vo[1], vo[2]));
+      u64 E[PXT];
+      if (PXT == 4) {
+        E[0] = ffma2(c08, ve[1], fmul2(c01, fadd2(ve[0], ve[2])));
+        E[1] = fmul2(c05, fadd2(ve[1], ve[2]));
+        E[PXT - 2] = ffma2(c08, vo[1], fmul2(c01, fadd2(vo[0], vo[2])));
+        E[PXT - 1] = fmul2(c05, fadd2(vo[1], vo[2]));
+      } else {
+        if (half) { ve[0] = vo[0]; ve[1] = vo[1]; ve[2] = vo[2]; }
+        E[0] = ffma2(c08, ve[1], fmul2(c01, fadd2(ve[0], ve[2])));
+        E[1] = fmul2(c05, fadd2(ve[1], ve[2]));
+      }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < PXT; ++e) {
         Bp[cc][e] = ffma2(E[e], cm1, R[cc][e]);  // R - E, rounded once like the scalar subtraction
         if (cc == 0) Lb[e] = fmaxf(hi_of(E[e]), 0.1f);  // L_bkg = expanded sustained reference (:264-266)
       }
@@ -587,7 +630,7 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
     if (lane == 0) mbar_arrive(bar_empty + 8 * lb);
     if (!tile_full) {  // pixels outside the image: a zero band gives log2|T' - R'| = -inf and D^beta = 0
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
+      for (int e = 0; e < PXT; ++e)
         if (!valid[e]) { Bp[0][e] = 0ull; Bp[1][e] = 0ull; }
     }
 
@@ -598,7 +641,7 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
     //        beta log2 D = beta p log2|T' - R'| - beta log2(1 + M^q), capped at beta log2 1e4              (:593-595)
     u64 acc2 = 0ull;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < PXT; ++e) {
       const float lgL = fast_log2(Lb[e]);
       const float yq = fminf(lgL, p.lg_y_hi);
       u64 lS2;  // log2 S' of the two channels
@@ -664,5 +707,5 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
   }
 }
 
-}  // namespace ws
+}  // namespace ws / ws16
 }  // namespace fvvdp

@@ -1,5 +1,6 @@
 // Instantiations of the warp-specialised band kernel (fvvdp_ws.cuh).  Compiled once per input kind with
-// -DWS_KIND={2: pyramid planes, 3: contiguous float frames} (fused::InputKind) so that the units build in parallel.
+// -DWS_KIND={2: pyramid planes, 3: contiguous float frames} (fused::InputKind) and -DWS_TAPS16={0: windows of up to 8 taps,
+// 1: up to 16 taps} so that the units build in parallel.
 #ifndef WS_KIND
 #error "compile with -DWS_KIND"
 #endif
@@ -7,7 +8,7 @@
 #include "fvvdp_fused_launch.h"
 
 namespace fvvdp {
-namespace ws {
+namespace WS_NS {
 
 #define WS_CAT2(a, b) a##b
 #define WS_CAT(a, b) WS_CAT2(a, b)
@@ -25,5 +26,5 @@ cudaError_t WS_FN(configure_band_ws_)() {
   return cudaFuncSetAttribute(band_ws_kernel<WS_KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Layout<WS_KIND, false>::bytes);
 }
 
-}  // namespace ws
+}  // namespace ws / ws16
 }  // namespace fvvdp

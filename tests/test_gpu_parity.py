@@ -602,6 +602,12 @@ def test_kernel_paths_agree_with_reference(fv_mod, golden, monkeypatch, levels):
     t, r = synth_pair_numpy(5, 270, 480)
     jod, st = fv_mod.fvvdp(display_name="standard_fhd", temp_padding="pingpong").predict(torch.from_numpy(t).cuda(), torch.from_numpy(r).cuda(), frames_per_second=25)
     check_jod(jod, g["jod"])
+    for pad in ("replicate", "pingpong", "circular"):  # 15-tap windows: the 16x64-tile build of the warp-specialised kernel
+        g = golden(f"video_short_60fps_{pad}")
+        t, r = synth_pair_numpy(5, 270, 480)
+        jod, st = fv_mod.fvvdp(display_name="standard_fhd", temp_padding=pad).predict(torch.from_numpy(t).cuda(), torch.from_numpy(r).cuda(), frames_per_second=60)
+        check_jod(jod, g["jod"])
+        check_q(st["Q_per_ch"], g["Q_per_ch"])
     g = golden("full_4k_9f")
     t, r = synth_pair_torch(9, 2160, 3840, torch.device("cuda:0"))
     jod, st = fv_mod.fvvdp(display_name="standard_4k").predict(t, r, frames_per_second=30)

@@ -14,7 +14,9 @@ from fovvideovdp_b200.synthetic import synth_pair_torch
 dev = torch.device("cuda:0")
 cases = [(12, 270, 480, "replicate", 30, None), (12, 270, 480, "pingpong", 30, None), (12, 270, 480, "circular", 30, None),
          (20, 540, 960, "replicate", 30, None), (20, 540, 960, "pingpong", 24, 7), (16, 1080, 1920, "replicate", 30, None),
-         (9, 135, 240, "circular", 25, 4), (10, 2160, 3840, "replicate", 30, None), (10, 1081, 1922, "pingpong", 30, None)]
+         (9, 135, 240, "circular", 25, 4), (10, 2160, 3840, "replicate", 30, None), (10, 1081, 1922, "pingpong", 30, None),
+         (20, 270, 480, "replicate", 60, None), (20, 540, 960, "pingpong", 50, 6), (24, 1080, 1920, "circular", 60, None),
+         (10, 2160, 3840, "replicate", 60, None), (12, 1081, 1922, "pingpong", 60, 5)]
 worst = 0.0
 for (N, H, W, pad, fps, T) in cases:
     t, r = synth_pair_torch(N, H, W, dev)
