@@ -29,7 +29,7 @@ struct fvvdp_b200_ctx {
   float* cell = nullptr;                       // fused: [n_bands][32][8] CSF cells over log2 Y
   CUtensorMap pmap[FVVDP_B200_MAX_LEVELS];     // fused: TMA descriptors of P[l] (2x + stream, y, slot), box = staged tile
   CUtensorMap pmap_ws[FVVDP_B200_MAX_LEVELS];  //   the same tensors with the staged-tile box of the warp-specialised kernel
-  int ws_th = 32, ws_rp = 7;                   //   its tile height / ring positions: ws (<= 8 taps) or ws16 (<= 16 taps)
+  int ws_th = ws::TH, ws_rp = ws::RP;                   //   its tile height / ring positions: ws (<= 8 taps) or ws16 (<= 16 taps)
   int ws_max_level = -1;                       // warp-specialised kernel on levels 0..ws_max_level (video, <= 8 taps, no debug outputs)
   int ntiles_used[FVVDP_B200_MAX_LEVELS] = {}; // tiles of the kernel that scored each level of the last block
   bool no_dup_skip = false;                    // A/B switch FVVDP_B200_NO_DUP_SKIP

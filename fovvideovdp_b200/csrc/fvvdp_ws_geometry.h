@@ -17,7 +17,11 @@ struct BandParams;
   cudaError_t launch_band_ws(int input_kind, bool foveated, const fused::BandParams& p, dim3 grid, cudaStream_t st);      \
   cudaError_t configure_band_ws_kernels();                                                                                 \
   }
+#ifdef WS_TH16   /* experiment: the 8-tap build on 16-row tiles as well */
+FVVDP_WS_DECLARE(ws, 16, 7)
+#else
 FVVDP_WS_DECLARE(ws, 32, 7)
+#endif
 FVVDP_WS_DECLARE(ws16, 16, 15)
 #undef FVVDP_WS_DECLARE
 }  // namespace fvvdp

@@ -17,7 +17,7 @@ for spec in sys.argv[1:]:
     obj = os.path.join(d, "obj")
     shutil.rmtree(d, ignore_errors=True)
     os.makedirs(obj)
-    rebuild_all = "FUSED" in flags  # flags of the fused kernels: every unit is recompiled
+    rebuild_all = "FUSED" in flags or "WS_TH16" in flags  # flags that reach beyond the warp-specialised units: every unit is recompiled
     for f in os.listdir(main_obj):
         if not f.startswith("ws_") and not rebuild_all:
             shutil.copy2(os.path.join(main_obj, f), os.path.join(obj, f))
