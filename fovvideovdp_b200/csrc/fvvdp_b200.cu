@@ -220,7 +220,8 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
       }
     }
     if (l < c->n_bands) {
-      CUC(cudaMalloc(&c->partial[l], sizeof(float) * (size_t)T * 2 * c->tiles_x[l] * c->tiles_y[l]));
+      // the warp-specialised kernels keep one partial sum per consumer warp (16 per tile)
+      CUC(cudaMalloc(&c->partial[l], sizeof(float) * (size_t)T * 2 * c->tiles_x[l] * c->tiles_y[l] * (c->ws_max_level >= 0 ? 16 : 1)));
       if (cfg->want_taps) {
         CUC(cudaMalloc(&c->tapC[l], sizeof(float) * px * nch * T));
         CUC(cudaMalloc(&c->tapL[l], sizeof(float) * px * T));
@@ -548,11 +549,11 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
       bp.h = ctx->lh[l]; bp.w = ctx->lw[l]; bp.h2 = ctx->lh[l + 1]; bp.w2 = ctx->lw[l + 1];
       bp.h_odd = bp.h & 1;
       // the warp-specialised kernel (one CTA of 24 warps per SM, 32x64 tiles) where it applies; it stages with TMA only
-      const bool use_ws = l <= ctx->ws_max_level && (l > 0 || l0_tma || !contig);
+      const bool use_ws = l <= ctx->ws_max_level && (l > 0 || l0_tma || !contig) && cfg.foveated != 2;  // custom geometry maps: fused kernel
       const int tx = use_ws ? (bp.w + ws::TW - 1) / ws::TW : ctx->tiles_x[l], ty = use_ws ? (bp.h + ctx->ws_th - 1) / ctx->ws_th : ctx->tiles_y[l];
       const int tiles = tx * ty;
       bp.ntiles = tiles;
-      ctx->ntiles_used[l] = tiles;
+      ctx->ntiles_used[l] = use_ws ? tiles * 16 : tiles;
       // small levels: split the time walk so that the grid still fills the machine (each chunk re-walks fl-1 frames)
       int nchunks = ((use_ws ? 1 : 4) * 148 + tiles - 1) / tiles;
       const int max_chunks = (n_frames + 3) / 4;

@@ -90,7 +90,10 @@ struct Layout {
   // luminance / filtered-reduced-tile buffers (frames in flight between the roles).  The pyramid levels stage with TMA straight
   // into these buffers, AHEAD = NLB - 2 frames ahead: the buffer that is refilled was released two iterations ago, so the
   // thread that issues the copies never waits for the consumers
-  static constexpr int NLB = LANDING ? (FOV ? 2 : 3) : (FOV ? 3 : 4);   // what fits beside the foveation constants
+#ifndef WS_FOV_NLB
+#define WS_FOV_NLB 3   // measured: a third buffer (+8 %) beats the larger L1 that two buffers would leave for the CSF records
+#endif
+  static constexpr int NLB = LANDING ? (FOV ? WS_FOV_NLB : 3) : (FOV ? 3 : 4);
   static constexpr int AHEAD = LANDING ? 2 : NLB - 2;
   static constexpr int oL = 0;                               // [NLB][LH][LW][2]
   static constexpr int oRaw = oL + NLB * TILE_FLOATS;        // LANDING: [2][2 streams][LH][LW]
@@ -99,9 +102,9 @@ struct Layout {
   static constexpr int oNr = oV + NV * 2 * NH * LW;          // [RP][NE][2] ring of reduced tiles
   static constexpr int oNc = oNr + RP * 2 * NE;              // [NLB][2][NE][2] temporally filtered reduced tiles
   static constexpr int oTab = oNc + NLB * 4 * NE;            // [32][8]
-  static constexpr int oRed = oTab + 256;                    // [MAXCHUNK][2][NCW]
-  static constexpr int oFov = oRed + MAXCHUNK * 2 * NCW;     // FOV: float4 [PXT][NCT]
-  static constexpr int total = oFov + (FOV ? 4 * PXT * NCT : 0);
+  static constexpr int oFov = oTab + 256;                    // FOV: float2 [PXT][NCT] (rho fraction, rho cell), then the view
+  static constexpr int oView = oFov + (FOV ? 2 * PXT * NCT : 0);  //   direction of the tile's columns [TW] and rows [TH] (deg)
+  static constexpr int total = oView + (FOV ? TW + TH : 0);
   static constexpr size_t bytes = sizeof(float) * (size_t)total;
   static_assert(bytes + 1024 <= 227 * 1024, "shared memory of one CTA");
 };
@@ -233,8 +236,8 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
   float* sNr = smem + LY::oNr;
   float* sNc = smem + LY::oNc;
   float* sTab = smem + LY::oTab;
-  float* sRed = smem + LY::oRed;
-  float4* sFov = reinterpret_cast<float4*>(smem + LY::oFov);
+  float2* sFov = reinterpret_cast<float2*>(smem + LY::oFov);
+  float* sView = smem + LY::oView;
   __shared__ __align__(8) u64 bars[4 + 2 * 4 + 4];  // [0..3] tile landed (TMA), [4..7] full (producers -> consumers), [8..11] empty,
                                                     // [12..13] EOTF pass done, [14..15] row pass done (among the producer warps)
 
@@ -519,21 +522,20 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
 #pragma unroll
     for (int e = 0; e < PXT; ++e) {
       const int x = min(qx + (e & 1), w - 1), y = min(qy + (PXT == 4 ? (e >> 1) : 0), h - 1);
-      float vx, vy, rq;
-      if (p.vmap != nullptr) {  // maps computed by a fvvdp_display_geometry subclass
-        const long long po = (long long)y * w + x;
-        vx = __ldg(p.vmap + po); vy = __ldg(p.vmap + (long long)h * w + po); rq = __ldg(p.rqmap + po);
-      } else {
-        vx = __ldg(p.vx + x); vy = __ldg(p.vy + y);
-        const float va = fminf(sqrtf(vx * vx + vy * vy), 89.9f) * 0.017453292519943295f;
-        const float res_mag = p.res_k0 / (__cosf(va) * __cosf(va + p.res_delta_rad));
-        rq = fast_log2(fminf(fmaxf(p.rho_band * res_mag, p.ax.lo[0]), p.ax.hi[0]));
-      }
+      // stock display geometry only (the view direction separates into a column and a row term, fvvdp_display_model.py:498-510);
+      // the maps of a fvvdp_display_geometry subclass go through the fused kernel
+      const float vx = __ldg(p.vx + x), vy = __ldg(p.vy + y);
+      const float va = fminf(sqrtf(vx * vx + vy * vy), 89.9f) * 0.017453292519943295f;
+      const float res_mag = p.res_k0 / (__cosf(va) * __cosf(va + p.res_delta_rad));
+      const float rq = fast_log2(fminf(fmaxf(p.rho_band * res_mag, p.ax.lo[0]), p.ax.hi[0]));
       int ii;
       float fr;
       locate_direct(rq, p.ax.x[0], p.ax.inv[0], p.ax.x0[0], p.ax.inv_dx[0], ii, fr);
-      sFov[e * NCT + tid] = make_float4(vx, vy, fr, __int_as_float(ii * 1024));
+      sFov[e * NCT + tid] = make_float2(fr, __int_as_float(ii * 1024));
+      if (warp == 0 || (PXT == 2 && warp == 1)) sView[2 * qb + (e & 1)] = vx;              // the tile's columns (any quad row has them all)
+      if (lane == 0) sView[TW + 2 * qa + half + (PXT == 4 ? (e >> 1) : 0)] = vy;          // the tile's rows
     }
+    asm volatile("bar.sync 2, %0;" ::"n"(NCT) : "memory");  // the consumers' view-direction tables are complete
   }
 
   u64 ring[RP][PXT];
@@ -542,8 +544,9 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
 #pragma unroll
     for (int e = 0; e < PXT; ++e) ring[k][e] = 0ull;
 
-  // per-frame partial sums: one warp-shuffle butterfly per frame, one pass over the warps at the end.  The two channel sums
-  // share the butterfly: after the first exchange the lower half-warp carries channel 0, the upper half channel 1.
+  // per-frame partial sums: one warp-shuffle butterfly per frame, written per warp ([frame][channel][tile][warp]; final_kernel adds
+  // them in double precision).  The two channel sums share the butterfly: after the first exchange the lower half-warp carries
+  // channel 0, the upper half channel 1.
   u64 pend2 = 0ull;
   int pend_row = -1;
   auto warp_sums = [&](u64 a2, int row) {
@@ -551,7 +554,7 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
     float v = (up ? hi_of(a2) : lo_of(a2)) + __shfl_xor_sync(0xffffffffu, up ? lo_of(a2) : hi_of(a2), 16);
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((lane & 15) == 0) sRed[(row * 2 + (up ? 1 : 0)) * NCW + warp] = v;
+    if ((lane & 15) == 0) p.partial[((long long)((f_lo + row) * 2 + (up ? 1 : 0)) * p.ntiles + tile) * NCW + warp] = v;
   };
   int rp = rp_first, lb = 0;
   unsigned lpar = 0;
@@ -652,18 +655,18 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
         const ulonglong2 td = *reinterpret_cast<const ulonglong2*>(sTab + cj + 4);  // (t0, t1), (dt0, dt1)
         lS2 = ffma2(pk(fj, fj), td.y, td.x);
       } else {
-        const float4 fc = sFov[e * NCT + tid];
+        const float2 fc = sFov[e * NCT + tid];
         int jj, kk;
         float fy, fe;
         locate_smem(yq, sTab, p.ax.x0[1], p.ax.inv_dx[1], jj, fy);
-        const float ex = fc.x - p.gaze[fi][0], ey = fc.y - p.gaze[fi][1];
+        const float ex = sView[2 * qb + (e & 1)] - p.gaze[fi][0], ey = sView[TW + 2 * qa + half + (PXT == 4 ? (e >> 1) : 0)] - p.gaze[fi][1];
         const float ecc = fast_sqrt(fmaf(ex, ex, ey * ey));  // eccentricity [deg] (fvvdp.py:432)
         const float eq = fast_sqrt(fminf(fmaxf(ecc, p.ax.lo[2]), p.ax.hi[2]));
         locate_smem(eq, sTab + 64, p.ax.x0[2], p.ax.inv_dx[2], kk, fe);
         // trilinear look-up of both temporal channels: 4 (rho, ecc) corners, each record holds the Y entry and its step
-        const float4* v = p.lut4 + __float_as_int(fc.w) + kk * 32 + jj;
+        const float4* v = p.lut4 + __float_as_int(fc.y) + kk * 32 + jj;
         const float4 c00 = __ldg(v), c01v = __ldg(v + 32), c10 = __ldg(v + 1024), c11 = __ldg(v + 1056);
-        const float fr = fc.z;
+        const float fr = fc.x;
         float ls[2];
 #pragma unroll
         for (int c2 = 0; c2 < 2; ++c2) {
@@ -697,14 +700,6 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
     pend_row = fi - f_lo;
   }
   if (pend_row >= 0) warp_sums(pend2, pend_row);
-  named_bar_sync<2, NCT>();
-  for (int i = tid; i < (f_hi - f_lo) * 2; i += NCT) {
-    float v = 0.0f;
-#pragma unroll
-    for (int k = 0; k < NCW; ++k) v += sRed[i * NCW + k];
-    const int fi = f_lo + (i >> 1), cc = i & 1;
-    p.partial[((long long)fi * 2 + cc) * p.ntiles + tile] = v;
-  }
 }
 
 }  // namespace ws / ws16
