@@ -21,7 +21,7 @@ EXPORTS = ["fvvdp_b200_create", "fvvdp_b200_score_block", "fvvdp_b200_heatmap", 
            "fvvdp_b200_level_size", "fvvdp_b200_launch_count", "fvvdp_b200_traffic_model", "fvvdp_b200_destroy",
            "fvvdp_b200_last_error", "fvvdp_b200_abi_version", "fvvdp_b200_pool_jod",
            "fvvdp_b200_profile", "fvvdp_b200_profile_read", "fvvdp_b200_heatmap_visualize", "fvvdp_b200_set_foveation_maps",
-           "fvvdp_b200_yuv_to_luminance", "fvvdp_b200_pu_sq_err", "fvvdp_b200_pu_sq_err_frames"]
+           "fvvdp_b200_yuv_to_luminance", "fvvdp_b200_pu_sq_err", "fvvdp_b200_pu_sq_err_frames", "fvvdp_b200_score_block_yuv"]
 COLORMAPS = {"threshold": 0, "supra-threshold": 1}
 PROFILE_CLASSES = MAX_LEVELS + 2
 
@@ -182,6 +182,21 @@ class Context:
         rc = self._lib.fvvdp_b200_score_block(self.handle, tp, rp, st, int(n_frames), fx, C.c_void_p(q_ptr), int(q_stride),
                                               int(q_col0), C.c_void_p(flags_ptr) if flags_ptr else None, C.c_void_p(stream))
         self._check(rc, "fvvdp_b200_score_block")
+
+    def score_block_yuv(self, desc, test_ptrs, ref_ptrs, n_frames, fixation_xy, q_ptr, q_stride, q_col0, stream):
+        """score_block for device copies of raw planar Y'CbCr frames (file layout) of the window slots."""
+        n = len(test_ptrs)
+        assert n == len(ref_ptrs)
+        tp = (C.c_void_p * n)(*test_ptrs)
+        rp = (C.c_void_p * n)(*ref_ptrs)
+        fx = None
+        if fixation_xy is not None:
+            flat = [float(v) for xy in fixation_xy for v in xy]
+            fx = (C.c_float * len(flat))(*flat)
+        self._lib.fvvdp_b200_score_block_yuv.restype = C.c_int
+        rc = self._lib.fvvdp_b200_score_block_yuv(self.handle, C.byref(desc), tp, rp, C.c_int(int(n_frames)), fx, C.c_void_p(q_ptr),
+                                                  C.c_int64(int(q_stride)), C.c_int64(int(q_col0)), C.c_void_p(stream))
+        self._check(rc, "fvvdp_b200_score_block_yuv")
 
     def heatmap(self, frame, beta_jod, jod_a_abs, out_ptr, stream):
         self._check(self._lib.fvvdp_b200_heatmap(self.handle, int(frame), float(beta_jod), float(jod_a_abs), C.c_void_p(out_ptr),

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <new>
 #include <vector>
 
@@ -442,9 +443,25 @@ extern "C" int fvvdp_b200_set_foveation_maps(fvvdp_b200_ctx* ctx, int level, con
   return FVVDP_B200_OK;
 }
 
-extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* test_slots, const void* const* ref_slots,
-                                      const int64_t strides[3], int n_frames, const float* fixation_xy, float* q_out,
-                                      int64_t q_stride, int64_t q_col0, uint32_t* flags_out, void* cuda_stream) {
+static void fill_yuv_params(const fvvdp_b200_yuv_desc* d, YuvParams& p) {
+  memset(&p, 0, sizeof(p));
+  p.W = d->width; p.H = d->height;
+  p.is420 = d->chroma_420 ? 1 : 0;
+  p.cw = p.is420 ? d->width / 2 : d->width; p.ch = p.is420 ? d->height / 2 : d->height;
+  p.is16 = d->bit_depth > 8;
+  const float scale = (float)(1 << (d->bit_depth - 8));
+  p.wy = 1.0f / (scale * 219.0f); p.oy = 16.0f / 219.0f;    // fixed2float, video_source_yuv.py:198-212
+  p.wc = 1.0f / (scale * 224.0f); p.oc = 128.0f / 224.0f;
+  for (int i = 0; i < 9; ++i) p.m[i] = d->ycbcr2rgb[i];
+  p.eotf = d->eotf;
+  p.Yscale = d->Y_peak - d->Y_black; p.Y_black = d->Y_black; p.Y_peak = d->Y_peak; p.gamma = d->gamma; p.L_min = d->L_min; p.L_max = d->L_max;
+  for (int i = 0; i < 3; ++i) p.rgb2y[i] = d->rgb2y[i];
+}
+
+// score_block for array frames (yuv == nullptr) or for DEVICE copies of raw planar Y'CbCr frames as stored in a .yuv file
+static int score_block_impl(fvvdp_b200_ctx* ctx, const void* const* test_slots, const void* const* ref_slots, const int64_t strides[3],
+                            int n_frames, const float* fixation_xy, float* q_out, int64_t q_stride, int64_t q_col0, uint32_t* flags_out,
+                            void* cuda_stream, const fvvdp_b200_yuv_desc* yuv) {
   if (!ctx) return FVVDP_B200_ERR_INVALID;
   const fvvdp_b200_config& cfg = ctx->cfg;
   if (!test_slots || !ref_slots || !strides || !q_out) return fail(ctx, FVVDP_B200_ERR_INVALID, "null argument");
@@ -472,7 +489,7 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
       bp.slot[1][s] = ref_slots[s];
       aligned = aligned && (((uintptr_t)test_slots[s] | (uintptr_t)ref_slots[s]) % 16 == 0);
     }
-    const bool contig = cfg.in_dtype == FVVDP_B200_F32 && cfg.in_channels == 1 && strides[2] == 1 && aligned && W % 4 == 0 &&
+    const bool contig = !yuv && cfg.in_dtype == FVVDP_B200_F32 && cfg.in_channels == 1 && strides[2] == 1 && aligned && W % 4 == 0 &&
                         strides[1] % 4 == 0 && strides[1] >= W && strides[1] * (int64_t)H < (1ll << 31);
     const int mode = cfg.temp_ch == 2 ? (fl > fused::RING ? 2 : 1) : 0;
     const int ring_len = mode == 2 ? fused::MAXRING : fused::RING;
@@ -584,7 +601,32 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
           if (!make_tile_map(&ctx->pmap[0], ctx->P[0], 3, dims, str, 2 * fused::LW) ||
               !make_tile_map(&ctx->pmap_ws[0], ctx->P[0], 3, dims, str, 2 * ws::LW, ctx->ws_th + 8)) return fail(ctx, FVVDP_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the luminance planes");
         }
-        {
+        if (yuv) {
+          // planar Y'CbCr frames: unpack, chroma upsampling, Y'CbCr -> R'G'B', display EOTF, RGB -> Y for the window slots of both
+          // streams in one launch, straight into the (test, reference) planes level 0 stages by TMA
+          ProfScope prof(ctx, 0, st);
+          YuvBlockParams yp;
+          memset(&yp, 0, sizeof(yp));
+          fill_yuv_params(yuv, yp.f);
+          for (int s = 0; s < n_slots; ++s) {
+            yp.frame[0][s] = test_slots[s]; yp.frame[1][s] = ref_slots[s];
+            yp.skip[s] = 0;  // (repeats of slot 0 are converted too: time chunks of small frames start their walk inside them)
+          }
+          yp.y_elems = (long long)W * H; yp.c_elems = (long long)yp.f.cw * yp.f.ch;
+          yp.out = ctx->P[0]; yp.slot_stride = (long long)H * ctx->pitch[0]; yp.pitch = ctx->pitch[0];
+          dim3 yg(((W + 1) / 2 + 31) / 32, (H + 7) / 8, n_slots);
+          switch (yuv->eotf) {
+            case FVVDP_B200_EOTF_NONE: yuv_planes_kernel<FVVDP_B200_EOTF_NONE><<<yg, 256, 0, st>>>(yp); break;
+            case FVVDP_B200_EOTF_SRGB: yuv_planes_kernel<FVVDP_B200_EOTF_SRGB><<<yg, 256, 0, st>>>(yp); break;
+            case FVVDP_B200_EOTF_GAMMA: yuv_planes_kernel<FVVDP_B200_EOTF_GAMMA><<<yg, 256, 0, st>>>(yp); break;
+            case FVVDP_B200_EOTF_PQ: yuv_planes_kernel<FVVDP_B200_EOTF_PQ><<<yg, 256, 0, st>>>(yp); break;
+            case FVVDP_B200_EOTF_LINEAR: yuv_planes_kernel<FVVDP_B200_EOTF_LINEAR><<<yg, 256, 0, st>>>(yp); break;
+            default: yuv_planes_kernel<FVVDP_B200_EOTF_ABSOLUTE><<<yg, 256, 0, st>>>(yp); break;
+          }
+          cudaError_t le1 = cudaGetLastError();
+          if (le1 != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "yuv_planes_kernel launch: %s", cudaGetErrorString(le1));
+          ctx->launches++;
+        } else {
           ProfScope prof(ctx, 0, st);
           // 4 pixels per thread with vector loads when rows are contiguous and every row / plane / frame starts aligned
           const bool vec_ok = strides[2] == 1 && aligned && strides[1] % 4 == 0 && (cfg.in_channels == 1 || strides[0] % 4 == 0);
@@ -606,6 +648,7 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
       ctx->launches++;
     }
   } else {
+  if (yuv) return fail(ctx, FVVDP_B200_ERR_INVALID, "raw .yuv frame blocks need a temporal window of at most %d taps", fused::MAXRING);
   // ---- K_front ----
   FrontParams fp;
   memset(&fp, 0, sizeof(fp));
@@ -733,6 +776,25 @@ extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* te
   return FVVDP_B200_OK;
 }
 
+extern "C" int fvvdp_b200_score_block(fvvdp_b200_ctx* ctx, const void* const* test_slots, const void* const* ref_slots,
+                                      const int64_t strides[3], int n_frames, const float* fixation_xy, float* q_out,
+                                      int64_t q_stride, int64_t q_col0, uint32_t* flags_out, void* cuda_stream) {
+  return score_block_impl(ctx, test_slots, ref_slots, strides, n_frames, fixation_xy, q_out, q_stride, q_col0, flags_out, cuda_stream, nullptr);
+}
+
+extern "C" int fvvdp_b200_score_block_yuv(fvvdp_b200_ctx* ctx, const fvvdp_b200_yuv_desc* desc, const void* const* test_frames,
+                                          const void* const* ref_frames, int n_frames, const float* fixation_xy, float* q_out,
+                                          int64_t q_stride, int64_t q_col0, void* cuda_stream) {
+  if (!ctx) return FVVDP_B200_ERR_INVALID;
+  if (!desc) return fail(ctx, FVVDP_B200_ERR_INVALID, "null argument");
+  if (desc->width != ctx->cfg.width || desc->height != ctx->cfg.height) return fail(ctx, FVVDP_B200_ERR_INVALID, "frame size %dx%d does not match the context (%dx%d)", desc->width, desc->height, ctx->cfg.width, ctx->cfg.height);
+  if (desc->bit_depth < 8 || desc->bit_depth > 16) return fail(ctx, FVVDP_B200_ERR_INVALID, "bit depth %d not in 8..16", desc->bit_depth);
+  if (desc->chroma_420 && ((desc->width | desc->height) & 1)) return fail(ctx, FVVDP_B200_ERR_INVALID, "4:2:0 frames need an even width and height");
+  if (desc->eotf < 0 || desc->eotf > 5) return fail(ctx, FVVDP_B200_ERR_INVALID, "Unknown EOTF %d", desc->eotf);
+  const int64_t strides[3] = {0, ctx->cfg.width, 1};
+  return score_block_impl(ctx, test_frames, ref_frames, strides, n_frames, fixation_xy, q_out, q_stride, q_col0, nullptr, cuda_stream, desc);
+}
+
 extern "C" int64_t fvvdp_b200_read_tap(fvvdp_b200_ctx* ctx, int tap, int level, int frame, float* dst, int64_t cap, void* cuda_stream) {
   if (!ctx) return FVVDP_B200_ERR_INVALID;
   if (!dst) return fail(ctx, FVVDP_B200_ERR_INVALID, "null destination");
@@ -836,19 +898,8 @@ extern "C" int fvvdp_b200_yuv_to_luminance(const fvvdp_b200_yuv_desc* d, const v
   if (d->eotf < 0 || d->eotf > 5) return fail(ctx, FVVDP_B200_ERR_INVALID, "Unknown EOTF %d", d->eotf);
   CU(cudaSetDevice(cuda_device));
   YuvParams p;
-  memset(&p, 0, sizeof(p));
+  fill_yuv_params(d, p);
   p.y = y_plane; p.u = u_plane; p.v = v_plane;
-  p.W = d->width; p.H = d->height;
-  p.is420 = d->chroma_420 ? 1 : 0;
-  p.cw = p.is420 ? d->width / 2 : d->width; p.ch = p.is420 ? d->height / 2 : d->height;
-  p.is16 = d->bit_depth > 8;
-  const float scale = (float)(1 << (d->bit_depth - 8));
-  p.wy = 1.0f / (scale * 219.0f); p.oy = 16.0f / 219.0f;    // fixed2float, video_source_yuv.py:198-212
-  p.wc = 1.0f / (scale * 224.0f); p.oc = 128.0f / 224.0f;
-  for (int i = 0; i < 9; ++i) p.m[i] = d->ycbcr2rgb[i];
-  p.eotf = d->eotf;
-  p.Yscale = d->Y_peak - d->Y_black; p.Y_black = d->Y_black; p.Y_peak = d->Y_peak; p.gamma = d->gamma; p.L_min = d->L_min; p.L_max = d->L_max;
-  for (int i = 0; i < 3; ++i) p.rgb2y[i] = d->rgb2y[i];
   p.lum = lum_out; p.rgb = rgb_out;
   dim3 grid(((d->width + 1) / 2 + 31) / 32, (d->height + 7) / 8);
   cudaStream_t st = (cudaStream_t)cuda_stream;

@@ -725,6 +725,74 @@ __global__ void __launch_bounds__(256) yuv_kernel(const YuvParams p) {
   }
 }
 
+// Block version for the metric: the window slots of BOTH streams in one launch, written as (test, reference) planes in the
+// pyramid layout ([slot][row][2 * column + stream]) so that level 0 of the band kernels stages them by TMA like any other level.
+// Frames are DEVICE copies of the file's frames as stored (Y plane, Cb plane, Cr plane).
+struct YuvBlockParams {
+  YuvParams f;                                    // format and display model (y / u / v / lum / rgb unused)
+  const void* frame[2][FVVDP_B200_MAX_SLOTS];     // [test|ref][slot]
+  unsigned char skip[FVVDP_B200_MAX_SLOTS];       // slots the band kernels never stage (repeats of the first frame)
+  long long y_elems, c_elems;                     // samples of the luma plane / of one chroma plane
+  float* out;                                     // [slot][H][pitch]
+  long long slot_stride;
+  int pitch;
+};
+
+template <int KIND>
+__device__ __forceinline__ void yuv_two_pixels(YuvParams p, int x, int y, float (&lum)[2]) {
+  float cb[2], cr[2];
+  if (p.is420) {
+    const float sy = fmaxf(0.5f * (float)y - 0.25f, 0.0f);
+    const int y0 = (int)sy, y1 = min(y0 + 1, p.ch - 1);
+    const float ly = sy - (float)y0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float sx = fmaxf(0.5f * (float)min(x + k, p.W - 1) - 0.25f, 0.0f);
+      const int x0 = (int)sx, x1 = min(x0 + 1, p.cw - 1);
+      const float lx = sx - (float)x0;
+      cb[k] = (1.0f - ly) * ((1.0f - lx) * yuv_chroma(p, p.u, y0, x0) + lx * yuv_chroma(p, p.u, y0, x1)) +
+              ly * ((1.0f - lx) * yuv_chroma(p, p.u, y1, x0) + lx * yuv_chroma(p, p.u, y1, x1));
+      cr[k] = (1.0f - ly) * ((1.0f - lx) * yuv_chroma(p, p.v, y0, x0) + lx * yuv_chroma(p, p.v, y0, x1)) +
+              ly * ((1.0f - lx) * yuv_chroma(p, p.v, y1, x0) + lx * yuv_chroma(p, p.v, y1, x1));
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      cb[k] = yuv_chroma(p, p.u, y, min(x + k, p.W - 1));
+      cr[k] = yuv_chroma(p, p.v, y, min(x + k, p.W - 1));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const long long i = (long long)y * p.W + min(x + k, p.W - 1);
+    const float Y = fminf(fmaxf(p.wy * yuv_sample(p.y, i, p.is16) - p.oy, 0.0f), 1.0f);
+    float rgb[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) rgb[c] = fminf(fmaxf(p.m[3 * c] * Y + p.m[3 * c + 1] * cb[k] + p.m[3 * c + 2] * cr[k], 0.0f), 1.0f);
+    lum[k] = yuv_eotf<KIND>(rgb[0], p) * p.rgb2y[0] + yuv_eotf<KIND>(rgb[1], p) * p.rgb2y[1] + yuv_eotf<KIND>(rgb[2], p) * p.rgb2y[2];
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) yuv_planes_kernel(const __grid_constant__ YuvBlockParams q) {
+  const int x = 2 * (blockIdx.x * 32 + (threadIdx.x & 31)), y = blockIdx.y * 8 + (threadIdx.x >> 5), slot = blockIdx.z;
+  if (x >= q.f.W || y >= q.f.H || q.skip[slot]) return;
+  float lum[2][2];
+#pragma unroll
+  for (int st = 0; st < 2; ++st) {
+    YuvParams p = q.f;
+    const char* base = reinterpret_cast<const char*>(q.frame[st][slot]);
+    const int esz = p.is16 ? 2 : 1;
+    p.y = base;
+    p.u = base + q.y_elems * esz;
+    p.v = base + (q.y_elems + q.c_elems) * esz;
+    yuv_two_pixels<KIND>(p, x, y, lum[st]);
+  }
+  float* o = q.out + slot * q.slot_stride + (long long)y * q.pitch + 2 * x;
+  if (x + 1 < q.f.W) *reinterpret_cast<float4*>(o) = make_float4(lum[0][0], lum[1][0], lum[0][1], lum[1][1]);
+  else *reinterpret_cast<float2*>(o) = make_float2(lum[0][0], lum[1][0]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K_pu: PU21-PSNR frame term (pupsnr.py:52-79, utils.py:157-202): sum over the frame of (PU(T) - PU(R))^2 with
 // PU(Y) = p6 (((p0 + p1 Y^p3) / (1 + p2 Y^p3))^p4 - p5), Y clipped to [L_min, L_max]

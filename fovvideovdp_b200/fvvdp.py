@@ -14,6 +14,7 @@ import ctypes
 import json
 import logging
 import math
+import os
 import threading
 
 import numpy as np
@@ -137,6 +138,32 @@ class _PinnedPool:
 
 
 _PINNED = _PinnedPool()
+
+
+class _PinnedBytesPool:
+    """Process-wide pool of pinned staging buffers for raw video frames, keyed by (elements, dtype)."""
+
+    def __init__(self, cap_bytes=4 << 30):
+        self.free, self.lock, self.cap, self.held = {}, threading.Lock(), cap_bytes, 0
+
+    def take(self, n, dtype):
+        with self.lock:
+            lst = self.free.get((n, dtype))
+            if lst:
+                buf = lst.pop()
+                self.held -= buf.numel() * buf.element_size()
+                return buf
+        return torch.empty(n, dtype=dtype, pin_memory=True)
+
+    def give(self, buf):
+        nbytes = buf.numel() * buf.element_size()
+        with self.lock:
+            if self.held + nbytes <= self.cap:
+                self.free.setdefault((buf.numel(), buf.dtype), []).append(buf)
+                self.held += nbytes
+
+
+_PINNED_BYTES = _PinnedBytesPool()
 
 
 class _LazyStats(dict):
@@ -341,6 +368,90 @@ class _FrameSet:
                 self.free.extend(((t, scored), (r, scored)))
 
 
+class _YuvFrames:
+    """Device copies of the raw frames of a fvvdp_video_source_yuv_file (file layout: Y plane, Cb plane, Cr plane), uploaded
+    block by block: worker threads copy the mem-mapped frames into pinned staging buffers, a copy stream moves them to the
+    device one block ahead of the kernels.  Same interface as _FrameSet as far as predict_video_source() uses it."""
+
+    def __init__(self, vid_source, device):
+        from concurrent.futures import ThreadPoolExecutor
+        self.readers = (vid_source.test_vidr, vid_source.reference_vidr)
+        self.device = device
+        self.raw, self.resident, self.strides = False, False, None
+        self.held, self.free, self.pinned = {}, [], []
+        self.h2d_bytes = 0
+        self.up_stream = torch.cuda.Stream(device=device)
+        self.pool = ThreadPoolExecutor(max_workers=8)
+        for rd in self.readers:
+            if rd.mm is None:
+                rd.mm = np.memmap(rd.file_name, rd.dtype, mode="r")
+        self.tdtype = torch.int16 if self.readers[0].dtype == np.uint16 else torch.uint8
+
+    def __del__(self):  # the staging buffers go back to the process-wide pool (pinning memory is far slower than copying into it)
+        try:
+            for buf, ev in self.pinned:
+                if ev is not None:
+                    ev.synchronize()
+                _PINNED_BYTES.give(buf)
+        except Exception:
+            pass
+
+    def _stage(self, which, idx):
+        """mem-mapped frame -> pinned staging buffer (runs in a worker thread; numpy releases the GIL for the copy)."""
+        reader = self.readers[which]
+        n = reader.frame_pixels
+        if self.pinned:
+            buf, ev = self.pinned.pop()
+            if ev is not None:
+                ev.synchronize()  # its previous upload has left the buffer
+        else:
+            buf = _PINNED_BYTES.take(n, self.tdtype)
+        o = int(idx) * n
+        np.copyto(buf.numpy().view(reader.dtype), reader.mm[o:o + n])
+        return buf
+
+    def fetch_all(self, indices):
+        todo = [i for i in dict.fromkeys(indices) if i not in self.held]
+        if not todo:
+            return
+        for i in todo:
+            if i < 0 or i >= self.readers[0].frame_count or i >= self.readers[1].frame_count:
+                raise RuntimeError("The frame index is outside the range of available frames")
+        staged = list(self.pool.map(lambda job: self._stage(*job), [(w, i) for i in todo for w in range(2)]))
+        with torch.cuda.stream(self.up_stream):
+            for k, i in enumerate(todo):
+                pair = []
+                for st in range(2):
+                    host = staged[2 * k + st]
+                    if self.free:
+                        dev, reusable = self.free.pop(0)
+                        if reusable is not None:
+                            self.up_stream.wait_event(reusable)
+                    else:
+                        dev = torch.empty(host.numel(), dtype=self.tdtype, device=self.device)
+                        self.up_stream.wait_stream(torch.cuda.current_stream(self.device))
+                    dev.copy_(host, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self.up_stream)
+                    self.pinned.append((host, ev))
+                    self.h2d_bytes += host.numel() * host.element_size()
+                    pair.append(dev)
+                self.held[i] = tuple(pair)
+
+    def uploaded(self):
+        ev = torch.cuda.Event()
+        ev.record(self.up_stream)
+        return ev
+
+    def block_pointers(self, indices):
+        return [self.held[i][0].data_ptr() for i in indices], [self.held[i][1].data_ptr() for i in indices]
+
+    def retain_only(self, keep, scored=None):
+        for idx in [k for k in self.held if k not in keep]:
+            t, r = self.held.pop(idx)
+            self.free.extend(((t, scored), (r, scored)))
+
+
 class fvvdp:
     def __init__(self, display_name="standard_4k", display_photometry=None, display_geometry=None, color_space="sRGB", foveated=False,
                  heatmap=None, quiet=False, device=None, temp_padding="replicate", use_checkpoints=False, block_frames=None,
@@ -509,7 +620,16 @@ class fvvdp:
         if is_array_source(vid_source):
             spec = photometry_kernel_spec(vid_source.dm_photometry)
         raw = spec is not None
-        frames = _FrameSet(vid_source, dev, raw)
+        # raw .yuv clips with a stock display model: the frames go to the device as stored and one kernel per block converts them
+        # into the planes level 0 stages (fvvdp_b200_score_block_yuv); resized clips / custom photometry: get_*_frame()
+        yuv_desc = None
+        if (type(vid_source).__name__ == "fvvdp_video_source_yuv_file" and type(vid_source).__module__.startswith("fovvideovdp_b200")
+                and getattr(vid_source, "_spec", None) is not None and vid_source.full_screen_resize is None and not is_image
+                and fl <= 16 and not self.debug_taps and not self.do_heatmap):
+            tr, rr = vid_source.test_vidr, vid_source.reference_vidr
+            if (tr.width, tr.height, tr.bit_depth, tr.chroma_ss, tr.color_space) == (rr.width, rr.height, rr.bit_depth, rr.chroma_ss, rr.color_space):
+                yuv_desc = tr._desc(vid_source._spec, vid_source.color_to_luminance)
+        frames = _YuvFrames(vid_source, dev) if yuv_desc is not None else _FrameSet(vid_source, dev, raw)
         if raw:
             C = 3 if vid_source.is_color else 1
             dtype = frames.dtype
@@ -589,8 +709,11 @@ class fvvdp:
                     fix = [fixation_point[f0 + i] if fixation_point.ndim == 2 else fixation_point for i in range(n)]
                     if custom_geo:  # gaze direction [deg] through the plugin (fvvdp.py:429-431)
                         fix = [self._gaze_direction(xy, width, height) for xy in fix]
-                ctx.score_block(test_ptrs, ref_ptrs, frames.strides, n, fix, Q_per_ch.data_ptr(), N_frames, f0,
-                                flags.data_ptr(), stream)
+                if yuv_desc is not None:
+                    ctx.score_block_yuv(yuv_desc, test_ptrs, ref_ptrs, n, fix, Q_per_ch.data_ptr(), N_frames, f0, stream)
+                else:
+                    ctx.score_block(test_ptrs, ref_ptrs, frames.strides, n, fix, Q_per_ch.data_ptr(), N_frames, f0,
+                                    flags.data_ptr(), stream)
                 if self.do_heatmap:
                     beta_jod = 10.0 ** self.log_jod_exp
                     for i in range(n):

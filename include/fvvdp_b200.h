@@ -176,6 +176,18 @@ int fvvdp_b200_yuv_to_luminance(const fvvdp_b200_yuv_desc* desc, const void* y_p
                                 float* lum_out, float* rgb_out, int cuda_device, void* cuda_stream);
 
 /*
+ * score_block for raw planar Y'CbCr clips: test_frames / ref_frames are DEVICE copies of the n_frames + filter_len - 1 window
+ * slots' frames exactly as stored in the .yuv file (Y plane, Cb plane, Cr plane; 8-bit or 16-bit little-endian samples).  One
+ * launch unpacks, upsamples the chroma planes, converts Y'CbCr -> R'G'B', applies the display EOTF and RGB -> Y for both streams
+ * (YUVReader.get_frame_rgb_tensor + fvvdp_video_source_yuv_file._get_frame, video_source_yuv.py:157-228,290-302) and writes the
+ * (test, reference) luminance planes level 0 of the metric stages by TMA; the rest is score_block.  The ctx is created with
+ * eotf = NONE, in_dtype = F32, in_channels = 1 and filter_len <= 16.
+ */
+int fvvdp_b200_score_block_yuv(fvvdp_b200_ctx* ctx, const fvvdp_b200_yuv_desc* desc, const void* const* test_frames,
+                               const void* const* ref_frames, int n_frames, const float* fixation_xy, float* q_out, int64_t q_stride,
+                               int64_t q_col0, void* cuda_stream);
+
+/*
  * PU21-PSNR (the reference CLI's second metric, pupsnr.py:52-79 with utils.PU, utils.py:157-202), ctx-free: adds
  * sum((PU(test) - PU(ref))^2) over `n` luminance samples (DEVICE floats, cd/m^2) to *sq_err_acc (DEVICE double, zeroed by
  * the caller).  The caller finishes a frame as 20 log10(peak / sqrt(acc / n)) and averages the frames.

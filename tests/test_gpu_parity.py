@@ -223,7 +223,8 @@ def test_yuv_video_source(fv_mod, golden, tmp_path, case):
     assert tuple(lum.shape) == (1, 1, 1, H, W)
     np.testing.assert_allclose(lum.cpu().numpy()[0, 0, 0], g["lum_test_f2"], rtol=5e-4, atol=2e-4)  # PQ amplifies the 1e-6 differences of the RGB stage
     fv = fv_mod.fvvdp(display_name=disp)
-    jod, st = fv.predict_video_source(vs)
+    jod, st = fv.predict_video_source(vs)   # block path: raw frames to the device, one conversion launch per block (score_block_yuv)
+    assert fv.last_run["h2d_bytes"] == 2 * 6 * t.shape[1] * t.itemsize
     check_jod(jod, g["jod"])
     check_q(st["Q_per_ch"], g["Q_per_ch"])
     # resized clip: RGB from the kernel, torch interpolate, display model through forward()
