@@ -206,8 +206,11 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
     const size_t px = (size_t)c->lh[l] * c->lw[l];
     // v1: 4-channel Gaussian levels of the temporal channels; the last level (base band) only lives in shared memory
     if (l < c->n_bands && (!c->fused || cfg->want_taps)) CUC(cudaMalloc(&c->G[l], sizeof(float) * px * nch * T));
-    // fused: 2-plane luminance pyramid per window slot; the row padding must stay zero (it is read as zero padding)
-    if (c->fused && l >= 1 && l < c->n_bands) {
+    // fused: 2-plane luminance pyramid per window slot; the row padding must stay zero (it is read as zero padding).  Level 0 has
+    // planes of its own when the input is known not to be contiguous single-channel float frames (uint8 / uint16 / RGB go
+    // through the luminance front end); strided float views and raw .yuv blocks get theirs on first use
+    const bool planes0 = l == 0 && (cfg->in_dtype != FVVDP_B200_F32 || cfg->in_channels != 1);
+    if (c->fused && ((l >= 1 && l < c->n_bands) || planes0)) {
       const size_t n = (size_t)(T + cfg->filter_len - 1) * c->lh[l] * c->pitch[l];
       CUC(cudaMalloc(&c->P[l], sizeof(float) * n));
       CUC(cudaMemset(c->P[l], 0, sizeof(float) * n));

@@ -671,7 +671,18 @@ class fvvdp:
         if self.do_heatmap:
             hm_ch = 1 if self.heatmap == "raw" else 3  # fvvdp.py:236
             heatmap = torch.zeros([1, hm_ch, N_frames, height, width], dtype=torch.float16, device="cpu")
-            hm_dev = torch.empty((hm_ch, height, width), dtype=torch.float16, device=dev)
+            # a ring of device / pinned staging planes: the device->host copy of frame j overlaps the kernels of frames j+1..j+3,
+            # the host copies a plane into the (pageable) result when its event has fired
+            HM_RING = 4
+            hm_dev = [torch.empty((hm_ch, height, width), dtype=torch.float16, device=dev) for _ in range(HM_RING)]
+            hm_pin = [_PINNED_BYTES.take(hm_ch * height * width, torch.float16).view(hm_ch, height, width) for _ in range(HM_RING)]
+            hm_ev, hm_frame, hm_count = [None] * HM_RING, [None] * HM_RING, 0
+
+            def hm_collect(k):
+                if hm_frame[k] is not None:
+                    hm_ev[k].synchronize()
+                    heatmap[0, :, hm_frame[k]].copy_(hm_pin[k])
+                    hm_frame[k] = None
         custom_geo = self.foveated and not geometry_is_stock(geo)
         if custom_geo:
             fov_maps = self._custom_foveation_maps(ctx, n_bands, freqs)  # kept alive until the end of this call
@@ -717,11 +728,17 @@ class fvvdp:
                 if self.do_heatmap:
                     beta_jod = 10.0 ** self.log_jod_exp
                     for i in range(n):
+                        k = hm_count % HM_RING
+                        hm_count += 1
+                        hm_collect(k)
                         if self.heatmap == "raw":
-                            ctx.heatmap(i, beta_jod, abs(self.jod_a), hm_dev.data_ptr(), stream)
+                            ctx.heatmap(i, beta_jod, abs(self.jod_a), hm_dev[k].data_ptr(), stream)
                         else:
-                            ctx.heatmap_visualize(i, beta_jod, abs(self.jod_a), self.heatmap, hm_dev.data_ptr(), stream)
-                        heatmap[0, :, f0 + i].copy_(hm_dev)
+                            ctx.heatmap_visualize(i, beta_jod, abs(self.jod_a), self.heatmap, hm_dev[k].data_ptr(), stream)
+                        hm_pin[k].copy_(hm_dev[k], non_blocking=True)
+                        hm_ev[k] = torch.cuda.Event()
+                        hm_ev[k].record(cur)
+                        hm_frame[k] = f0 + i
                 scored = None
                 if frames.up_stream is not None:
                     scored = torch.cuda.Event()
@@ -753,6 +770,9 @@ class fvvdp:
         stats["height"] = height
         stats["N_frames"] = N_frames
         if self.do_heatmap:
+            for k in range(HM_RING):
+                hm_collect(k)
+                _PINNED_BYTES.give(hm_pin[k].view(-1))
             stats["heatmap"] = heatmap
         return out[0], stats
 
