@@ -631,3 +631,21 @@ def test_sharded_clip_equals_single_gpu_nccl(fv_mod):
                         "29533", os.path.join(root, "tools", "check_sharding_nccl.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "MISMATCH" not in r.stdout
+
+
+def test_results_are_repeatable_bit_for_bit(fv_mod, monkeypatch):
+    """The warp roles of the warp-specialised kernels hand tiles over through mbarriers (which compute-sanitizer's racecheck does
+    not model): a missing hand-off would show as run-to-run differences.  Ten runs per configuration (every level on that kernel,
+    8- and 15-tap windows, warm-up walk of the rings, several tiles per SM) must give bit-identical per-frame energies."""
+    monkeypatch.setenv("FVVDP_B200_WS_LEVELS", "7")
+    dev = torch.device("cuda:0")
+    t, r = synth_pair_torch(24, 1080, 1920, dev)
+    for fps, pad in ((30, "pingpong"), (60, "circular"), (30, "replicate")):
+        fv = fv_mod.fvvdp(display_name="standard_fhd", temp_padding=pad, block_frames=9)
+        first = None
+        for _ in range(10):
+            jod, st = fv.predict(t, r, frames_per_second=fps)
+            q = st["Q_per_ch"].copy()
+            if first is None:
+                first = q
+            assert np.array_equal(q, first)
