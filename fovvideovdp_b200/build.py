@@ -13,6 +13,7 @@ HEADERS = [os.path.join(CSRC, h) for h in ("fvvdp_common.cuh", "fvvdp_kernels.cu
 # (object name, source, extra defines)
 UNITS = [("fvvdp_b200", "fvvdp_b200.cu", []), ("fused_dispatch", "fvvdp_fused_dispatch.cu", [])] + \
     [(f"fused_{k}_{v}", "fvvdp_fused_inst.cu", [f"-DFUSED_KIND={k}", f"-DFUSED_VIDEO={v}"]) for k in (0, 2, 3) for v in range(3)] + \
+    [("fused_2_3", "fvvdp_fused_inst.cu", ["-DFUSED_KIND=2", "-DFUSED_VIDEO=3"])] + \
     [(f"ws{'16' if t else ''}_{k}", "fvvdp_ws_inst.cu", [f"-DWS_KIND={k}", f"-DWS_TAPS16={t}"]) for k in (2, 3) for t in (0, 1)]
 DEPS = HEADERS + [os.path.join(CSRC, u[1]) for u in UNITS]
 OBJ_DIR = os.path.join(PKG, "_lib", "obj")

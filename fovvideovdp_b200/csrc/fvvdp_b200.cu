@@ -24,7 +24,8 @@ struct fvvdp_b200_ctx {
   int nch = 4, n_bands = 0, T = 1;
   int lh[FVVDP_B200_MAX_LEVELS], lw[FVVDP_B200_MAX_LEVELS];
   int tiles_x[FVVDP_B200_MAX_LEVELS], tiles_y[FVVDP_B200_MAX_LEVELS];
-  bool fused = false;                          // fused band kernels (filter_len <= 16) or the general v1 path
+  bool fused = false;                          // band kernels (fused / warp-specialised) or the general v1 path
+  bool ch2 = false;                            // band kernels on two filtered planes per slot (filter_len 17..32): front_kernel, pairs output
   float* P[FVVDP_B200_MAX_LEVELS] = {};        // fused: luminance pyramid, level >= 1: [slots][h_l][pitch_l], (test, ref) interleaved
   int pitch[FVVDP_B200_MAX_LEVELS] = {};
   float* cell = nullptr;                       // fused: [n_bands][32][8] CSF cells over log2 Y
@@ -187,7 +188,10 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
     // FVVDP_B200_WS_LEVELS=n (warp-specialised kernel on levels < n; default: level 0 only for windows of up to 8 taps, where it
     // only ties the fused kernel on the pyramid levels, every level for 9..16 taps)
     const char* force = getenv("FVVDP_B200_PATH");
-    c->fused = cfg->filter_len <= fused::MAXRING && !(force && strcmp(force, "v1") == 0);
+    const bool v1 = force && strcmp(force, "v1") == 0;
+    // windows of 17..32 taps: the filters run in a register-ring walk of their own and the band kernels take two planes per slot
+    c->ch2 = cfg->filter_len > fused::MAXRING && cfg->temp_ch == 2 && !cfg->want_taps && !cfg->want_dmap && !v1;
+    c->fused = (cfg->filter_len <= fused::MAXRING || c->ch2) && !v1;
     const bool ws_ok = c->fused && !(force && strcmp(force, "fused") == 0) && cfg->temp_ch == 2 && cfg->filter_len >= 2 &&
                        cfg->filter_len <= ws16::RP + 1 && !cfg->want_taps && !cfg->want_dmap;
     if (cfg->filter_len > ws::RP + 1) { c->ws_th = ws16::TH; c->ws_rp = ws16::RP; }
@@ -209,12 +213,13 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
     // fused: 2-plane luminance pyramid per window slot; the row padding must stay zero (it is read as zero padding).  Level 0 has
     // planes of its own when the input is known not to be contiguous single-channel float frames (uint8 / uint16 / RGB go
     // through the luminance front end); strided float views and raw .yuv blocks get theirs on first use
-    const bool planes0 = l == 0 && (cfg->in_dtype != FVVDP_B200_F32 || cfg->in_channels != 1);
+    const bool planes0 = l == 0 && (c->ch2 || cfg->in_dtype != FVVDP_B200_F32 || cfg->in_channels != 1);
+    const size_t plane_slots = c->ch2 ? 2 * (size_t)T : (size_t)(T + cfg->filter_len - 1);  // ch2: [2 temporal channels][T frames]
     if (c->fused && ((l >= 1 && l < c->n_bands) || planes0)) {
-      const size_t n = (size_t)(T + cfg->filter_len - 1) * c->lh[l] * c->pitch[l];
+      const size_t n = plane_slots * c->lh[l] * c->pitch[l];
       CUC(cudaMalloc(&c->P[l], sizeof(float) * n));
       CUC(cudaMemset(c->P[l], 0, sizeof(float) * n));
-      const cuuint64_t dims[3] = {(cuuint64_t)(2 * c->lw[l]), (cuuint64_t)c->lh[l], (cuuint64_t)(T + cfg->filter_len - 1)};
+      const cuuint64_t dims[3] = {(cuuint64_t)(2 * c->lw[l]), (cuuint64_t)c->lh[l], (cuuint64_t)plane_slots};
       const cuuint64_t str[2] = {(cuuint64_t)c->pitch[l] * 4, (cuuint64_t)c->lh[l] * c->pitch[l] * 4};
       if (!make_tile_map(&c->pmap[l], c->P[l], 3, dims, str, 2 * fused::LW) ||
           !make_tile_map(&c->pmap_ws[l], c->P[l], 3, dims, str, 2 * ws::LW, c->ws_th + 8)) {
@@ -416,12 +421,12 @@ extern "C" int fvvdp_b200_profile_read(fvvdp_b200_ctx* ctx, float* ms, int32_t* 
   return FVVDP_B200_OK;
 }
 
-template <int FL, int PX, bool CONTIG>
+template <int FL, int PX, bool CONTIG, bool PAIRS = false>
 static cudaError_t launch_front(const FrontParams& fp, cudaStream_t st) {
   const long long npx = (long long)fp.H * fp.W;
   const long long nthreads = (npx + PX - 1) / PX;
   const unsigned blocks = (unsigned)((nthreads + 255) / 256);
-  front_kernel<FL, PX, CONTIG><<<blocks, 256, 0, st>>>(fp);
+  front_kernel<FL, PX, CONTIG, PAIRS><<<blocks, 256, 0, st>>>(fp);
   return cudaGetLastError();
 }
 
@@ -494,7 +499,8 @@ static int score_block_impl(fvvdp_b200_ctx* ctx, const void* const* test_slots, 
     }
     const bool contig = !yuv && cfg.in_dtype == FVVDP_B200_F32 && cfg.in_channels == 1 && strides[2] == 1 && aligned && W % 4 == 0 &&
                         strides[1] % 4 == 0 && strides[1] >= W && strides[1] * (int64_t)H < (1ll << 31);
-    const int mode = cfg.temp_ch == 2 ? (fl > fused::RING ? 2 : 1) : 0;
+    const bool ch2 = ctx->ch2;
+    const int mode = ch2 ? 3 : (cfg.temp_ch == 2 ? (fl > fused::RING ? 2 : 1) : 0);
     const int ring_len = mode == 2 ? fused::MAXRING : fused::RING;
     for (int cc = 0; cc < cfg.temp_ch; ++cc)
       for (int i = 0; i < 2 * ring_len; ++i) {
@@ -531,10 +537,45 @@ static int score_block_impl(fvvdp_b200_ctx* ctx, const void* const* test_slots, 
       }
       (void)base; (void)step;
     }
-    bp.n_frames = n_frames; bp.fl = fl;
+    if (ch2) {
+      // ---- temporal filters of the frames (register-ring walk, every input sample read and converted once) -> two (test, ref)
+      //      planes per frame in the pyramid layout: P[0][temporal channel][frame]
+      FrontParams fp;
+      memset(&fp, 0, sizeof(fp));
+      for (int s = 0; s < n_slots; ++s) { fp.slot[0][s] = test_slots[s]; fp.slot[1][s] = ref_slots[s]; }
+      for (int cc = 0; cc < 2; ++cc)
+        for (int k = 0; k < 32; ++k) {
+          const int kk = k - (32 - fl);  // window position within the real filter, 0 = oldest
+          fp.wgt[cc][k] = kk >= 0 ? cfg.filt[cc][fl - 1 - kk] : 0.0f;  // corr_filter = F.flip(0), fvvdp.py:298
+        }
+      fp.R = ctx->P[0]; fp.pitch = ctx->pitch[0]; fp.pairs_slots = ctx->T;
+      fp.flags = flags_out;
+      fp.sC = strides[0]; fp.sH = strides[1]; fp.sW = strides[2];
+      fp.H = H; fp.W = W; fp.n_frames = n_frames; fp.fl = fl; fp.nch = 4; fp.C = cfg.in_channels;
+      fp.dtype = cfg.in_dtype; fp.eotf = cfg.eotf;
+      fp.Yscale = cfg.Y_peak - cfg.Y_black; fp.Y_black = cfg.Y_black; fp.Y_peak = cfg.Y_peak; fp.gamma = cfg.gamma;
+      fp.L_min = cfg.L_min; fp.L_max = cfg.L_max;
+      for (int i = 0; i < 3; ++i) fp.rgb2y[i] = cfg.rgb2y[i];
+      const bool fcontig = cfg.in_dtype == FVVDP_B200_F32 && cfg.in_channels == 1 && strides[2] == 1 && aligned;
+      ProfScope prof(ctx, 0, st);
+      for (int cc = 0; cc < 2; ++cc)
+        for (int a = 0; a < 32; ++a) fp.wage[cc][a] = a < fl ? cfg.filt[cc][a] : 0.0f;  // cfg.filt[cc][0] weighs the newest frame (corr_filter = F.flip(0), fvvdp.py:298)
+      fp.ring_phase = (int)(((q_col0 - (fl - 1)) % 32 + 32) % 32);  // slot 0 is the frame shown at time q_col0 - (fl-1)
+      {
+        const long long npx = (long long)H * W;
+        const unsigned blocks = (unsigned)((npx + 255) / 256);
+        if (fcontig) front_pairs_kernel<true><<<blocks, 256, 0, st>>>(fp);
+        else front_pairs_kernel<false><<<blocks, 256, 0, st>>>(fp);
+      }
+      cudaError_t lf = cudaGetLastError();
+      if (lf != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "front_kernel launch: %s", cudaGetErrorString(lf));
+      ctx->launches++;
+      bp.ch2_slots_in = bp.ch2_slots_out = ctx->T;
+    }
+    bp.n_frames = n_frames; bp.fl = ch2 ? 1 : fl;
     bp.ring_phase = (int)(((q_col0 - (fl - 1)) % ring_len + ring_len) % ring_len);  // slot 0 is the frame shown at time q_col0 - (fl-1)
     bp.ring_phase_ws = (int)(((q_col0 - (fl - 1)) % ctx->ws_rp + ctx->ws_rp) % ctx->ws_rp);
-    while (bp.dup_prefix + 1 < n_slots && test_slots[bp.dup_prefix + 1] == test_slots[0] && ref_slots[bp.dup_prefix + 1] == ref_slots[0]) bp.dup_prefix++;
+    while (!ch2 && bp.dup_prefix + 1 < n_slots && test_slots[bp.dup_prefix + 1] == test_slots[0] && ref_slots[bp.dup_prefix + 1] == ref_slots[0]) bp.dup_prefix++;
     if (ctx->no_dup_skip) bp.dup_prefix = 0;  // A/B switch
     bp.sC = strides[0]; bp.sH = strides[1]; bp.sW = strides[2];
     bp.C = cfg.in_channels; bp.dtype = cfg.in_dtype; bp.eotf = cfg.eotf;
@@ -592,8 +633,9 @@ static int score_block_impl(fvvdp_b200_ctx* ctx, const void* const* test_slots, 
       bp.tapG = cfg.want_taps ? ctx->G[l + 1] : nullptr;
       bp.tapC = ctx->tapC[l]; bp.tapL = ctx->tapL[l]; bp.tapS = ctx->tapS[l]; bp.tapD = ctx->tapD[l];
       bp.dmap = ctx->dmap[l];
-      int kind = l == 0 ? (l0_tma ? fused::IN_LEVEL0_TMA : fused::IN_LEVEL0_CPASYNC) : fused::IN_PYRAMID_TMA;
-      if (l == 0 && !contig) {
+      int kind = l == 0 && !ch2 ? (l0_tma ? fused::IN_LEVEL0_TMA : fused::IN_LEVEL0_CPASYNC) : fused::IN_PYRAMID_TMA;
+      if (l == 0 && ch2) { bp.tmap[0] = ctx->pmap[0]; bp.tmap_ws[0] = ctx->pmap_ws[0]; }
+      if (l == 0 && !contig && !ch2) {
         // any other input format: one luminance pass into planes laid out like the pyramid, then level 0 is TMA-staged too
         if (!ctx->P[0]) {
           const size_t n = (size_t)(ctx->T + cfg.filter_len - 1) * H * ctx->pitch[0];

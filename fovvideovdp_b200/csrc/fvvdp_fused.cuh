@@ -81,6 +81,7 @@ struct BandParams {
                                               //   the frame's index in the CLIP, so the summation order of the temporal filters (and
                                               //   with it every rounding) does not depend on how the clip is cut into blocks / ranks
   int ring_phase_ws;                          // the same for the 7-position rings of the warp-specialised kernel
+  int ch2_slots_in, ch2_slots_out;            // CH2 (see band_kernel): planes of temporal channel 1 start this many slots after channel 0's
   u64 wext[2][2 * MAXRING];                    // [temporal channel][i]: (w, w) packed weight of AGE (i mod ring length), 0 = newest frame;
                                               //   ring position j has age (rp - j) mod ring length when the newest frame sits at position rp: weight wext[rp + RL - j]
   // ---- level-0 input format ----
@@ -375,14 +376,21 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
   constexpr bool TMA = KIND == IN_PYRAMID_TMA || KIND == IN_LEVEL0_TMA;
   constexpr bool LANDING = KIND == IN_LEVEL0_TMA || KIND == IN_LEVEL0_CPASYNC;  // raw planes land first, the EOTF pass interleaves them
   constexpr int NLUM = KIND == IN_PYRAMID_TMA ? 2 : 1;  // the pyramid planes are interleaved in HBM: TMA lands them as luminance tiles
+  // CH2: temporal windows too long for the on-chip rings (17..32 taps).  The temporal filters are applied to the frames by a
+  // register-ring walk of their own (front_kernel, pairs output) and every slot arrives as TWO (test, reference) planes, the
+  // sustained and the transient channel; the kernel stages, reduces and writes out both (the reference's pyramid per temporal
+  // channel, fvvdp_lpyr_dec.py:248-273) and needs no ring.
+  constexpr bool CH2 = FL == 1 && TC == 2;
+  static_assert(!CH2 || KIND == IN_PYRAMID_TMA, "two-channel slots are staged from pyramid-layout planes");
+  constexpr int CHN = CH2 ? 2 : 1;
   constexpr int NCH = 2 * TC;
   extern __shared__ __align__(128) float smem[];
-  float* sL = smem;                                  // [NLUM][LH][LW][2]   luminance tile, (test, ref) interleaved
-  float* sRaw = sL + NLUM * TILE_FLOATS;             // LANDING: [2 buffers][2 streams][LH][LW]
-  float* sV = sRaw + (LANDING ? 2 * TILE_FLOATS : 0);  // [NH][LW][2]   row-reduced
-  float* sNr = sV + 2 * NH * LW;                     // [FL][NE][2]   ring of reduced tiles
+  float* sL = smem;                                  // [NLUM][CHN][LH][LW][2]   luminance tile, (test, ref) interleaved
+  float* sRaw = sL + NLUM * CHN * TILE_FLOATS;       // LANDING: [2 buffers][2 streams][LH][LW]
+  float* sV = sRaw + (LANDING ? 2 * TILE_FLOATS : 0);  // [CHN][NH][LW][2]   row-reduced
+  float* sNr = sV + CHN * 2 * NH * LW;               // [FL][NE][2]   ring of reduced tiles (CH2: the two channels' reduced tiles)
   float* sNc = (FL == 1) ? sNr : sNr + FL * 2 * NE;  // [TC][NE][2]   temporally filtered reduced tiles
-  float* sTab = sNr + FL * 2 * NE + (FL == 1 ? 0 : NCH * NE);  // [32][8]
+  float* sTab = sNr + (CH2 ? 2 : FL) * 2 * NE + (FL == 1 ? 0 : NCH * NE);  // [32][8]
   float* sRed = sTab + 256;                          // [MAXCHUNK][2][NT/32]
   float4* sFov = reinterpret_cast<float4*>(sRed + MAXCHUNK * 2 * (NT / 32));  // FOV: [PXT pixels][NT] (view x, view y, rho fraction, rho cell)
   __shared__ __align__(8) u64 bars[2];
@@ -422,7 +430,7 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
     reinterpret_cast<float4*>(sTab)[2 * tid] = a;
     reinterpret_cast<float4*>(sTab)[2 * tid + 1] = b;
   }
-  for (int i = tid; i < FL * 2 * NE; i += NT) sNr[i] = 0.0f;  // window positions that are never loaded must hold finite values
+  for (int i = tid; i < (CH2 ? 2 : FL) * 2 * NE; i += NT) sNr[i] = 0.0f;  // window positions that are never loaded must hold finite values
 
   // LANDING: the 4-pixel position chunks of this thread are chunk tid (and tid + NT): 16 * chunk bytes into a landing plane,
   // 32 * chunk bytes into the luminance tile.  ld_goff = element offset inside a frame, or -1 = outside the image.
@@ -507,9 +515,10 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
   auto issue_load = [&](int slot, int buf) {
     if (TMA) {
       if (tid == 0) {
-        mbar_expect_tx(bar0 + 8 * buf, TILE_FLOATS * 4);
+        mbar_expect_tx(bar0 + 8 * buf, CHN * TILE_FLOATS * 4);
         if (KIND == IN_PYRAMID_TMA) {
-          tma_load_3d(sL_u32 + buf * (TILE_FLOATS * 4), &p.tmap[0], bar0 + 8 * buf, 2 * (tx0 - 4), ty0 - 4, slot);
+          tma_load_3d(sL_u32 + buf * (CHN * TILE_FLOATS * 4), &p.tmap[0], bar0 + 8 * buf, 2 * (tx0 - 4), ty0 - 4, slot);
+          if (CH2) tma_load_3d(sL_u32 + (buf * CHN + 1) * (TILE_FLOATS * 4), &p.tmap[0], bar0 + 8 * buf, 2 * (tx0 - 4), ty0 - 4, slot + p.ch2_slots_in);
         } else {
           const unsigned dst = sRaw_u32 + buf * (TILE_FLOATS * 4);
           tma_load_3d(dst, &p.tmap[0], bar0 + 8 * buf, tx0 - 4, ty0 - 4, (int)p.slot_frame[0][slot]);
@@ -560,10 +569,12 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
     }
   };
   // stage B: reduce, rows: sV[a][c] = sum_k K[k] L[2j-2+k][c],  j = clamp(jy0-1+a)  (zero padding + edge terms)
-  auto rows_pass = [&](const float* sLb) {
+  auto rows_pass = [&](const float* sLb0, int ch) {
+    const float* sLb = sLb0 + ch * TILE_FLOATS;
+    float* sVc = sV + ch * (2 * NH * LW);
     if (tid < ROW_THREADS) {  // one thread walks down a third of one staged column, (test, ref) pairs
       const float* col = sLb + 2 * rw_c;
-      float* out = sV + 2 * rw_c;
+      float* out = sVc + 2 * rw_c;
       if (rows_interior) {  // no clamped coarse rows, no edge terms: sliding 5-row window
         const float* g = col + (2 * rw_a0) * (2 * LW);
         u64 g0 = *reinterpret_cast<const u64*>(g), g1 = *reinterpret_cast<const u64*>(g + 2 * LW), g2 = *reinterpret_cast<const u64*>(g + 4 * LW);
@@ -596,14 +607,15 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
   };
   // stage C: reduce, columns -> ring position rp (+ next level out); dup > 0: every ring position and `dup` further
   // pyramid slots get the same tile (repeats of the first frame)
-  auto cols_pass = [&](int s, int rp, int dup) {
+  auto cols_pass = [&](int s, int rp, int dup, int ch) {
     {
-      float* ring_s = sNr + rp * (2 * NE);
-      float* gout = (p.Pn != nullptr && s >= s_lo + ((bz > 0) ? p.fl - 1 : 0)) ? p.Pn + (long long)s * p.Pn_slot_stride : nullptr;
+      const float* sVc = sV + ch * (2 * NH * LW);
+      float* ring_s = sNr + (CH2 ? ch : rp) * (2 * NE);
+      float* gout = (p.Pn != nullptr && s >= s_lo + ((bz > 0) ? p.fl - 1 : 0)) ? p.Pn + (long long)(s + ch * p.ch2_slots_out) * p.Pn_slot_stride : nullptr;
 #pragma unroll
       for (int i = 0; i < NCOL; ++i) {
         if (i < NCOL - 1 || cl_src[i] >= 0) {  // only the last round is partial
-          const float* v = sV + (cl_src[i] & 0xFFFFFFF);
+          const float* v = sVc + (cl_src[i] & 0xFFFFFFF);
           const ulonglong2 v01 = *reinterpret_cast<const ulonglong2*>(v), v23 = *reinterpret_cast<const ulonglong2*>(v + 4);
           const u64 v4 = *reinterpret_cast<const u64*>(v + 8);
           u64 o = tap5(v01.x, v01.y, v23.x, v23.y, v4);
@@ -611,7 +623,7 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
             float ot = lo_of(o), orf = hi_of(o);
             if (cl_src[i] & (1 << 28)) { ot += K1 * v[4] + K0 * v[6]; orf += K1 * v[5] + K0 * v[7]; }
             if (cl_src[i] & (2 << 28)) {
-              const float* e = sV + ((cl_src[i] & 0xFFFFFFF) / (2 * LW)) * (2 * LW) + 2 * (w - 1 - tx0 + 4);  // y[w-1] of this row
+              const float* e = sVc + ((cl_src[i] & 0xFFFFFFF) / (2 * LW)) * (2 * LW) + 2 * (w - 1 - tx0 + 4);  // y[w-1] of this row
               // keyed on the ROW count, fvvdp_lpyr_dec.py:202
               ot += p.h_odd ? (K3 * e[0] + K4 * e[-2]) : K4 * e[0];
               orf += p.h_odd ? (K3 * e[1] + K4 * e[-1]) : K4 * e[1];
@@ -642,9 +654,9 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
       issue_load(0, 0);
       stage_tile(0, 0, false);
       __syncthreads();
-      rows_pass(sL);
+      rows_pass(sL, 0);
       __syncthreads();
-      cols_pass(0, 0, dup);
+      cols_pass(0, 0, dup, 0);
       // every ring position starts as the first frame: the repeats sit where the time loop would have put them, the
       // positions beyond the window carry zero weights
       ring_store<FL, 0>(ring, sL, coff);
@@ -671,16 +683,18 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
 
   for (int s = s_begin; s < s_hi; ++s) {
     const int buf = (s - s_begin) & 1;
-    const float* sLb = sL + (NLUM == 2 ? buf * TILE_FLOATS : 0);
+    const float* sLb = sL + (NLUM == 2 ? buf * CHN * TILE_FLOATS : 0);
     stage_tile(buf, ((s - s_begin) >> 1) & 1, s + 1 < s_hi);
     __syncthreads();  // (1) luminance tile of slot s complete; every reader of the buffers refilled below is done
     if (LANDING) { if (s + 2 < s_hi) issue_load(s + 2, buf); }
     else if (KIND == IN_PYRAMID_TMA) { if (s + 1 < s_hi) issue_load(s + 1, buf ^ 1); }
 
-    rows_pass(sLb);
+    rows_pass(sLb, 0);
+    if (CH2) rows_pass(sLb, 1);
     __syncthreads();  // (2)
     const int rp = (s + p.ring_phase) % FL;  // ring position of slot s
-    cols_pass(s, rp, 0);
+    cols_pass(s, rp, 0, 0);
+    if (CH2) cols_pass(s, rp, 0, 1);
 
     const bool emit = s >= f_lo + p.fl - 1;
     const int fi = s - (p.fl - 1);  // output frame
@@ -696,12 +710,25 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
 #endif
 #undef FVVDP_CASE
     }
+    u64 ring2[PXT];  // CH2: the thread's pixels of the second temporal channel
+    if (CH2) {
+      const ulonglong2 r0 = *reinterpret_cast<const ulonglong2*>(sLb + TILE_FLOATS + coff);
+      ring2[0] = r0.x; ring2[1] = r0.y;
+      if (PXT == 4) {
+        const ulonglong2 r1 = *reinterpret_cast<const ulonglong2*>(sLb + TILE_FLOATS + coff + 2 * LW);
+        ring2[PXT - 2] = r1.x; ring2[PXT - 1] = r1.y;
+      }
+    }
     if (NLUM == 1 || emit) __syncthreads();  // (3) filtered coarse tiles visible; the single luminance tile may be rewritten
     if (!emit) continue;
 
     // ---- temporal filter of the own pixels, expand of the filtered coarse tile, contrast, CSF, masking, pooling ----
     u64 R[TC][PXT];
     fir_quad<FL, TC>(ring, wp, R);
+    if (CH2) {
+#pragma unroll
+      for (int e = 0; e < PXT; ++e) R[TC - 1][e] = ring2[e];
+    }
     float acc[2] = {0.0f, 0.0f};
     float Lb[PXT], lgL[PXT], fj[PXT];
     int cj[PXT];
@@ -847,8 +874,9 @@ __global__ void __launch_bounds__(threads_of(FL), FL > RING ? 1 : 2) band_kernel
 template <int KIND, int FL, int TC, bool FOV>
 constexpr size_t band_smem_bytes() {
   constexpr int NT = threads_of(FL);
-  return (FOV ? sizeof(float4) * pixels_of(FL) * NT : 0) + sizeof(float) * (size_t)((KIND == IN_PYRAMID_TMA ? 2 : 1) * TILE_FLOATS + ((KIND == IN_LEVEL0_TMA || KIND == IN_LEVEL0_CPASYNC) ? 2 * TILE_FLOATS : 0) +
-                                  2 * NH * LW + FL * 2 * NE + (FL == 1 ? 0 : 2 * TC * NE) + 256 + MAXCHUNK * 2 * (NT / 32));
+  constexpr int CHN = (FL == 1 && TC == 2) ? 2 : 1;  // CH2: two planes per slot
+  return (FOV ? sizeof(float4) * pixels_of(FL) * NT : 0) + sizeof(float) * (size_t)((KIND == IN_PYRAMID_TMA ? 2 : 1) * CHN * TILE_FLOATS + ((KIND == IN_LEVEL0_TMA || KIND == IN_LEVEL0_CPASYNC) ? 2 * TILE_FLOATS : 0) +
+                                  CHN * 2 * NH * LW + (CHN == 2 ? 2 : FL) * 2 * NE + (FL == 1 ? 0 : 2 * TC * NE) + 256 + MAXCHUNK * 2 * (NT / 32));
 }
 
 }  // namespace fused

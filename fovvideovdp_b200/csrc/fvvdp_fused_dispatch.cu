@@ -10,11 +10,12 @@ namespace fused {
   cudaError_t launch_band_##k##_##v(bool foveated, bool extra, const BandParams& p, dim3 grid, cudaStream_t st); \
   cudaError_t configure_band_##k##_##v();
 #define DECL3(k) DECL(k, 0) DECL(k, 1) DECL(k, 2)
-DECL3(0) DECL3(2) DECL3(3)
+DECL3(0) DECL3(2) DECL3(3) DECL(2, 3)
 #undef DECL3
 #undef DECL
 
 cudaError_t launch_band(int kind, int mode, bool foveated, bool extra, const BandParams& p, dim3 grid, cudaStream_t st) {
+  if (mode == 3) return launch_band_2_3(foveated, extra, p, grid, st);  // two planes per slot: pyramid-layout planes only
   switch (kind * 3 + mode) {
 #define CASE(k, v) case (k) * 3 + (v): return launch_band_##k##_##v(foveated, extra, p, grid, st);
     CASE(0, 0) CASE(0, 1) CASE(0, 2) CASE(2, 0) CASE(2, 1) CASE(2, 2) CASE(3, 0) CASE(3, 1) CASE(3, 2)
@@ -229,7 +230,7 @@ cudaError_t launch_pu_frames(const BandParams& p, const void* pu_params, double*
 cudaError_t configure_band_kernels() {
   cudaError_t e;
 #define CONF(k, v) if ((e = configure_band_##k##_##v()) != cudaSuccess) return e;
-  CONF(0, 0) CONF(0, 1) CONF(0, 2) CONF(2, 0) CONF(2, 1) CONF(2, 2) CONF(3, 0) CONF(3, 1) CONF(3, 2)
+  CONF(0, 0) CONF(0, 1) CONF(0, 2) CONF(2, 0) CONF(2, 1) CONF(2, 2) CONF(3, 0) CONF(3, 1) CONF(3, 2) CONF(2, 3)
 #undef CONF
   return cudaSuccess;
 }

@@ -1,5 +1,6 @@
 // Instantiations of the fused band kernel.  Compiled once per (input kind, temporal mode) with
-// -DFUSED_KIND={0,2,3} (fused::InputKind) -DFUSED_VIDEO={0: image, 1: video with up to 8 taps, 2: video with up to 16 taps}
+// -DFUSED_KIND={0,2,3} (fused::InputKind) -DFUSED_VIDEO={0: image, 1: video with up to 8 taps, 2: video with up to 16 taps,
+// 3: video whose temporal channels arrive filtered, as two planes per slot (windows of 17..32 taps; FUSED_KIND=2 only)}
 // so that the nine translation units build in parallel.
 #ifndef FUSED_KIND
 #error "compile with -DFUSED_KIND and -DFUSED_VIDEO"
@@ -11,7 +12,7 @@
 namespace fvvdp {
 namespace fused {
 
-constexpr int kFL = FUSED_VIDEO == 2 ? MAXRING : (FUSED_VIDEO ? RING : 1);
+constexpr int kFL = FUSED_VIDEO == 2 ? MAXRING : (FUSED_VIDEO == 1 ? RING : 1);
 constexpr int kTC = FUSED_VIDEO ? 2 : 1;
 
 #define FUSED_CAT2(a, b, c) a##b##_##c

@@ -17,7 +17,10 @@ namespace fvvdp {
 struct FrontParams {
   const void* slot[2][FVVDP_B200_MAX_SLOTS];  // [test|ref][window slot] frame base pointers (device)
   float wgt[2][FVVDP_B200_MAX_FILTER_LEN];    // [channel][window position], position 0 = OLDEST frame
-  float* R;                                   // [n_frames][nch][H][W]
+  float* R;                                   // [n_frames][nch][H][W]; pairs output: [2 channels][pairs_slots][H][pitch], (test, ref) interleaved
+  int pitch, pairs_slots;                     // pairs output only (the planes the fused band kernel stages by TMA)
+  float wage[2][32];                          // front_pairs_kernel: weight of the frame of AGE a (0 = newest), 0 beyond the window
+  int ring_phase;                             //   slot s sits at ring position (s + ring_phase) mod 32: the position follows the index in the clip
   uint32_t* flags;
   long long sC, sH, sW;                       // element strides of the input frames
   int H, W, n_frames, fl, nch, C, dtype, eotf;
@@ -98,7 +101,7 @@ __device__ __forceinline__ void store_px(float* dst, const float (&v)[PX]) {
 // One thread owns PX consecutive pixels and walks the frames of the block keeping the last FL luminance
 // samples of both streams in a register ring (position of slot s is (s + FL - fl) % FL, all indices static
 // after unrolling).  Every input sample is read from HBM once per block and EOTF'd once.
-template <int FL, int PX, bool CONTIG>
+template <int FL, int PX, bool CONTIG, bool PAIRS = false>
 __global__ void __launch_bounds__(256) front_kernel(const __grid_constant__ FrontParams p) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long npx = (long long)p.H * p.W;
@@ -146,8 +149,116 @@ __global__ void __launch_bounds__(256) front_kernel(const __grid_constant__ Fron
               ar[e] = fmaf(win[1][(j + k) % FL][e], w, ar[e]);
             }
           }
-          store_px<PX>(dst + (cc * 2 + 0) * plane, at);
-          store_px<PX>(dst + (cc * 2 + 1) * plane, ar);
+          if (PAIRS) {  // (test, reference) pairs in the pyramid layout, one plane per temporal channel and frame
+            float* o = p.R + (((long long)cc * p.pairs_slots + i) * p.H + y) * p.pitch + 2 * x;
+#pragma unroll
+            for (int e = 0; e < PX; ++e) *reinterpret_cast<float2*>(o + 2 * e) = make_float2(at[e], ar[e]);
+          } else {
+            store_px<PX>(dst + (cc * 2 + 0) * plane, at);
+            store_px<PX>(dst + (cc * 2 + 1) * plane, ar);
+          }
+        }
+      }
+    }
+  }
+  if (oor && p.flags) atomicOr(p.flags, 1u);
+}
+
+// Temporal filters for windows of 17..32 taps, (test, reference) pairs: one thread owns one pixel of both streams and walks the
+// slots of the block with the last 31 luminance pairs in a register ring (62 registers; a window of fl taps needs fl - 1 stored
+// frames: the newest frame's sustained tap is 1e-36 of the sum and the oldest frame's transient tap is exactly 0, fvvdp.py:609-626).
+// The loop over the slots is unrolled by the ring length, so the ring position of a step is a compile-time constant and every
+// weight a uniform operand of its FFMA2; a frame sits at position (index in the clip) mod 31, so the summation order does not
+// depend on how the clip is cut into blocks.  Every input sample is read and converted once; the output is the two planes per frame
+// (sustained, transient) the two-channel band kernel stages by TMA.
+__device__ __forceinline__ unsigned long long fp_pk(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fp_ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long fp_fadd2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// The history of a pixel is a SHIFT REGISTER that moves once per FOUR steps: inside the four-times unrolled step the frame of age a
+// sits at hist[a + 3 - d] (d = step within the group), so every filter weight is an operand at a static constant-bank address
+// -- no loads, four code versions -- and the history is shifted by four positions (70 register moves) once per group.  The
+// summation order goes by age and does not depend on how the clip is cut into blocks.  Measured alternatives (64-frame 4K clip,
+// this kernel alone): the walk unrolled over 32 ring positions with uniform-register weights 12-15 ms (95-180 kB of code:
+// instruction-cache bound), rotating weights from register-indexed constant loads 13.9 ms or from shared-memory broadcasts 14.7 ms
+// (64 LDC / 128 shared-memory wavefronts per step and warp: load-issue bound), a shift per step 12.9 ms (62 moves per step, spills).
+__device__ __forceinline__ float eotf_front(float v, const FrontParams& p, bool& oor) {
+  if (p.eotf == FVVDP_B200_EOTF_SRGB) {  // the hot case without divisions (fvvdp_display_model.py:17-19)
+    oor |= (v > 1.0f) | (v < 0.0f);
+    const float t = __saturatef(fmaf(v, 1.0f / 1.055f, 0.055f / 1.055f));
+    const float lin = (v > 0.04045f) ? fast_exp2(2.4f * fast_log2(t)) : __saturatef(v * (1.0f / 12.92f));
+    return fmaf(p.Yscale, lin, p.Y_black);
+  }
+  return eotf_apply(v, p, oor);
+}
+template <bool CONTIG>
+__global__ void __launch_bounds__(256, 2) front_pairs_kernel(const __grid_constant__ FrontParams p) {
+  constexpr int NA = 32;  // ages kept: 0 (newest) .. 31
+  constexpr int PF = 4;   // steps per group = slots whose samples are in flight ahead of the one being filtered
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)p.H * p.W) return;
+  const int y = (int)(pix / p.W), x = (int)(pix % p.W);
+  float ht[NA + PF - 1], hr[NA + PF - 1];  // luminance history of the test / reference stream
+#pragma unroll
+  for (int k = 0; k < NA + PF - 1; ++k) ht[k] = hr[k] = 0.0f;
+  bool oor = false;
+  const int n_slots = p.n_frames + p.fl - 1;
+  float* out = p.R + (long long)y * p.pitch + 2 * x;
+  const long long frame_stride = (long long)p.H * p.pitch, chan_stride = (long long)p.pairs_slots * frame_stride;
+  const long long in_off = (long long)y * p.sH + x;
+  float pre[PF][2];  // CONTIG: raw samples of the slots ahead
+  if (CONTIG) {
+#pragma unroll
+    for (int d = 0; d < PF; ++d) {
+      pre[d][0] = d < n_slots ? __ldg(reinterpret_cast<const float*>(p.slot[0][d]) + in_off) : 0.0f;
+      pre[d][1] = d < n_slots ? __ldg(reinterpret_cast<const float*>(p.slot[1][d]) + in_off) : 0.0f;
+    }
+  }
+  for (int s4 = 0; s4 < n_slots; s4 += PF) {
+    // make room for the four frames of this group: age a moves from hist[a] ... to hist[a + 4] (what falls off the end is older than 31)
+#pragma unroll
+    for (int k = NA + PF - 2; k >= PF; --k) { ht[k] = ht[k - PF]; hr[k] = hr[k - PF]; }
+#pragma unroll
+    for (int d = 0; d < PF; ++d) {
+      const int s = s4 + d;
+      if (s < n_slots) {
+        float a[1], b[1];
+        if (CONTIG) {
+          a[0] = eotf_front(pre[d][0], p, oor);
+          b[0] = eotf_front(pre[d][1], p, oor);
+          if (s + PF < n_slots) {
+            pre[d][0] = __ldg(reinterpret_cast<const float*>(p.slot[0][s + PF]) + in_off);
+            pre[d][1] = __ldg(reinterpret_cast<const float*>(p.slot[1][s + PF]) + in_off);
+          }
+        } else {
+          load_lum<1, false>(p, p.slot[0][s], y, x, a, oor);
+          load_lum<1, false>(p, p.slot[1][s], y, x, b, oor);
+        }
+        ht[PF - 1 - d] = a[0];   // age 0 of step d; age k sits at hist[k + PF - 1 - d]
+        hr[PF - 1 - d] = b[0];
+        if (s >= p.fl - 1) {
+          const int i = s - (p.fl - 1);
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            float st[2] = {0.0f, 0.0f}, sr[2] = {0.0f, 0.0f};  // two partial sums per stream
+#pragma unroll
+            for (int k = 0; k < NA; ++k) {
+              st[k & 1] = fmaf(ht[k + PF - 1 - d], p.wage[cc][k], st[k & 1]);
+              sr[k & 1] = fmaf(hr[k + PF - 1 - d], p.wage[cc][k], sr[k & 1]);
+            }
+            *reinterpret_cast<float2*>(out + cc * chan_stride + i * frame_stride) = make_float2(st[0] + st[1], sr[0] + sr[1]);
+          }
         }
       }
     }

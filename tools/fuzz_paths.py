@@ -17,7 +17,7 @@ worst_j, worst_q, bad = 0.0, 0.0, 0
 for case in range(n_cases):
     H, W = int(rng.integers(17, 320)), int(rng.integers(17, 420))
     N = int(rng.integers(1, 24))
-    fps = [24, 25, 30, 50, 60][int(rng.integers(0, 5))]
+    fps = [24, 25, 30, 50, 60, 90, 120][int(rng.integers(0, 7))]
     pad = ["replicate", "circular", "pingpong"][int(rng.integers(0, 3))]
     C = [1, 3][int(rng.integers(0, 2))]
     kind = ["f32", "u8", "u16"][int(rng.integers(0, 3))]
