@@ -190,9 +190,11 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
     const char* force = getenv("FVVDP_B200_PATH");
     const bool v1 = force && strcmp(force, "v1") == 0;
     // windows of 17..32 taps: the filters run in a register-ring walk of their own and the band kernels take two planes per slot
-    c->ch2 = cfg->filter_len > fused::MAXRING && cfg->temp_ch == 2 && !cfg->want_taps && !cfg->want_dmap && !v1;
+    const char* ct = getenv("FVVDP_B200_CH2_TAPS");  // A/B switch: smallest window that takes this route (default 17)
+    const int ch2_min = ct ? atoi(ct) : fused::MAXRING + 1;
+    c->ch2 = cfg->filter_len >= ch2_min && cfg->filter_len >= 2 && cfg->temp_ch == 2 && !cfg->want_taps && !cfg->want_dmap && !v1;
     c->fused = (cfg->filter_len <= fused::MAXRING || c->ch2) && !v1;
-    const bool ws_ok = c->fused && !(force && strcmp(force, "fused") == 0) && cfg->temp_ch == 2 && cfg->filter_len >= 2 &&
+    const bool ws_ok = c->fused && !c->ch2 && !(force && strcmp(force, "fused") == 0) && cfg->temp_ch == 2 && cfg->filter_len >= 2 &&
                        cfg->filter_len <= ws16::RP + 1 && !cfg->want_taps && !cfg->want_dmap;
     if (cfg->filter_len > ws::RP + 1) { c->ws_th = ws16::TH; c->ws_rp = ws16::RP; }
     const char* wl = getenv("FVVDP_B200_WS_LEVELS");
@@ -564,8 +566,13 @@ static int score_block_impl(fvvdp_b200_ctx* ctx, const void* const* test_slots, 
       {
         const long long npx = (long long)H * W;
         const unsigned blocks = (unsigned)((npx + 255) / 256);
-        if (fcontig) front_pairs_kernel<true><<<blocks, 256, 0, st>>>(fp);
-        else front_pairs_kernel<false><<<blocks, 256, 0, st>>>(fp);
+        if (fl <= 16) {
+          if (fcontig) front_pairs_kernel<true, 16><<<blocks, 256, 0, st>>>(fp);
+          else front_pairs_kernel<false, 16><<<blocks, 256, 0, st>>>(fp);
+        } else {
+          if (fcontig) front_pairs_kernel<true, 32><<<blocks, 256, 0, st>>>(fp);
+          else front_pairs_kernel<false, 32><<<blocks, 256, 0, st>>>(fp);
+        }
       }
       cudaError_t lf = cudaGetLastError();
       if (lf != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "front_kernel launch: %s", cudaGetErrorString(lf));

@@ -202,9 +202,8 @@ __device__ __forceinline__ float eotf_front(float v, const FrontParams& p, bool&
   }
   return eotf_apply(v, p, oor);
 }
-template <bool CONTIG>
+template <bool CONTIG, int NA>   // NA = ages kept (0 = newest): 32, or 16 for windows of up to 16 taps
 __global__ void __launch_bounds__(256, 2) front_pairs_kernel(const __grid_constant__ FrontParams p) {
-  constexpr int NA = 32;  // ages kept: 0 (newest) .. 31
   constexpr int PF = 4;   // steps per group = slots whose samples are in flight ahead of the one being filtered
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= (long long)p.H * p.W) return;
