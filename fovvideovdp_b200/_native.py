@@ -58,7 +58,10 @@ class YuvDesc(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bit_depth", C.c_int32), ("chroma_420", C.c_int32),
                 ("ycbcr2rgb", C.c_float * 9), ("eotf", C.c_int32),
                 ("Y_peak", C.c_float), ("Y_black", C.c_float), ("gamma", C.c_float), ("L_min", C.c_float), ("L_max", C.c_float),
-                ("rgb2y", C.c_float * 3)]
+                ("rgb2y", C.c_float * 3), ("resize", C.c_int32), ("out_width", C.c_int32), ("out_height", C.c_int32)]
+
+
+RESIZE_CODES = {None: 0, "nearest": 1, "bilinear": 2, "bicubic": 3, "area": 4}  # fvvdp_b200_resize
 
 
 class PuParams(C.Structure):

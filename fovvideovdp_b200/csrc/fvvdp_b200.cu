@@ -468,6 +468,21 @@ static void fill_yuv_params(const fvvdp_b200_yuv_desc* d, YuvParams& p) {
   for (int i = 0; i < 3; ++i) p.rgb2y[i] = d->rgb2y[i];
 }
 
+static const char* check_yuv_desc(const fvvdp_b200_yuv_desc* d) {
+  if (d->width < 1 || d->height < 1) return "bad frame size";
+  if (d->bit_depth < 8 || d->bit_depth > 16) return "bit depth not in 8..16";
+  if (d->chroma_420 && ((d->width | d->height) & 1)) return "4:2:0 frames need an even width and height";
+  if (d->eotf < 0 || d->eotf > 5) return "unknown EOTF";
+  if (d->resize < FVVDP_B200_RESIZE_NONE || d->resize > FVVDP_B200_RESIZE_AREA) return "unknown resize mode";
+  if (d->resize != FVVDP_B200_RESIZE_NONE && (d->out_width < 1 || d->out_height < 1)) return "bad output size";
+  return nullptr;
+}
+
+static void fill_resize_params(const fvvdp_b200_yuv_desc* d, ResizeParams& r) {
+  r.mode = d->resize; r.outW = d->out_width; r.outH = d->out_height;
+  r.sx = (float)d->width / (float)d->out_width; r.sy = (float)d->height / (float)d->out_height;  // ATen area_pixel_compute_scale
+}
+
 // score_block for array frames (yuv == nullptr) or for DEVICE copies of raw planar Y'CbCr frames as stored in a .yuv file
 static int score_block_impl(fvvdp_b200_ctx* ctx, const void* const* test_slots, const void* const* ref_slots, const int64_t strides[3],
                             int n_frames, const float* fixation_xy, float* q_out, int64_t q_stride, int64_t q_col0, uint32_t* flags_out,
@@ -664,9 +679,23 @@ static int score_block_impl(fvvdp_b200_ctx* ctx, const void* const* test_slots, 
             yp.frame[0][s] = test_slots[s]; yp.frame[1][s] = ref_slots[s];
             yp.skip[s] = 0;  // (repeats of slot 0 are converted too: time chunks of small frames start their walk inside them)
           }
-          yp.y_elems = (long long)W * H; yp.c_elems = (long long)yp.f.cw * yp.f.ch;
+          yp.y_elems = (long long)yp.f.W * yp.f.H; yp.c_elems = (long long)yp.f.cw * yp.f.ch;
           yp.out = ctx->P[0]; yp.slot_stride = (long long)H * ctx->pitch[0]; yp.pitch = ctx->pitch[0];
           dim3 yg(((W + 1) / 2 + 31) / 32, (H + 7) / 8, n_slots);
+          if (yuv->resize) {
+            // full-screen resize: every output pixel gathers its taps from the planar frames (yuv_resize_planes_kernel)
+            ResizeParams rs;
+            fill_resize_params(yuv, rs);
+            dim3 rg((W + 31) / 32, (H + 7) / 8, n_slots);
+            switch (yuv->eotf) {
+              case FVVDP_B200_EOTF_NONE: yuv_resize_planes_kernel<FVVDP_B200_EOTF_NONE><<<rg, 256, 0, st>>>(yp, rs); break;
+              case FVVDP_B200_EOTF_SRGB: yuv_resize_planes_kernel<FVVDP_B200_EOTF_SRGB><<<rg, 256, 0, st>>>(yp, rs); break;
+              case FVVDP_B200_EOTF_GAMMA: yuv_resize_planes_kernel<FVVDP_B200_EOTF_GAMMA><<<rg, 256, 0, st>>>(yp, rs); break;
+              case FVVDP_B200_EOTF_PQ: yuv_resize_planes_kernel<FVVDP_B200_EOTF_PQ><<<rg, 256, 0, st>>>(yp, rs); break;
+              case FVVDP_B200_EOTF_LINEAR: yuv_resize_planes_kernel<FVVDP_B200_EOTF_LINEAR><<<rg, 256, 0, st>>>(yp, rs); break;
+              default: yuv_resize_planes_kernel<FVVDP_B200_EOTF_ABSOLUTE><<<rg, 256, 0, st>>>(yp, rs); break;
+            }
+          } else
           switch (yuv->eotf) {
             case FVVDP_B200_EOTF_NONE: yuv_planes_kernel<FVVDP_B200_EOTF_NONE><<<yg, 256, 0, st>>>(yp); break;
             case FVVDP_B200_EOTF_SRGB: yuv_planes_kernel<FVVDP_B200_EOTF_SRGB><<<yg, 256, 0, st>>>(yp); break;
@@ -839,10 +868,9 @@ extern "C" int fvvdp_b200_score_block_yuv(fvvdp_b200_ctx* ctx, const fvvdp_b200_
                                           int64_t q_stride, int64_t q_col0, void* cuda_stream) {
   if (!ctx) return FVVDP_B200_ERR_INVALID;
   if (!desc) return fail(ctx, FVVDP_B200_ERR_INVALID, "null argument");
-  if (desc->width != ctx->cfg.width || desc->height != ctx->cfg.height) return fail(ctx, FVVDP_B200_ERR_INVALID, "frame size %dx%d does not match the context (%dx%d)", desc->width, desc->height, ctx->cfg.width, ctx->cfg.height);
-  if (desc->bit_depth < 8 || desc->bit_depth > 16) return fail(ctx, FVVDP_B200_ERR_INVALID, "bit depth %d not in 8..16", desc->bit_depth);
-  if (desc->chroma_420 && ((desc->width | desc->height) & 1)) return fail(ctx, FVVDP_B200_ERR_INVALID, "4:2:0 frames need an even width and height");
-  if (desc->eotf < 0 || desc->eotf > 5) return fail(ctx, FVVDP_B200_ERR_INVALID, "Unknown EOTF %d", desc->eotf);
+  if (const char* why = check_yuv_desc(desc)) return fail(ctx, FVVDP_B200_ERR_INVALID, "yuv frame description: %s", why);
+  const int ow = desc->resize ? desc->out_width : desc->width, oh = desc->resize ? desc->out_height : desc->height;
+  if (ow != ctx->cfg.width || oh != ctx->cfg.height) return fail(ctx, FVVDP_B200_ERR_INVALID, "frame size %dx%d does not match the context (%dx%d)", ow, oh, ctx->cfg.width, ctx->cfg.height);
   const int64_t strides[3] = {0, ctx->cfg.width, 1};
   return score_block_impl(ctx, test_frames, ref_frames, strides, n_frames, fixation_xy, q_out, q_stride, q_col0, nullptr, cuda_stream, desc);
 }
@@ -944,10 +972,7 @@ extern "C" int fvvdp_b200_yuv_to_luminance(const fvvdp_b200_yuv_desc* d, const v
                                            float* lum_out, float* rgb_out, int cuda_device, void* cuda_stream) {
   fvvdp_b200_ctx* ctx = nullptr;  // ctx-free: errors are reported through fvvdp_b200_last_error(NULL)
   if (!d || !y_plane || !u_plane || !v_plane || (!lum_out && !rgb_out)) return fail(ctx, FVVDP_B200_ERR_INVALID, "null argument");
-  if (d->width < 1 || d->height < 1) return fail(ctx, FVVDP_B200_ERR_INVALID, "bad frame size %dx%d", d->width, d->height);
-  if (d->bit_depth < 8 || d->bit_depth > 16) return fail(ctx, FVVDP_B200_ERR_INVALID, "bit depth %d not in 8..16", d->bit_depth);
-  if (d->chroma_420 && ((d->width | d->height) & 1)) return fail(ctx, FVVDP_B200_ERR_INVALID, "4:2:0 frames need an even width and height");
-  if (d->eotf < 0 || d->eotf > 5) return fail(ctx, FVVDP_B200_ERR_INVALID, "Unknown EOTF %d", d->eotf);
+  if (const char* why = check_yuv_desc(d)) return fail(ctx, FVVDP_B200_ERR_INVALID, "yuv frame description: %s", why);
   CU(cudaSetDevice(cuda_device));
   YuvParams p;
   fill_yuv_params(d, p);
@@ -955,6 +980,19 @@ extern "C" int fvvdp_b200_yuv_to_luminance(const fvvdp_b200_yuv_desc* d, const v
   p.lum = lum_out; p.rgb = rgb_out;
   dim3 grid(((d->width + 1) / 2 + 31) / 32, (d->height + 7) / 8);
   cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (d->resize) {
+    ResizeParams rs;
+    fill_resize_params(d, rs);
+    dim3 rg((rs.outW + 31) / 32, (rs.outH + 7) / 8);
+    switch (lum_out ? d->eotf : FVVDP_B200_EOTF_NONE) {
+      case FVVDP_B200_EOTF_NONE: yuv_resize_kernel<FVVDP_B200_EOTF_NONE><<<rg, 256, 0, st>>>(p, rs); break;
+      case FVVDP_B200_EOTF_SRGB: yuv_resize_kernel<FVVDP_B200_EOTF_SRGB><<<rg, 256, 0, st>>>(p, rs); break;
+      case FVVDP_B200_EOTF_GAMMA: yuv_resize_kernel<FVVDP_B200_EOTF_GAMMA><<<rg, 256, 0, st>>>(p, rs); break;
+      case FVVDP_B200_EOTF_PQ: yuv_resize_kernel<FVVDP_B200_EOTF_PQ><<<rg, 256, 0, st>>>(p, rs); break;
+      case FVVDP_B200_EOTF_LINEAR: yuv_resize_kernel<FVVDP_B200_EOTF_LINEAR><<<rg, 256, 0, st>>>(p, rs); break;
+      default: yuv_resize_kernel<FVVDP_B200_EOTF_ABSOLUTE><<<rg, 256, 0, st>>>(p, rs); break;
+    }
+  } else
   switch (lum_out ? d->eotf : FVVDP_B200_EOTF_NONE) {
     case FVVDP_B200_EOTF_NONE: yuv_kernel<FVVDP_B200_EOTF_NONE><<<grid, 256, 0, st>>>(p); break;
     case FVVDP_B200_EOTF_SRGB: yuv_kernel<FVVDP_B200_EOTF_SRGB><<<grid, 256, 0, st>>>(p); break;

@@ -904,6 +904,137 @@ __global__ void __launch_bounds__(256) yuv_planes_kernel(const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------
+// Full-screen resize of .yuv clips (fvvdp_video_source_yuv_file._get_frame, video_source_yuv.py:293-297: the display-encoded
+// R'G'B' frame goes through torch.nn.functional.interpolate(size=display resolution, mode=nearest|bilinear|bicubic|area),
+// align_corners unset, then .clip(0, 1), then the display model).  Here every output pixel gathers its taps straight from
+// the planar Y'CbCr frame -- each tap converted like yuv_kernel does -- so no R'G'B' frame at the clip's own resolution is
+// ever written.  Tap positions and weights follow ATen's upsample kernels: scale = in / out in float; nearest
+// min(floor(dst * scale), in - 1); bilinear src = max(scale (dst + 0.5) - 0.5, 0); bicubic src = scale (dst + 0.5) - 0.5,
+// A = -0.75, taps clamped to the frame; area = adaptive average pooling over [floor(i in / out), ceil((i + 1) in / out)).
+// ------------------------------------------------------------------------------------------------
+struct ResizeParams {
+  int mode;        // fvvdp_b200_resize
+  int outW, outH;
+  float sx, sy;    // (float)in / out
+};
+
+// display-encoded, clipped R'G'B' of ONE source pixel
+__device__ __forceinline__ void yuv_rgb_at(const YuvParams& p, int x, int y, float (&rgb)[3]) {
+  float cb, cr;
+  if (p.is420) {
+    const float sy = fmaxf(0.5f * (float)y - 0.25f, 0.0f), sx = fmaxf(0.5f * (float)x - 0.25f, 0.0f);
+    const int y0 = (int)sy, y1 = min(y0 + 1, p.ch - 1), x0 = (int)sx, x1 = min(x0 + 1, p.cw - 1);
+    const float ly = sy - (float)y0, lx = sx - (float)x0;
+    cb = (1.0f - ly) * ((1.0f - lx) * yuv_chroma(p, p.u, y0, x0) + lx * yuv_chroma(p, p.u, y0, x1)) +
+         ly * ((1.0f - lx) * yuv_chroma(p, p.u, y1, x0) + lx * yuv_chroma(p, p.u, y1, x1));
+    cr = (1.0f - ly) * ((1.0f - lx) * yuv_chroma(p, p.v, y0, x0) + lx * yuv_chroma(p, p.v, y0, x1)) +
+         ly * ((1.0f - lx) * yuv_chroma(p, p.v, y1, x0) + lx * yuv_chroma(p, p.v, y1, x1));
+  } else {
+    cb = yuv_chroma(p, p.u, y, x);
+    cr = yuv_chroma(p, p.v, y, x);
+  }
+  const float Y = fminf(fmaxf(p.wy * yuv_sample(p.y, (long long)y * p.W + x, p.is16) - p.oy, 0.0f), 1.0f);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) rgb[c] = fminf(fmaxf(p.m[3 * c] * Y + p.m[3 * c + 1] * cb + p.m[3 * c + 2] * cr, 0.0f), 1.0f);
+}
+
+__device__ __forceinline__ void cubic_weights(float t, float (&w)[4]) {  // ATen get_cubic_upsample_coefficients, A = -0.75
+  const float A = -0.75f;
+  const float a = t + 1.0f, b = t, c = 1.0f - t, d = 2.0f - t;
+  w[0] = ((A * a - 5.0f * A) * a + 8.0f * A) * a - 4.0f * A;
+  w[1] = ((A + 2.0f) * b - (A + 3.0f)) * b * b + 1.0f;
+  w[2] = ((A + 2.0f) * c - (A + 3.0f)) * c * c + 1.0f;
+  w[3] = ((A * d - 5.0f * A) * d + 8.0f * A) * d - 4.0f * A;
+}
+
+// resized, clipped R'G'B' of output pixel (ox, oy)
+__device__ __noinline__ void yuv_resized_rgb(const YuvParams& p, const ResizeParams& r, int ox, int oy, float (&rgb)[3]) {
+  float t[3];
+  rgb[0] = rgb[1] = rgb[2] = 0.0f;
+  if (r.mode == FVVDP_B200_RESIZE_NEAREST) {
+    yuv_rgb_at(p, min((int)floorf((float)ox * r.sx), p.W - 1), min((int)floorf((float)oy * r.sy), p.H - 1), rgb);
+  } else if (r.mode == FVVDP_B200_RESIZE_BILINEAR) {
+    const float fx = fmaxf(r.sx * ((float)ox + 0.5f) - 0.5f, 0.0f), fy = fmaxf(r.sy * ((float)oy + 0.5f) - 0.5f, 0.0f);
+    const int x0 = min((int)fx, p.W - 1), y0 = min((int)fy, p.H - 1), x1 = x0 + (x0 < p.W - 1 ? 1 : 0), y1 = y0 + (y0 < p.H - 1 ? 1 : 0);
+    const float lx = fx - (float)x0, ly = fy - (float)y0, kx = 1.0f - lx, ky = 1.0f - ly;
+    float a[3], b[3];
+    yuv_rgb_at(p, x0, y0, a);
+    yuv_rgb_at(p, x1, y0, b);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) rgb[c] = ky * (kx * a[c] + lx * b[c]);
+    yuv_rgb_at(p, x0, y1, a);
+    yuv_rgb_at(p, x1, y1, b);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) rgb[c] += ly * (kx * a[c] + lx * b[c]);
+  } else if (r.mode == FVVDP_B200_RESIZE_BICUBIC) {
+    const float fx = r.sx * ((float)ox + 0.5f) - 0.5f, fy = r.sy * ((float)oy + 0.5f) - 0.5f;
+    const float bx = floorf(fx), by = floorf(fy);
+    float wx[4], wy[4];
+    cubic_weights(fx - bx, wx);
+    cubic_weights(fy - by, wy);
+    for (int j = 0; j < 4; ++j) {
+      const int yy = max(min((int)by - 1 + j, p.H - 1), 0);
+      float row[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        yuv_rgb_at(p, max(min((int)bx - 1 + i, p.W - 1), 0), yy, t);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) row[c] += t[c] * wx[i];
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) rgb[c] += row[c] * wy[j];
+    }
+  } else {  // area
+    const int x0 = (int)(((long long)ox * p.W) / r.outW), x1 = (int)((((long long)ox + 1) * p.W + r.outW - 1) / r.outW);
+    const int y0 = (int)(((long long)oy * p.H) / r.outH), y1 = (int)((((long long)oy + 1) * p.H + r.outH - 1) / r.outH);
+    for (int yy = y0; yy < y1; ++yy)
+      for (int xx = x0; xx < x1; ++xx) {
+        yuv_rgb_at(p, xx, yy, t);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) rgb[c] += t[c];
+      }
+    const float n = (float)((y1 - y0) * (x1 - x0));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) rgb[c] /= n;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) rgb[c] = fminf(fmaxf(rgb[c], 0.0f), 1.0f);
+}
+
+// one frame: luminance [outH][outW] and / or resized R'G'B' [outH][outW][3]
+template <int KIND>
+__global__ void __launch_bounds__(256) yuv_resize_kernel(const YuvParams p, const ResizeParams r) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= r.outW || y >= r.outH) return;
+  float rgb[3];
+  yuv_resized_rgb(p, r, x, y, rgb);
+  const long long i = (long long)y * r.outW + x;
+  if (p.rgb) { p.rgb[3 * i] = rgb[0]; p.rgb[3 * i + 1] = rgb[1]; p.rgb[3 * i + 2] = rgb[2]; }
+  if (p.lum) p.lum[i] = yuv_eotf<KIND>(rgb[0], p) * p.rgb2y[0] + yuv_eotf<KIND>(rgb[1], p) * p.rgb2y[1] + yuv_eotf<KIND>(rgb[2], p) * p.rgb2y[2];
+}
+
+// block version: the window slots of both streams into the (test, reference) planes level 0 stages (see yuv_planes_kernel)
+template <int KIND>
+__global__ void __launch_bounds__(256) yuv_resize_planes_kernel(const __grid_constant__ YuvBlockParams q, const ResizeParams r) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), slot = blockIdx.z;
+  if (x >= r.outW || y >= r.outH) return;
+  float lum[2];
+#pragma unroll 1
+  for (int st = 0; st < 2; ++st) {
+    YuvParams p = q.f;
+    const char* base = reinterpret_cast<const char*>(q.frame[st][slot]);
+    const int esz = p.is16 ? 2 : 1;
+    p.y = base;
+    p.u = base + q.y_elems * esz;
+    p.v = base + (q.y_elems + q.c_elems) * esz;
+    float rgb[3];
+    yuv_resized_rgb(p, r, x, y, rgb);
+    lum[st] = yuv_eotf<KIND>(rgb[0], p) * p.rgb2y[0] + yuv_eotf<KIND>(rgb[1], p) * p.rgb2y[1] + yuv_eotf<KIND>(rgb[2], p) * p.rgb2y[2];
+  }
+  *reinterpret_cast<float2*>(q.out + slot * q.slot_stride + (long long)y * q.pitch + 2 * x) = make_float2(lum[0], lum[1]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K_pu: PU21-PSNR frame term (pupsnr.py:52-79, utils.py:157-202): sum over the frame of (PU(T) - PU(R))^2 with
 // PU(Y) = p6 (((p0 + p1 Y^p3) / (1 + p2 Y^p3))^p4 - p5), Y clipped to [L_min, L_max]
 // ------------------------------------------------------------------------------------------------

@@ -621,14 +621,14 @@ class fvvdp:
             spec = photometry_kernel_spec(vid_source.dm_photometry)
         raw = spec is not None
         # raw .yuv clips with a stock display model: the frames go to the device as stored and one kernel per block converts them
-        # into the planes level 0 stages (fvvdp_b200_score_block_yuv); resized clips / custom photometry: get_*_frame()
+        # into the planes level 0 stages (fvvdp_b200_score_block_yuv), full-screen resize included; custom photometry: get_*_frame()
         yuv_desc = None
         if (type(vid_source).__name__ == "fvvdp_video_source_yuv_file" and type(vid_source).__module__.startswith("fovvideovdp_b200")
-                and getattr(vid_source, "_spec", None) is not None and vid_source.full_screen_resize is None and not is_image
+                and getattr(vid_source, "_spec", None) is not None and not is_image
                 and fl <= 16 and not self.debug_taps and not self.do_heatmap):
             tr, rr = vid_source.test_vidr, vid_source.reference_vidr
             if (tr.width, tr.height, tr.bit_depth, tr.chroma_ss, tr.color_space) == (rr.width, rr.height, rr.bit_depth, rr.chroma_ss, rr.color_space):
-                yuv_desc = tr._desc(vid_source._spec, vid_source.color_to_luminance)
+                yuv_desc = tr._desc(vid_source._spec, vid_source.color_to_luminance, vid_source.resize_of(tr))
         frames = _YuvFrames(vid_source, dev) if yuv_desc is not None else _FrameSet(vid_source, dev, raw)
         if raw:
             C = 3 if vid_source.is_color else 1

@@ -99,7 +99,8 @@ class YUVReader:
         Y, u, v = self._planes(frame_index)
         return np.reshape(Y, self.y_shape, "C"), np.reshape(u, self.uv_shape, "C"), np.reshape(v, self.uv_shape, "C")
 
-    def _desc(self, spec=None, rgb2y=None):
+    def _desc(self, spec=None, rgb2y=None, resize=None):
+        """`resize` = (mode, (out_width, out_height)) of a full-screen resize, or None."""
         d = _native.YuvDesc()
         d.width, d.height, d.bit_depth = self.width, self.height, self.bit_depth
         d.chroma_420 = 1 if self.chroma_ss == "420" else 0
@@ -111,10 +112,14 @@ class YUVReader:
         d.L_min, d.L_max = spec.get("L_min", 0.0), spec.get("L_max", 0.0)
         for i, w in enumerate(rgb2y or [0.0, 0.0, 0.0]):
             d.rgb2y[i] = float(w)
+        if resize is not None:
+            if resize[0] not in _native.RESIZE_CODES:
+                raise ValueError(f"Unknown full_screen_resize mode '{resize[0]}' (nearest, bilinear, bicubic or area)")
+            d.resize, d.out_width, d.out_height = _native.RESIZE_CODES[resize[0]], int(resize[1][0]), int(resize[1][1])
         return d
 
-    def _convert(self, frame_index, device, spec, rgb2y, want_lum, want_rgb):
-        """Upload the frame's planes in their file layout and run the conversion kernel on `device`."""
+    def _convert(self, frame_index, device, spec, rgb2y, want_lum, want_rgb, resize=None):
+        """Upload the frame's planes in their file layout and run the conversion (+ resize) kernel on `device`."""
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("fovvideovdp_b200 converts .yuv frames on CUDA devices only; there is no CPU fallback")
@@ -127,21 +132,23 @@ class YUVReader:
         with torch.cuda.device(device):
             dev = host.to(device, non_blocking=True)
             esz = dev.element_size()
-            lum = torch.empty((1, 1, 1, self.height, self.width), dtype=torch.float32, device=device) if want_lum else None
-            rgb = torch.empty((self.height, self.width, 3), dtype=torch.float32, device=device) if want_rgb else None
-            _native.yuv_to_luminance(self._desc(spec, rgb2y), dev.data_ptr(), dev.data_ptr() + self.y_pixels * esz,
+            ow, oh = (self.width, self.height) if resize is None else (int(resize[1][0]), int(resize[1][1]))
+            lum = torch.empty((1, 1, 1, oh, ow), dtype=torch.float32, device=device) if want_lum else None
+            rgb = torch.empty((oh, ow, 3), dtype=torch.float32, device=device) if want_rgb else None
+            _native.yuv_to_luminance(self._desc(spec, rgb2y, resize), dev.data_ptr(), dev.data_ptr() + self.y_pixels * esz,
                                      dev.data_ptr() + (self.y_pixels + self.uv_pixels) * esz, lum.data_ptr() if want_lum else 0,
                                      rgb.data_ptr() if want_rgb else 0, device.index, torch.cuda.current_stream(device).cuda_stream)
             dev.record_stream(torch.cuda.current_stream(device))
         return lum, rgb
 
-    def get_frame_rgb_tensor(self, frame_index, device):
-        """Display-encoded RGB (H,W,3) float32 in [0,1] on `device` (video_source_yuv.py:157-182)."""
-        return self._convert(frame_index, device, None, None, False, True)[1]
+    def get_frame_rgb_tensor(self, frame_index, device, resize=None):
+        """Display-encoded RGB (H,W,3) float32 in [0,1] on `device` (video_source_yuv.py:157-182); with `resize` = (mode,
+        (width, height)) resampled like torch.nn.functional.interpolate(mode=...) and clipped (:293-297), in the same kernel."""
+        return self._convert(frame_index, device, None, None, False, True, resize)[1]
 
-    def get_frame_luminance(self, frame_index, device, spec, rgb2y):
+    def get_frame_luminance(self, frame_index, device, spec, rgb2y, resize=None):
         """Luminance (1,1,1,H,W) float32 in cd/m^2 for a stock photometry `spec` (display_model.photometry_kernel_spec)."""
-        return self._convert(frame_index, device, spec, rgb2y, True, False)[0]
+        return self._convert(frame_index, device, spec, rgb2y, True, False, resize)[0]
 
     def __enter__(self):
         return self
@@ -175,6 +182,12 @@ class fvvdp_video_source_yuv_file(fvvdp_video_source_dm):
     def get_frames_per_second(self):
         return self.test_vidr.fps
 
+    def resize_of(self, vid_reader):
+        """(mode, (width, height)) when this reader's frames are resampled to the display resolution (video_source_yuv.py:293), else None."""
+        if self.full_screen_resize is None or (vid_reader.height == self.resize_resolution[1] and vid_reader.width == self.resize_resolution[0]):
+            return None
+        return (self.full_screen_resize, (int(self.resize_resolution[0]), int(self.resize_resolution[1])))
+
     def get_test_frame(self, frame, device):
         return self._get_frame(self.test_vidr, frame, device)
 
@@ -182,14 +195,11 @@ class fvvdp_video_source_yuv_file(fvvdp_video_source_dm):
         return self._get_frame(self.reference_vidr, frame, device)
 
     def _get_frame(self, vid_reader, frame, device):
-        resize = self.full_screen_resize is not None and (vid_reader.height != self.resize_resolution[1] or vid_reader.width != self.resize_resolution[0])
-        if self._spec is not None and not resize:
-            return vid_reader.get_frame_luminance(frame, device, self._spec, self.color_to_luminance)
-        # resized clips and custom photometry plugins: RGB from the kernel, the rest as the reference does it (:290-302)
-        RGB = vid_reader.get_frame_rgb_tensor(frame, device).permute(2, 0, 1)[None]
-        if resize:
-            RGB = torch.nn.functional.interpolate(RGB, size=(self.resize_resolution[1], self.resize_resolution[0]),
-                                                  mode=self.full_screen_resize).clip(0.0, 1.0)
+        resize = self.resize_of(vid_reader)
+        if self._spec is not None:
+            return vid_reader.get_frame_luminance(frame, device, self._spec, self.color_to_luminance, resize)
+        # custom photometry plugins: (resized) RGB from the kernel, the plugin's forward() as the reference does it (:290-302)
+        RGB = vid_reader.get_frame_rgb_tensor(frame, device, resize).permute(2, 0, 1)[None]
         RGB_lin = self.dm_photometry.forward(RGB[:, :, None])
         w = self.color_to_luminance
         return RGB_lin[:, 0:1] * w[0] + RGB_lin[:, 1:2] * w[1] + RGB_lin[:, 2:3] * w[2]

@@ -161,8 +161,12 @@ int fvvdp_b200_set_foveation_maps(fvvdp_b200_ctx* ctx, int level, const float* v
  * video_source_file.py:219-276): limited-range fixed2float, bilinear 4:2:0 chroma upsampling, ycbcr2rgb, clip to [0,1],
  * display EOTF, RGB2Y.  Planes are DEVICE pointers (uint8, or uint16 when bit_depth > 8); 4:2:0 needs even width/height.
  * lum_out: DEVICE float (H,W) in cd/m^2, or NULL; rgb_out: DEVICE float (H,W,3) display-encoded RGB (for callers that
- * resize or apply their own photometry), or NULL.
+ * apply their own photometry), or NULL.  With desc->resize set, both have the output size (out_height, out_width).
  */
+typedef enum fvvdp_b200_resize {
+  FVVDP_B200_RESIZE_NONE = 0, FVVDP_B200_RESIZE_NEAREST = 1, FVVDP_B200_RESIZE_BILINEAR = 2, FVVDP_B200_RESIZE_BICUBIC = 3,
+  FVVDP_B200_RESIZE_AREA = 4
+} fvvdp_b200_resize;
 typedef struct fvvdp_b200_yuv_desc {
   int32_t width, height;
   int32_t bit_depth;          /* 8..16 */
@@ -171,6 +175,11 @@ typedef struct fvvdp_b200_yuv_desc {
   int32_t eotf;               /* fvvdp_b200_eotf */
   float Y_peak, Y_black, gamma, L_min, L_max;
   float rgb2y[3];
+  /* full-screen resize (fvvdp_video_source_yuv_file(full_screen_resize=..., resize_resolution=...), video_source_yuv.py:293-297):
+   * with resize != NONE the R'G'B' frame is resampled to out_width x out_height like torch.nn.functional.interpolate(mode=...)
+   * and clipped to [0,1] before the display EOTF; lum_out / rgb_out / the context then have the OUTPUT size */
+  int32_t resize;             /* fvvdp_b200_resize */
+  int32_t out_width, out_height;
 } fvvdp_b200_yuv_desc;
 int fvvdp_b200_yuv_to_luminance(const fvvdp_b200_yuv_desc* desc, const void* y_plane, const void* u_plane, const void* v_plane,
                                 float* lum_out, float* rgb_out, int cuda_device, void* cuda_stream);

@@ -227,10 +227,52 @@ def test_yuv_video_source(fv_mod, golden, tmp_path, case):
     assert fv.last_run["h2d_bytes"] == 2 * 6 * t.shape[1] * t.itemsize
     check_jod(jod, g["jod"])
     check_q(st["Q_per_ch"], g["Q_per_ch"])
-    # resized clip: RGB from the kernel, torch interpolate, display model through forward()
+    # resized clip (resize kernel; parity: test_yuv_full_screen_resize)
     vs2 = vy.fvvdp_video_source_yuv_file(ft, fr, display_photometry=disp, full_screen_resize="bilinear", resize_resolution=(W * 2, H * 2))
     jod2, st2 = fv.predict_video_source(vs2)
     assert st2["width"] == 2 * W and st2["height"] == 2 * H and 0 < float(jod2) <= 10
+
+
+def test_yuv_full_screen_resize(fv_mod, golden, tmp_path):
+    """--full-screen-resize of raw .yuv clips (video_source_yuv.py:293-297): the four interpolate modes, up- and down-scaling by
+    non-integer factors, done inside the conversion kernels (per frame: fvvdp_b200_yuv_to_luminance, per block:
+    fvvdp_b200_score_block_yuv).  Checked against the reference's frames and scores (tests/golden/yuv_resize.npz) and, for the
+    resampled R'G'B' itself, against torch.nn.functional.interpolate on the kernel's own unresized R'G'B' (fp32 reference of
+    the same op)."""
+    from fovvideovdp_b200 import video_source_yuv as vy
+    from fovvideovdp_b200.synthetic import synth_yuv_pair
+    g = golden("yuv_resize")
+    H, W, bits, fps = int(g["H"]), int(g["W"]), int(g["bits"]), float(g["fps"])
+    t, r = synth_yuv_pair(4, H, W, bits, "420")
+    props = dict(width=W, height=H, bit_depth=bits, color_space="2020", chroma_ss="420", fps=fps)
+    ft, fr = str(tmp_path / vy.create_yuv_fname("test", props)), str(tmp_path / vy.create_yuv_fname("ref", props))
+    t.tofile(ft)
+    r.tofile(fr)
+    dev = torch.device("cuda:0")
+    for disp in ("standard_hdr_pq", "standard_4k"):
+        fv = fv_mod.fvvdp(display_name=disp)
+        for mode in ("nearest", "bilinear", "bicubic", "area"):
+            for tag, res in (("up", (200, 130)), ("down", (116, 75))):
+                key = f"{disp}_{mode}_{tag}"
+                vs = vy.fvvdp_video_source_yuv_file(ft, fr, display_photometry=disp, full_screen_resize=mode, resize_resolution=res)
+                assert list(vs.get_video_size()) == [res[1], res[0], 4]
+                rgb0 = vs.test_vidr.get_frame_rgb_tensor(1, dev)
+                rgb = vs.test_vidr.get_frame_rgb_tensor(1, dev, vs.resize_of(vs.test_vidr))
+                want = torch.nn.functional.interpolate(rgb0.permute(2, 0, 1)[None], size=(res[1], res[0]), mode=mode).clip(0.0, 1.0)[0].permute(1, 2, 0)
+                assert tuple(rgb.shape) == (res[1], res[0], 3)
+                assert float((rgb - want).abs().max()) < 3e-6, key
+                lum = vs.get_test_frame(1, dev)
+                assert tuple(lum.shape) == (1, 1, 1, res[1], res[0])
+                np.testing.assert_allclose(lum.cpu().numpy()[0, 0, 0], g["lum_" + key], rtol=5e-4, atol=2e-4, err_msg=key)
+                if disp == "standard_hdr_pq":
+                    jod, st = fv.predict_video_source(vs)  # block path, resize in yuv_resize_planes_kernel
+                    assert fv.last_run["h2d_bytes"] == 2 * 4 * t.shape[1] * t.itemsize  # the frames travel at the clip's own size
+                    check_jod(jod, g["jod_" + key])
+                    # 4 small frames, PQ: the luminance front end's 7e-5 relative differences (fast exp2/log2 in the EOTF) show up
+                    # as up to 3e-4 of a channel's largest band energy; the JOD bound above is the stated one (1e-4)
+                    check_q(st["Q_per_ch"], g["Q_" + key], tol=5e-4)
+    with pytest.raises(ValueError):
+        vy.fvvdp_video_source_yuv_file(ft, fr, full_screen_resize="lanczos", resize_resolution=(200, 130)).get_test_frame(0, dev)
 
 
 def test_batch_front_end(fv_mod, tmp_path, capsys):

@@ -6,6 +6,7 @@ CUDA path).  Inputs are analytic / seeded so only outputs (and small inputs) are
     python tools/gen_golden.py            # rewrites every fixture
     python tools/gen_golden.py widen      # only the fixtures of the widened surface (heat-map colour maps, custom geometry)
     python tools/gen_golden.py yuv        # only the raw .yuv video-source fixtures
+    python tools/gen_golden.py yuvresize  # only the full-screen-resize fixtures of .yuv clips
     python tools/gen_golden.py round2     # only the fixtures added in round 2 (GOG, 120 fps, colour-space mismatch, the 64-frame 4K bench clip)
 
 Large tap tensors are stored as strided sub-samples ([::SY, ::SX]) to keep the fixtures small.
@@ -405,6 +406,36 @@ def gen_yuv_cases():
                  H=H, W=W, bits=bits, fps=fps, frames_per_second=st["frames_per_second"])
 
 
+def gen_yuv_resize_cases():
+    """Full-screen resize of raw .yuv clips (video_source_yuv.py:293-297): every torch.nn.functional.interpolate mode the
+    reference's command line offers, up- and down-scaling with non-integer factors; one frame of luminance + the JOD each."""
+    import tempfile
+    sys.path.insert(0, "/root/reference/pyfvvdp")
+    import video_source_yuv as vy
+    from fovvideovdp_b200.synthetic import synth_yuv_pair
+    vy.YUVReader.color_transfer = "n/a"   # see gen_yuv_cases
+    vy.YUVReader.in_pix_fmt = "n/a"
+    H, W, bits, css, cs, fps = 96, 160, 10, "420", "2020", 30
+    t, r = synth_yuv_pair(4, H, W, bits, css)
+    out = dict(H=H, W=W, bits=bits, fps=fps)
+    with tempfile.TemporaryDirectory() as d:
+        props = dict(width=W, height=H, bit_depth=bits, color_space=cs, chroma_ss=css, fps=fps)
+        ft, fr = os.path.join(d, vy.create_yuv_fname("test", props)), os.path.join(d, vy.create_yuv_fname("ref", props))
+        t.tofile(ft)
+        r.tofile(fr)
+        for disp in ("standard_hdr_pq", "standard_4k"):
+            for mode in ("nearest", "bilinear", "bicubic", "area"):
+                for tag, res in (("up", (200, 130)), ("down", (116, 75))):
+                    vs = vy.fvvdp_video_source_yuv_file(ft, fr, display_photometry=disp, full_screen_resize=mode, resize_resolution=res)
+                    key = f"{disp}_{mode}_{tag}"
+                    out["lum_" + key] = vs.get_test_frame(1, CPU).numpy()[0, 0, 0]
+                    if disp == "standard_hdr_pq":
+                        q, st = pyfvvdp.fvvdp(display_name=disp, device=CPU).predict_video_source(vs)
+                        out["jod_" + key] = float(q)
+                        out["Q_" + key] = st["Q_per_ch"].numpy() if hasattr(st["Q_per_ch"], "numpy") else st["Q_per_ch"]
+    save("yuv_resize", **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_grad_enabled(False)
@@ -423,11 +454,15 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "yuv":
         gen_yuv_cases()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "yuvresize":
+        gen_yuv_resize_cases()
+        sys.exit(0)
     gen_unit_cases()
     gen_metric_cases()
     gen_known_answer()
     gen_widened_cases()
     gen_yuv_cases()
+    gen_yuv_resize_cases()
     gen_pu_psnr_cases()
     gen_full_size_cases()
     gen_round2_cases()
