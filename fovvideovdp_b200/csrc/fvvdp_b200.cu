@@ -833,7 +833,7 @@ static int score_block_impl(fvvdp_b200_ctx* ctx, const void* const* test_slots, 
   fin.inv_beta = 1.0 / (double)cfg.beta;
   {
     ProfScope prof(ctx, FVVDP_B200_MAX_LEVELS + 1, st);
-    final_kernel<<<n_frames * ctx->n_bands * 2, 128, 0, st>>>(fin);
+    final_kernel<<<n_frames * ctx->n_bands * 2, 256, 0, st>>>(fin);
   }
   le = cudaGetLastError();
   if (le != cudaSuccess) return fail(ctx, FVVDP_B200_ERR_CUDA, "final_kernel launch: %s", cudaGetErrorString(le));

@@ -534,20 +534,30 @@ struct FinalParams {
   double inv_beta;
 };
 
-__global__ void __launch_bounds__(128) final_kernel(const __grid_constant__ FinalParams p) {
+__global__ void __launch_bounds__(256) final_kernel(const __grid_constant__ FinalParams p) {
   const int cc = blockIdx.x & 1, bb = (blockIdx.x >> 1) % p.n_bands, f = (blockIdx.x >> 1) / p.n_bands;
-  __shared__ double sd[4];
+  __shared__ double sd[8];
   double s = 0.0;
   if (cc < p.temp_ch) {
-    const float* src = p.partial[bb] + ((long long)f * 2 + cc) * p.ntiles[bb];
-    for (int i = threadIdx.x; i < p.ntiles[bb]; i += 128) s += (double)src[i];
+    const int n = p.ntiles[bb];
+    const float* src = p.partial[bb] + ((long long)f * 2 + cc) * n;
+    if ((n & 3) == 0) {  // level 0 holds 16 per-warp partials per tile (65 280 floats at 4K): 128-bit loads, four in flight
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll 4
+      for (int i = threadIdx.x; i < (n >> 2); i += 256) {
+        const float4 v = __ldg(s4 + i);
+        s += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+      }
+    } else {
+      for (int i = threadIdx.x; i < n; i += 256) s += (double)src[i];
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) sd[threadIdx.x >> 5] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
-    const double t = sd[0] + sd[1] + sd[2] + sd[3];
+    const double t = ((sd[0] + sd[1]) + (sd[2] + sd[3])) + ((sd[4] + sd[5]) + (sd[6] + sd[7]));
     const double q = (cc < p.temp_ch) ? pow(t / p.npix[bb], p.inv_beta) : 0.0;
     p.q_out[((long long)bb * 2 + cc) * p.q_stride + p.q_col0 + f] = (float)q;
   }

@@ -262,6 +262,23 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
   // ring position of the first slot (the position follows the frame's index in the clip), advanced as the slots go by
   int rp_first = (s_lo + p.ring_phase_ws) % RP;
 
+  auto slot_of = [&](int i) { return s_lo + i + (i > 0 ? dup : 0); };
+  // start staging the tile of iteration i (lb = i mod NLB)
+  auto issue_load = [&](int i, int lb) {
+    const int slot = slot_of(i);
+    if (LANDING) {
+      const int rb = i & 1;
+      const unsigned bar = bar0 + 8 * rb, dst = sRaw_u32 + rb * (TILE_FLOATS * 4);
+      mbar_expect_tx(bar, TILE_FLOATS * 4);
+      tma_load_3d(dst, &p.tmap_ws[0], bar, tx0 - 4, ty0 - 4, (int)p.slot_frame[0][slot]);
+      tma_load_3d(dst + PLANE * 4, &p.tmap_ws[1], bar, tx0 - 4, ty0 - 4, (int)p.slot_frame[1][slot]);
+    } else {
+      const unsigned bar = bar0 + 8 * lb;
+      mbar_expect_tx(bar, TILE_FLOATS * 4);
+      tma_load_3d(sL_u32 + lb * (TILE_FLOATS * 4), &p.tmap_ws[0], bar, 2 * (tx0 - 4), ty0 - 4, slot);
+    }
+  };
+
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -275,6 +292,9 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
       mbar_init(bar_row + 8 * i, NPW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // the first tiles are requested at once, before the tables below are loaded and the roles split: their latency is the
+    // first thing every CTA waits for
+    for (int i = 0; i < LY::AHEAD && i < n_iter; ++i) issue_load(i, i);
   }
   if (FOV && tid < 64) {
     // foveated: the Y and eccentricity axes of the CSF table as (x[j], 1 / (x[j+1] - x[j] + 1e-6)) pairs (interp.py:11-20)
@@ -330,25 +350,6 @@ __global__ void __launch_bounds__(NT, 1) band_ws_kernel(const __grid_constant__ 
     // row pass: column pair and first reduced row of this thread (ptid < ROW_THREADS)
     const int rw_cp = ptid % ROW_CP, rw_a0 = ROW_SEG * (ptid / ROW_CP);
 
-    auto slot_of = [&](int i) { return s_lo + i + (i > 0 ? dup : 0); };
-    // start staging the tile of iteration i (lb = i mod NLB)
-    auto issue_load = [&](int i, int lb) {
-      const int slot = slot_of(i);
-      if (LANDING) {
-        const int rb = i & 1;
-        const unsigned bar = bar0 + 8 * rb, dst = sRaw_u32 + rb * (TILE_FLOATS * 4);
-        mbar_expect_tx(bar, TILE_FLOATS * 4);
-        tma_load_3d(dst, &p.tmap_ws[0], bar, tx0 - 4, ty0 - 4, (int)p.slot_frame[0][slot]);
-        tma_load_3d(dst + PLANE * 4, &p.tmap_ws[1], bar, tx0 - 4, ty0 - 4, (int)p.slot_frame[1][slot]);
-      } else {
-        const unsigned bar = bar0 + 8 * lb;
-        mbar_expect_tx(bar, TILE_FLOATS * 4);
-        tma_load_3d(sL_u32 + lb * (TILE_FLOATS * 4), &p.tmap_ws[0], bar, 2 * (tx0 - 4), ty0 - 4, slot);
-      }
-    };
-    if (ptid == 0) {
-      for (int i = 0; i < LY::AHEAD && i < n_iter; ++i) issue_load(i, i);
-    }
     const bool halo_inside = (ty0 >= 4) && (ty0 + TH + 4 <= h) && (tx0 >= 4) && (tx0 + TW + 4 <= w);
 
     // ---- stage C of iteration j: reduce, columns -> ring position rp (+ next level out), then the temporal filters of the
