@@ -94,7 +94,10 @@ def initial_window(n_frames, filter_len, temp_padding):
     raise RuntimeError('Unknown padding method "{}"'.format(temp_padding))
 
 
-HALO_SLOT_COST = 0.6   # a temporal-halo frame (staged, converted, reduced, filtered into the rings, not scored) relative to a scored one
+# a temporal-halo frame (staged, converted, reduced, filtered into the rings, not scored) relative to a scored one.  Measured with
+# tools/halo_cost.py on the warp-specialised kernel (its producer warps do all of their work for a halo frame): 0.83-0.85; the
+# cuts at 0.85-1.0 are the same for 2 and 8 ranks of 64 frames each and 1 % faster than those at 0.6
+HALO_SLOT_COST = 0.9
 
 
 def frame_block(n_frames, rank, world_size, halo=0, first_halo=None, halo_cost=HALO_SLOT_COST):

@@ -12,7 +12,7 @@ from fovvideovdp_b200 import _native, config
 from fovvideovdp_b200 import build as native_build
 from fovvideovdp_b200.display_model import (fvvdp_display_geometry, fvvdp_display_photo_absolute, fvvdp_display_photo_eotf,
                                             fvvdp_display_photo_gog, fvvdp_display_photometry, geometry_is_stock, photometry_kernel_spec)
-from fovvideovdp_b200.fvvdp import frame_block, initial_window, pyramid_layout, temporal_filters
+from fovvideovdp_b200.fvvdp import HALO_SLOT_COST, frame_block, initial_window, pyramid_layout, temporal_filters
 from fovvideovdp_b200.video_source import fvvdp_video_source_array, reshuffle_dims
 from oracle import fvvdp_oracle as O
 
@@ -102,8 +102,8 @@ def test_frame_block_work_balanced():
             assert blocks[0][0] == 0 and blocks[-1][1] == N
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(G - 1)) and all(b > a for a, b in blocks)
             sizes = [b - a for a, b in blocks]
-            assert sizes[0] == max(sizes) and max(sizes) - min(sizes) <= 5
-            work = [sz + 0.6 * (1 if r == 0 else 7) for r, sz in enumerate(sizes)]
+            assert sizes[0] == max(sizes) and max(sizes) - min(sizes) <= 7
+            work = [sz + HALO_SLOT_COST * (1 if r == 0 else 7) for r, sz in enumerate(sizes)]
             if N >= 16 * G:
                 assert max(work) - min(work) <= 1.5
 
