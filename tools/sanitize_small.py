@@ -32,3 +32,26 @@ for name, ctor, (a, b), kw in runs:
     print(f"{name}: JOD {float(jod):.4f}")
 q, _ = m.pu_psnr(device=dev).predict(t, r, frames_per_second=30)
 print(f"PU21-PSNR {float(q):.3f} dB")
+# raw .yuv clips: per-frame conversion, block path, full-screen resize in every mode (up and down)
+import tempfile
+
+from fovvideovdp_b200 import video_source_yuv as vy
+from fovvideovdp_b200.synthetic import synth_yuv_pair
+
+for bits, css, cs, disp in ((10, "420", "2020", "standard_hdr_pq"), (8, "444", "709", "standard_fhd")):
+    yt, yr = synth_yuv_pair(5, 70, 150 if css == "444" else 152, bits, css)
+    with tempfile.TemporaryDirectory() as d:
+        props = dict(width=150 if css == "444" else 152, height=70, bit_depth=bits, color_space=cs, chroma_ss=css, fps=30)
+        ft, fr = os.path.join(d, vy.create_yuv_fname("t", props)), os.path.join(d, vy.create_yuv_fname("r", props))
+        yt.tofile(ft)
+        yr.tofile(fr)
+        fv = m.fvvdp(device=dev, display_name=disp)
+        jod, _ = fv.predict_video_source(vy.fvvdp_video_source_yuv_file(ft, fr, display_photometry=disp))
+        print(f"yuv {bits}b {css}: JOD {float(jod):.4f}")
+        for mode in ("nearest", "bilinear", "bicubic", "area"):
+            for res in ((211, 97), (90, 41)):
+                vs = vy.fvvdp_video_source_yuv_file(ft, fr, display_photometry=disp, full_screen_resize=mode, resize_resolution=res)
+                vs.get_test_frame(0, dev)
+                jod, _ = fv.predict_video_source(vs)
+                torch.cuda.synchronize()
+                print(f"yuv {bits}b {css} resize {mode} -> {res[0]}x{res[1]}: JOD {float(jod):.4f}")
