@@ -485,6 +485,62 @@ def yuv_frame_rgb(Y, u, v, bit_depth, chroma_ss, color_space):
     return np.clip(yuv @ M.T, _F(0), _F(1)).astype(_F)
 
 
+def resize_rgb(rgb, out_w, out_h, mode):
+    """Full-screen resize of a display-encoded (H,W,3) frame (fvvdp_video_source_yuv_file._get_frame, video_source_yuv.py:293-297):
+    torch.nn.functional.interpolate(size=(out_h, out_w), mode=mode), align_corners unset, then clip to [0,1].  Tap positions and
+    weights restate ATen's upsample kernels: scale = in / out (float32); nearest: min(floor(dst * scale), in - 1); bilinear:
+    src = max(scale (dst + 0.5) - 0.5, 0), second tap clamped; bicubic: src = scale (dst + 0.5) - 0.5, A = -0.75, taps clamped to
+    the frame; area: mean over [floor(i in / out), ceil((i + 1) in / out))."""
+    rgb = np.asarray(rgb, _F)
+    H, W = rgb.shape[:2]
+
+    def lin_taps(n_out, n_in):
+        src = np.maximum(_F(n_in) / _F(n_out) * (np.arange(n_out, dtype=_F) + _F(0.5)) - _F(0.5), _F(0))
+        i0 = src.astype(np.int64)
+        return i0, i0 + (i0 < n_in - 1), (src - i0.astype(_F)).astype(_F)
+
+    def cubic_taps(n_out, n_in):
+        src = _F(n_in) / _F(n_out) * (np.arange(n_out, dtype=_F) + _F(0.5)) - _F(0.5)
+        b = np.floor(src)
+        t = (src - b).astype(_F)
+        A = _F(-0.75)
+        c1 = lambda x: ((A + _F(2)) * x - (A + _F(3))) * x * x + _F(1)
+        c2 = lambda x: ((A * x - _F(5) * A) * x + _F(8) * A) * x - _F(4) * A
+        w = np.stack([c2(t + _F(1)), c1(t), c1(_F(1) - t), c2(_F(2) - t)], 1).astype(_F)
+        idx = np.clip(b.astype(np.int64)[:, None] + np.arange(-1, 3)[None, :], 0, n_in - 1)
+        return idx, w
+
+    if mode == "nearest":
+        iy = np.minimum(np.floor(np.arange(out_h, dtype=_F) * (_F(H) / _F(out_h))).astype(np.int64), H - 1)
+        ix = np.minimum(np.floor(np.arange(out_w, dtype=_F) * (_F(W) / _F(out_w))).astype(np.int64), W - 1)
+        out = rgb[iy][:, ix]
+    elif mode == "bilinear":
+        y0, y1, ly = lin_taps(out_h, H)
+        x0, x1, lx = lin_taps(out_w, W)
+        ly, lx = ly[:, None, None], lx[None, :, None]
+        top = (_F(1) - lx) * rgb[y0][:, x0] + lx * rgb[y0][:, x1]
+        bot = (_F(1) - lx) * rgb[y1][:, x0] + lx * rgb[y1][:, x1]
+        out = (_F(1) - ly) * top + ly * bot
+    elif mode == "bicubic":
+        iy, wy = cubic_taps(out_h, H)
+        ix, wx = cubic_taps(out_w, W)
+        rows = np.zeros((H, out_w, 3), _F)
+        for k in range(4):
+            rows += rgb[:, ix[:, k]] * wx[None, :, k, None]
+        out = np.zeros((out_h, out_w, 3), _F)
+        for k in range(4):
+            out += rows[iy[:, k]] * wy[:, k, None, None]
+    elif mode == "area":
+        ys = [((i * H) // out_h, -((-(i + 1) * H) // out_h)) for i in range(out_h)]
+        xs = [((i * W) // out_w, -((-(i + 1) * W) // out_w)) for i in range(out_w)]
+        cols = np.stack([rgb[:, a:b].sum(1, dtype=_F) for a, b in xs], 1)                      # (H, out_w, 3)
+        out = np.stack([cols[a:b].sum(0, dtype=_F) for a, b in ys], 0)
+        out = out / (np.array([b - a for a, b in ys], _F)[:, None, None] * np.array([b - a for a, b in xs], _F)[None, :, None])
+    else:
+        raise ValueError(f"unknown resize mode {mode}")
+    return np.clip(out, _F(0), _F(1)).astype(_F)
+
+
 # ----------------------------------------------------------------------------------------------
 # PU21-PSNR (pupsnr.py:52-79, utils.py:157-202)
 # ----------------------------------------------------------------------------------------------

@@ -292,6 +292,31 @@ def test_yuv_video_source(golden, case):
     _check_q(st["Q_per_ch"], g["Q_per_ch"])
 
 
+def test_yuv_full_screen_resize(golden):
+    """--full-screen-resize of raw .yuv clips (video_source_yuv.py:293-297): the oracle's restatement of the four interpolate
+    modes against the reference's frames, up- and down-scaling by non-integer factors, and one score."""
+    from fovvideovdp_b200.synthetic import synth_yuv_pair
+    g = golden("yuv_resize")
+    H, W, bits, fps = int(g["H"]), int(g["W"]), int(g["bits"]), float(g["fps"])
+    ny, nc = H * W, H * W // 4
+    t, r = synth_yuv_pair(4, H, W, bits, "420")
+    rgb = lambda f: O.yuv_frame_rgb(f[:ny].reshape(H, W), f[ny:ny + nc].reshape(H // 2, W // 2), f[ny + nc:].reshape(H // 2, W // 2), bits, "420", "2020")
+    frame = rgb(t[1])
+    for disp in ("standard_hdr_pq", "standard_4k"):
+        photo = O.photometry_from_preset(disp)
+        for mode in ("nearest", "bilinear", "bicubic", "area"):
+            for tag, res in (("up", (200, 130)), ("down", (116, 75))):
+                out = O.resize_rgb(frame, res[0], res[1], mode)
+                assert out.shape == (res[1], res[0], 3)
+                lum = O.frame_luminance(np.transpose(out, (2, 0, 1)), photo, O.metric_data()["rgb2y"]["BT.2020"])
+                np.testing.assert_allclose(lum, g[f"lum_{disp}_{mode}_{tag}"], rtol=3e-4, atol=1e-4, err_msg=f"{disp} {mode} {tag}")
+    rt = np.stack([O.resize_rgb(rgb(f), 200, 130, "bicubic") for f in t], 0)
+    rr = np.stack([O.resize_rgb(rgb(f), 200, 130, "bicubic") for f in r], 0)
+    jod, st = O.predict(rt, rr, dim_order="FHWC", frames_per_second=fps, display_name="standard_hdr_pq", color_space="BT.2020")
+    assert abs(jod - float(g["jod_standard_hdr_pq_bicubic_up"])) / float(g["jod_standard_hdr_pq_bicubic_up"]) < JOD_RTOL
+    _check_q(st["Q_per_ch"], g["Q_standard_hdr_pq_bicubic_up"])
+
+
 @pytest.mark.parametrize("hw", [(135, 240), (136, 241), (67, 97), (64, 64)])
 def test_odd_sizes(golden, hw):
     H, W = hw
