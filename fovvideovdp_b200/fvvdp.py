@@ -14,7 +14,6 @@ import ctypes
 import json
 import logging
 import math
-import os
 import threading
 
 import numpy as np
