@@ -24,7 +24,7 @@ from .display_model import (fvvdp_display_geometry, fvvdp_display_photometry, ge
 from .video_source import fvvdp_video_source_array, is_array_source
 
 _DTYPES = {torch.float32: _native.DTYPE_F32, torch.uint8: _native.DTYPE_U8, torch.int16: _native.DTYPE_U16}
-_WORKSPACE_BUDGET_BYTES = 16e9  # device memory a scoring context may take for its per-block pyramids
+_WORKSPACE_BUDGET_BYTES = 32e9  # device memory a scoring context may take for its per-block pyramids (4K: the full 96-frame block of the general kernels)
 _HOST_BLOCK_FRAMES = 8          # clips in host memory: frames per block, so that uploads and kernels overlap block by block
 
 
