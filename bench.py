@@ -21,6 +21,7 @@ and the per-band pooled energies are combined by one NCCL all-reduce before the 
   reference_cuda the unmodified reference on cuda:0 of the same B200 (TF32 off) on the same 64-frame tensors, with its JOD
   other_configs  BASELINE configs[1] (1080p, standard_fhd) and configs[4] (4K PQ, standard_hdr_pq, foveated, moving gaze)
   strong_256     BASELINE configs[3]: ONE 3840x2160x256-frame clip split over the N ranks (frame block + 7-frame halo each)
+  independent_pairs  (N > 1) one independent 64-frame pair per GPU instead of one sharded 64N-frame clip: no halo, no all-reduce
 
 `--impl reference` times the unmodified reference's torch-CPU path (all host threads) on bounded samples of the same
 workload and prints the same JSON line with "impl": "reference".
@@ -404,6 +405,20 @@ def run_ours(args, W, H):
         torch.cuda.empty_cache()
         t, r = synth_pair_torch(last - first + halo, H, W, dev, first_frame=first - halo)
 
+    # ---- N > 1: one independent 64-frame pair per GPU (pair-level data parallelism, what the CLI's batch front end does with a list
+    #      of pairs): no temporal halo, no all-reduce.  Beside `value` it shows how much of the sharded clip's loss is the halo.
+    pairs = None
+    if extras and world > 1:
+        fvp = m.fvvdp(display_name=args.display, device=dev)
+        Fp = min(F, int(t.shape[2]))
+        vsp = source(t[:, :, :Fp], r[:, :, :Fp], first_frame=0, total=Fp, metric=fvp)
+        for _ in range(3):
+            fvp.predict_video_source(vsp)
+        ms_p, jod_p = timed(fvp, vsp, args.steps, False)
+        pairs = {"value": world * Fp * args.steps / (ms_p / 1000.0), "unit": "frames/s", "ms_per_step": ms_p / args.steps,
+                 "what": "one independent %d-frame pair per GPU (no halo, no collective), max over ranks" % Fp, "jod_rank0": jod_p}
+        del vsp, fvp
+
     # ---- the other single-GPU configurations of BASELINE.json
     other = None
     if extras and world == 1:
@@ -487,7 +502,7 @@ def run_ours(args, W, H):
                        "frames_per_gpu": F, "frames_this_rank": last - first, "block_frames": info.get("block_frames"), "l2": "inputs exceed L2 (2 x %.1f GB per step)" % (F * H * W * 4 / 1e9),
                        "parallelism": f"frame blocks over {world} GPU(s), one all-reduce of the pooled energies" if world > 1 else "single GPU"},
             "jod": jod, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "sustained": sustained, "strong_256": strong, "other_configs": other, "reference_cuda": ref_cuda,
+            "sustained": sustained, "strong_256": strong, "independent_pairs": pairs, "other_configs": other, "reference_cuda": ref_cuda,
         }
         print(json.dumps(line))
     if world > 1:
