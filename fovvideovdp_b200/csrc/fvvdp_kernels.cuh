@@ -916,9 +916,9 @@ __global__ void __launch_bounds__(256) yuv_planes_kernel(const __grid_constant__
 // ------------------------------------------------------------------------------------------------
 // Full-screen resize of .yuv clips (fvvdp_video_source_yuv_file._get_frame, video_source_yuv.py:293-297: the display-encoded
 // R'G'B' frame goes through torch.nn.functional.interpolate(size=display resolution, mode=nearest|bilinear|bicubic|area),
-// align_corners unset, then .clip(0, 1), then the display model).  Here every output pixel gathers its taps straight from
-// the planar Y'CbCr frame -- each tap converted like yuv_kernel does -- so no R'G'B' frame at the clip's own resolution is
-// ever written.  Tap positions and weights follow ATen's upsample kernels: scale = in / out in float; nearest
+// align_corners unset, then .clip(0, 1), then the display model).  Here a CTA converts the source pixels its 32x8 output
+// pixels touch from the planar Y'CbCr frame into shared memory (like yuv_kernel does) and every output pixel gathers its taps
+// from there, so no R'G'B' frame at the clip's own resolution is ever written to HBM.  Tap positions and weights follow ATen's upsample kernels: scale = in / out in float; nearest
 // min(floor(dst * scale), in - 1); bilinear src = max(scale (dst + 0.5) - 0.5, 0); bicubic src = scale (dst + 0.5) - 0.5,
 // A = -0.75, taps clamped to the frame; area = adaptive average pooling over [floor(i in / out), ceil((i + 1) in / out)).
 // ------------------------------------------------------------------------------------------------
@@ -928,22 +928,23 @@ struct ResizeParams {
   float sx, sy;    // (float)in / out
 };
 
-// display-encoded, clipped R'G'B' of ONE source pixel
-__device__ __forceinline__ void yuv_rgb_at(const YuvParams& p, int x, int y, float (&rgb)[3]) {
+// display-encoded, clipped R'G'B' of ONE source pixel (py / pu / pv: the frame's planes; p: format, read where it lies -- the
+// kernel parameters -- so nothing of it is copied to the stack)
+__device__ __forceinline__ void yuv_rgb_at(const YuvParams& p, const void* py, const void* pu, const void* pv, int x, int y, float (&rgb)[3]) {
   float cb, cr;
   if (p.is420) {
     const float sy = fmaxf(0.5f * (float)y - 0.25f, 0.0f), sx = fmaxf(0.5f * (float)x - 0.25f, 0.0f);
     const int y0 = (int)sy, y1 = min(y0 + 1, p.ch - 1), x0 = (int)sx, x1 = min(x0 + 1, p.cw - 1);
     const float ly = sy - (float)y0, lx = sx - (float)x0;
-    cb = (1.0f - ly) * ((1.0f - lx) * yuv_chroma(p, p.u, y0, x0) + lx * yuv_chroma(p, p.u, y0, x1)) +
-         ly * ((1.0f - lx) * yuv_chroma(p, p.u, y1, x0) + lx * yuv_chroma(p, p.u, y1, x1));
-    cr = (1.0f - ly) * ((1.0f - lx) * yuv_chroma(p, p.v, y0, x0) + lx * yuv_chroma(p, p.v, y0, x1)) +
-         ly * ((1.0f - lx) * yuv_chroma(p, p.v, y1, x0) + lx * yuv_chroma(p, p.v, y1, x1));
+    cb = (1.0f - ly) * ((1.0f - lx) * yuv_chroma(p, pu, y0, x0) + lx * yuv_chroma(p, pu, y0, x1)) +
+         ly * ((1.0f - lx) * yuv_chroma(p, pu, y1, x0) + lx * yuv_chroma(p, pu, y1, x1));
+    cr = (1.0f - ly) * ((1.0f - lx) * yuv_chroma(p, pv, y0, x0) + lx * yuv_chroma(p, pv, y0, x1)) +
+         ly * ((1.0f - lx) * yuv_chroma(p, pv, y1, x0) + lx * yuv_chroma(p, pv, y1, x1));
   } else {
-    cb = yuv_chroma(p, p.u, y, x);
-    cr = yuv_chroma(p, p.v, y, x);
+    cb = yuv_chroma(p, pu, y, x);
+    cr = yuv_chroma(p, pv, y, x);
   }
-  const float Y = fminf(fmaxf(p.wy * yuv_sample(p.y, (long long)y * p.W + x, p.is16) - p.oy, 0.0f), 1.0f);
+  const float Y = fminf(fmaxf(p.wy * yuv_sample(py, (long long)y * p.W + x, p.is16) - p.oy, 0.0f), 1.0f);
 #pragma unroll
   for (int c = 0; c < 3; ++c) rgb[c] = fminf(fmaxf(p.m[3 * c] * Y + p.m[3 * c + 1] * cb + p.m[3 * c + 2] * cr, 0.0f), 1.0f);
 }
@@ -957,23 +958,59 @@ __device__ __forceinline__ void cubic_weights(float t, float (&w)[4]) {  // ATen
   w[3] = ((A * d - 5.0f * A) * d + 8.0f * A) * d - 4.0f * A;
 }
 
-// resized, clipped R'G'B' of output pixel (ox, oy)
-__device__ __noinline__ void yuv_resized_rgb(const YuvParams& p, const ResizeParams& r, int ox, int oy, float (&rgb)[3]) {
+// where the taps of a resized pixel come from: converted on the fly from the planar frame, or read from the CTA's patch of
+// already converted source pixels in shared memory ([3][RESIZE_PATCH], origin (x_lo, y_lo), row length pw)
+constexpr int RESIZE_PATCH = 3072;   // source pixels a CTA converts once for its 32x8 output pixels (36 kB); larger footprints
+                                     // (down-scaling by more than ~3.5) convert per tap
+struct YuvTapDirect {
+  const YuvParams& p;
+  const void *py, *pu, *pv;
+  __device__ __forceinline__ void operator()(int x, int y, float (&rgb)[3]) const { yuv_rgb_at(p, py, pu, pv, x, y, rgb); }
+};
+struct YuvTapPatch {
+  const float* s;
+  int x_lo, y_lo, pw;
+  __device__ __forceinline__ void operator()(int x, int y, float (&rgb)[3]) const {
+    const int i = (y - y_lo) * pw + (x - x_lo);
+    rgb[0] = s[i]; rgb[1] = s[RESIZE_PATCH + i]; rgb[2] = s[2 * RESIZE_PATCH + i];
+  }
+};
+
+// first and last source sample along one axis that the output samples o_first..o_last touch (the tap rules of resized_rgb)
+__device__ __forceinline__ void resize_src_range(int mode, float s, int n_in, int n_out, int o_first, int o_last, int& lo, int& hi) {
+  if (mode == FVVDP_B200_RESIZE_NEAREST) {
+    lo = min((int)floorf((float)o_first * s), n_in - 1);
+    hi = min((int)floorf((float)o_last * s), n_in - 1);
+  } else if (mode == FVVDP_B200_RESIZE_BILINEAR) {
+    lo = min((int)fmaxf(s * ((float)o_first + 0.5f) - 0.5f, 0.0f), n_in - 1);
+    hi = min(min((int)fmaxf(s * ((float)o_last + 0.5f) - 0.5f, 0.0f), n_in - 1) + 1, n_in - 1);
+  } else if (mode == FVVDP_B200_RESIZE_BICUBIC) {
+    lo = max(min((int)floorf(s * ((float)o_first + 0.5f) - 0.5f) - 1, n_in - 1), 0);
+    hi = max(min((int)floorf(s * ((float)o_last + 0.5f) - 0.5f) + 2, n_in - 1), 0);
+  } else {
+    lo = (int)(((long long)o_first * n_in) / n_out);
+    hi = (int)((((long long)o_last + 1) * n_in + n_out - 1) / n_out) - 1;
+  }
+}
+
+// resized, clipped R'G'B' of output pixel (ox, oy) of a W x H source
+template <class Tap>
+__device__ __forceinline__ void resized_rgb(const Tap& tap, int W, int H, const ResizeParams& r, int ox, int oy, float (&rgb)[3]) {
   float t[3];
   rgb[0] = rgb[1] = rgb[2] = 0.0f;
   if (r.mode == FVVDP_B200_RESIZE_NEAREST) {
-    yuv_rgb_at(p, min((int)floorf((float)ox * r.sx), p.W - 1), min((int)floorf((float)oy * r.sy), p.H - 1), rgb);
+    tap(min((int)floorf((float)ox * r.sx), W - 1), min((int)floorf((float)oy * r.sy), H - 1), rgb);
   } else if (r.mode == FVVDP_B200_RESIZE_BILINEAR) {
     const float fx = fmaxf(r.sx * ((float)ox + 0.5f) - 0.5f, 0.0f), fy = fmaxf(r.sy * ((float)oy + 0.5f) - 0.5f, 0.0f);
-    const int x0 = min((int)fx, p.W - 1), y0 = min((int)fy, p.H - 1), x1 = x0 + (x0 < p.W - 1 ? 1 : 0), y1 = y0 + (y0 < p.H - 1 ? 1 : 0);
+    const int x0 = min((int)fx, W - 1), y0 = min((int)fy, H - 1), x1 = x0 + (x0 < W - 1 ? 1 : 0), y1 = y0 + (y0 < H - 1 ? 1 : 0);
     const float lx = fx - (float)x0, ly = fy - (float)y0, kx = 1.0f - lx, ky = 1.0f - ly;
     float a[3], b[3];
-    yuv_rgb_at(p, x0, y0, a);
-    yuv_rgb_at(p, x1, y0, b);
+    tap(x0, y0, a);
+    tap(x1, y0, b);
 #pragma unroll
     for (int c = 0; c < 3; ++c) rgb[c] = ky * (kx * a[c] + lx * b[c]);
-    yuv_rgb_at(p, x0, y1, a);
-    yuv_rgb_at(p, x1, y1, b);
+    tap(x0, y1, a);
+    tap(x1, y1, b);
 #pragma unroll
     for (int c = 0; c < 3; ++c) rgb[c] += ly * (kx * a[c] + lx * b[c]);
   } else if (r.mode == FVVDP_B200_RESIZE_BICUBIC) {
@@ -983,11 +1020,11 @@ __device__ __noinline__ void yuv_resized_rgb(const YuvParams& p, const ResizePar
     cubic_weights(fx - bx, wx);
     cubic_weights(fy - by, wy);
     for (int j = 0; j < 4; ++j) {
-      const int yy = max(min((int)by - 1 + j, p.H - 1), 0);
+      const int yy = max(min((int)by - 1 + j, H - 1), 0);
       float row[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        yuv_rgb_at(p, max(min((int)bx - 1 + i, p.W - 1), 0), yy, t);
+        tap(max(min((int)bx - 1 + i, W - 1), 0), yy, t);
 #pragma unroll
         for (int c = 0; c < 3; ++c) row[c] += t[c] * wx[i];
       }
@@ -995,11 +1032,11 @@ __device__ __noinline__ void yuv_resized_rgb(const YuvParams& p, const ResizePar
       for (int c = 0; c < 3; ++c) rgb[c] += row[c] * wy[j];
     }
   } else {  // area
-    const int x0 = (int)(((long long)ox * p.W) / r.outW), x1 = (int)((((long long)ox + 1) * p.W + r.outW - 1) / r.outW);
-    const int y0 = (int)(((long long)oy * p.H) / r.outH), y1 = (int)((((long long)oy + 1) * p.H + r.outH - 1) / r.outH);
+    const int x0 = (int)(((long long)ox * W) / r.outW), x1 = (int)((((long long)ox + 1) * W + r.outW - 1) / r.outW);
+    const int y0 = (int)(((long long)oy * H) / r.outH), y1 = (int)((((long long)oy + 1) * H + r.outH - 1) / r.outH);
     for (int yy = y0; yy < y1; ++yy)
       for (int xx = x0; xx < x1; ++xx) {
-        yuv_rgb_at(p, xx, yy, t);
+        tap(xx, yy, t);
 #pragma unroll
         for (int c = 0; c < 3; ++c) rgb[c] += t[c];
       }
@@ -1011,13 +1048,39 @@ __device__ __noinline__ void yuv_resized_rgb(const YuvParams& p, const ResizePar
   for (int c = 0; c < 3; ++c) rgb[c] = fminf(fmaxf(rgb[c], 0.0f), 1.0f);
 }
 
+// The CTA's 32x8 output pixels of one frame: the source pixels they touch are converted ONCE into shared memory (a 2x up-scale
+// with bicubic taps converts 19x7 source pixels instead of 256 x 16 taps), then every output pixel gathers its taps from there.
+// All 256 threads call this (barriers inside); `inside` = this thread's pixel lies in the output frame.
+__device__ __forceinline__ void yuv_resized_tile(const YuvParams& p, const void* py, const void* pu, const void* pv, const ResizeParams& r, float* sP,
+                                                 int ox, int oy, bool inside, float (&rgb)[3]) {
+  const int ox0 = blockIdx.x * 32, oy0 = blockIdx.y * 8;
+  int x_lo, x_hi, y_lo, y_hi;
+  resize_src_range(r.mode, r.sx, p.W, r.outW, ox0, min(ox0 + 31, r.outW - 1), x_lo, x_hi);
+  resize_src_range(r.mode, r.sy, p.H, r.outH, oy0, min(oy0 + 7, r.outH - 1), y_lo, y_hi);
+  const int pw = x_hi - x_lo + 1, n = pw * (y_hi - y_lo + 1);
+  if (n <= RESIZE_PATCH) {  // uniform over the CTA
+    __syncthreads();        // the previous user of the patch is done with it
+    for (int i = threadIdx.x; i < n; i += 256) {
+      float t[3];
+      yuv_rgb_at(p, py, pu, pv, x_lo + i % pw, y_lo + i / pw, t);
+      sP[i] = t[0]; sP[RESIZE_PATCH + i] = t[1]; sP[2 * RESIZE_PATCH + i] = t[2];
+    }
+    __syncthreads();
+    if (inside) resized_rgb(YuvTapPatch{sP, x_lo, y_lo, pw}, p.W, p.H, r, ox, oy, rgb);
+  } else if (inside) {
+    resized_rgb(YuvTapDirect{p, py, pu, pv}, p.W, p.H, r, ox, oy, rgb);
+  }
+}
+
 // one frame: luminance [outH][outW] and / or resized R'G'B' [outH][outW][3]
 template <int KIND>
-__global__ void __launch_bounds__(256) yuv_resize_kernel(const YuvParams p, const ResizeParams r) {
+__global__ void __launch_bounds__(256) yuv_resize_kernel(const __grid_constant__ YuvParams p, const __grid_constant__ ResizeParams r) {
+  __shared__ float sP[3 * RESIZE_PATCH];
   const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x >= r.outW || y >= r.outH) return;
-  float rgb[3];
-  yuv_resized_rgb(p, r, x, y, rgb);
+  const bool inside = x < r.outW && y < r.outH;
+  float rgb[3] = {0.0f, 0.0f, 0.0f};
+  yuv_resized_tile(p, p.y, p.u, p.v, r, sP, x, y, inside, rgb);
+  if (!inside) return;
   const long long i = (long long)y * r.outW + x;
   if (p.rgb) { p.rgb[3 * i] = rgb[0]; p.rgb[3 * i + 1] = rgb[1]; p.rgb[3 * i + 2] = rgb[2]; }
   if (p.lum) p.lum[i] = yuv_eotf<KIND>(rgb[0], p) * p.rgb2y[0] + yuv_eotf<KIND>(rgb[1], p) * p.rgb2y[1] + yuv_eotf<KIND>(rgb[2], p) * p.rgb2y[2];
@@ -1025,23 +1088,21 @@ __global__ void __launch_bounds__(256) yuv_resize_kernel(const YuvParams p, cons
 
 // block version: the window slots of both streams into the (test, reference) planes level 0 stages (see yuv_planes_kernel)
 template <int KIND>
-__global__ void __launch_bounds__(256) yuv_resize_planes_kernel(const __grid_constant__ YuvBlockParams q, const ResizeParams r) {
+__global__ void __launch_bounds__(256) yuv_resize_planes_kernel(const __grid_constant__ YuvBlockParams q, const __grid_constant__ ResizeParams r) {
+  __shared__ float sP[3 * RESIZE_PATCH];
   const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), slot = blockIdx.z;
-  if (x >= r.outW || y >= r.outH) return;
+  const bool inside = x < r.outW && y < r.outH;
+  const YuvParams& p = q.f;
   float lum[2];
 #pragma unroll 1
   for (int st = 0; st < 2; ++st) {
-    YuvParams p = q.f;
     const char* base = reinterpret_cast<const char*>(q.frame[st][slot]);
     const int esz = p.is16 ? 2 : 1;
-    p.y = base;
-    p.u = base + q.y_elems * esz;
-    p.v = base + (q.y_elems + q.c_elems) * esz;
-    float rgb[3];
-    yuv_resized_rgb(p, r, x, y, rgb);
+    float rgb[3] = {0.0f, 0.0f, 0.0f};
+    yuv_resized_tile(p, base, base + q.y_elems * esz, base + (q.y_elems + q.c_elems) * esz, r, sP, x, y, inside, rgb);
     lum[st] = yuv_eotf<KIND>(rgb[0], p) * p.rgb2y[0] + yuv_eotf<KIND>(rgb[1], p) * p.rgb2y[1] + yuv_eotf<KIND>(rgb[2], p) * p.rgb2y[2];
   }
-  *reinterpret_cast<float2*>(q.out + slot * q.slot_stride + (long long)y * q.pitch + 2 * x) = make_float2(lum[0], lum[1]);
+  if (inside) *reinterpret_cast<float2*>(q.out + slot * q.slot_stride + (long long)y * q.pitch + 2 * x) = make_float2(lum[0], lum[1]);
 }
 
 // ------------------------------------------------------------------------------------------------

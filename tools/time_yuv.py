@@ -21,6 +21,8 @@ ap.add_argument("--fps", type=int, default=30)
 ap.add_argument("--bits", type=int, default=10)
 ap.add_argument("--dir", default="/dev/shm")
 ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--resize", default=None, help="full-screen resize mode (nearest, bilinear, bicubic, area) to --resize-to")
+ap.add_argument("--resize-to", default="3840x2160")
 a = ap.parse_args()
 W, H = [int(v) for v in a.size.split("x")]
 props = dict(width=W, height=H, bit_depth=a.bits, color_space="709", chroma_ss="420", fps=a.fps)
@@ -33,7 +35,8 @@ with open(ft, "wb") as f1, open(fr, "wb") as f2:
 try:
     dev = torch.device("cuda:0")
     fv = m.fvvdp(display_name="standard_4k", device=dev)
-    vs = m.fvvdp_video_source_yuv_file(ft, fr, display_photometry="standard_4k")
+    rw, rh = [int(v) for v in a.resize_to.split("x")]
+    vs = m.fvvdp_video_source_yuv_file(ft, fr, display_photometry="standard_4k", full_screen_resize=a.resize, resize_resolution=(rw, rh) if a.resize else None)
     for _ in range(2):
         jod, _ = fv.predict_video_source(vs)
         float(jod)
@@ -43,7 +46,7 @@ try:
         jod = float(jod)
     dt = (time.perf_counter() - t0) / a.steps
     nbytes = os.path.getsize(ft) + os.path.getsize(fr)
-    print(f".yuv pair {W}x{H}x{a.frames} {a.bits}-bit 4:2:0 from {a.dir}: {a.frames / dt:.1f} frames/s ({dt * 1e3:.1f} ms/clip, "
+    print(f".yuv pair {W}x{H}x{a.frames} {a.bits}-bit 4:2:0{(' ' + a.resize + ' -> ' + a.resize_to) if a.resize else ''} from {a.dir}: {a.frames / dt:.1f} frames/s ({dt * 1e3:.1f} ms/clip, "
           f"{nbytes / dt / 1e9:.1f} GB/s of file data), JOD={jod:.4f}, block={fv.last_run['block_frames']}, launches={fv.last_run['gpu_launches']}")
 finally:
     os.remove(ft)
