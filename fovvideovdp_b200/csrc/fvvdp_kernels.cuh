@@ -727,7 +727,7 @@ __device__ __forceinline__ float vis_scale(int i, float b_min, float b_max, floa
 }
 
 __global__ void __launch_bounds__(256) vis_apply_kernel(const float* __restrict__ recon, const float* __restrict__ y, long long n,
-                                                        const VisWork* __restrict__ ws, VisColorMap cm, float beta_jod, float jod_a_abs,
+                                                        const VisWork* __restrict__ ws, const __grid_constant__ VisColorMap cm, float beta_jod, float jod_a_abs,
                                                         __half* __restrict__ out) {
   const long long i = blockIdx.x * 256ll + threadIdx.x;
   if (i >= n) return;
