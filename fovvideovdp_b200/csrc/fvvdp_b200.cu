@@ -33,6 +33,8 @@ struct fvvdp_b200_ctx {
   CUtensorMap pmap_ws[FVVDP_B200_MAX_LEVELS];  //   the same tensors with the staged-tile box of the warp-specialised kernel
   int ws_th = ws::TH, ws_rp = ws::RP;                   //   its tile height / ring positions: ws (<= 8 taps) or ws16 (<= 16 taps)
   int ws_max_level = -1;                       // warp-specialised kernel on levels 0..ws_max_level (video, <= 8 taps, no debug outputs)
+  int ws_min_tiles = 0;                        // ... and, past level 0, only where a level has at least this many tiles (one per SM); the
+                                               //   small levels go to the fused kernel (2 CTAs per SM, time chunks).  0 with FVVDP_B200_WS_LEVELS
   int ntiles_used[FVVDP_B200_MAX_LEVELS] = {}; // tiles of the kernel that scored each level of the last block
   bool no_dup_skip = false;                    // A/B switch FVVDP_B200_NO_DUP_SKIP
   float* G[FVVDP_B200_MAX_LEVELS] = {};        // v1 (and taps): G[0] = R; [T][nch][h_l][w_l]
@@ -199,6 +201,7 @@ extern "C" int fvvdp_b200_create(const fvvdp_b200_config* cfg, int cuda_device, 
     if (cfg->filter_len > ws::RP + 1) { c->ws_th = ws16::TH; c->ws_rp = ws16::RP; }
     const char* wl = getenv("FVVDP_B200_WS_LEVELS");
     c->ws_max_level = ws_ok ? (wl ? atoi(wl) - 1 : (c->ws_rp == ws::RP ? 0 : FVVDP_B200_MAX_LEVELS)) : -1;
+    c->ws_min_tiles = wl ? 0 : 148;
     c->no_dup_skip = getenv("FVVDP_B200_NO_DUP_SKIP") != nullptr;
   }
   const int tile_w = c->fused ? fused::TW : TW, tile_h = c->fused ? fused::TH : TH;
@@ -632,8 +635,10 @@ static int score_block_impl(fvvdp_b200_ctx* ctx, const void* const* test_slots, 
       bp.h = ctx->lh[l]; bp.w = ctx->lw[l]; bp.h2 = ctx->lh[l + 1]; bp.w2 = ctx->lw[l + 1];
       bp.h_odd = bp.h & 1;
       // the warp-specialised kernel (one CTA of 24 warps per SM, 32x64 tiles) where it applies; it stages with TMA only
-      const bool use_ws = l <= ctx->ws_max_level && (l > 0 || l0_tma || !contig) && cfg.foveated != 2;  // custom geometry maps: fused kernel
-      const int tx = use_ws ? (bp.w + ws::TW - 1) / ws::TW : ctx->tiles_x[l], ty = use_ws ? (bp.h + ctx->ws_th - 1) / ctx->ws_th : ctx->tiles_y[l];
+      const int ws_tx = (bp.w + ws::TW - 1) / ws::TW, ws_ty = (bp.h + ctx->ws_th - 1) / ctx->ws_th;
+      const bool use_ws = l <= ctx->ws_max_level && (l > 0 || l0_tma || !contig) && cfg.foveated != 2 &&  // custom geometry maps: fused kernel
+                          (l == 0 || ws_tx * ws_ty >= ctx->ws_min_tiles);
+      const int tx = use_ws ? ws_tx : ctx->tiles_x[l], ty = use_ws ? ws_ty : ctx->tiles_y[l];
       const int tiles = tx * ty;
       bp.ntiles = tiles;
       ctx->ntiles_used[l] = use_ws ? tiles * 16 : tiles;
