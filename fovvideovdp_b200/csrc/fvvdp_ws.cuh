@@ -3,8 +3,8 @@
 // luminance frame, (test, reference) pairs, temporal rings on chip), restructured around the measured limiter of that
 // kernel -- latency at 16 warps per SM behind three CTA-wide barriers per frame:
 //
-//   * ONE CTA per SM owns a 32x64 tile (tile halo 1.41x instead of 1.69x) and runs 24 warps in two roles,
-//       producer warps (8):  wait for the TMA tile -> display EOTF -> luminance tile -> 5-tap reduce (rows, columns;
+//   * ONE CTA per SM owns a 32x64 tile (tile halo 1.41x instead of 1.69x) and runs 28 warps (24 on the pyramid levels) in two roles,
+//       producer warps (12 at level 0, 8 on the pyramid levels): wait for the TMA tile -> display EOTF -> luminance tile -> 5-tap reduce (rows, columns;
 //                            fvvdp_lpyr_dec.py:183-207) -> next pyramid level out -> ring of reduced tiles -> temporal
 //                            filters of the reduced tile (fvvdp.py:294-300),
 //       consumer warps (16): register ring of the tile's own pixels (one 2x2 quad per thread) -> temporal filters ->
@@ -12,7 +12,7 @@
 //                            (fvvdp_lpyr_dec.py:259-269, fvvdp.py:520-537, 574-607),
 //     decoupled by mbarriers (full / empty per luminance buffer): no CTA-wide barrier in the frame loop, the producers run
 //     up to two frames ahead, MUFU-heavy (EOTF, masking) and FMA-heavy (filters, stencils) warps are co-resident by
-//     construction.  `setmaxnreg` moves registers from the producers (48) to the consumers (96).
+//     construction.  `setmaxnreg` moves registers from the producers (40 / 48) to the consumers (96).
 //   * 7-position rings: the newest frame's sustained tap is 1e-36 (t = 0 in fvvdp.py:609-620) and the oldest frame's
 //     transient tap is exactly 0 (:626), so a window of fl taps needs fl-1 stored frames; the newest frame enters the
 //     transient filter from the registers it was just loaded into.
